@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Headline benchmark: replica-steps/s of the fused Langevin-splitting protocol.
+
+Workload (BASELINE.json configs[1]): 1-D double well
+(m = 10, beta = 1, gamma = 100, dt = 0.35), 1 048 576 replicas PER GPU, protocol_length 10
+(the reference's convention: 9 integrator steps per leg, forward + reverse leg), all six
+5-letter symmetric splittings over {O, R, V}; one bench "step" = one pass over the batch =
+6 fused protocol launches + the DeltaF_neq moment reduction (all-reduced over ranks).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events, max over
+ranks); `e2e` goes through the public API with pinned HOST buffers (H2D of the equilibrium
+cache, D2H of the works, every step); `roofline` holds the dominant kernel against the FP64
+FMA peak measured in the same run; `cpu_baseline` is the CPU oracle port on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SPLITTINGS = {"OVRVO": "O V R V O", "ORVRO": "O R V R O", "RVOVR": "R V O V R",
+              "ROVOR": "R O V O R", "VRORV": "V R O R V", "VOROV": "V O R O V"}
+SYSTEM, MASS, BETA, GAMMA, DT = "double_well", 10.0, 1.0, 100.0, 0.35
+N_CACHE = 1_000_000
+METRIC, UNIT = "replica-steps/sec (double well, six 5-letter splittings, F+R protocol)", "replica-steps/s"
+
+# Algorithmic flops per replica-step (DESIGN.md "flop convention"): FMA = 2, add/mul = 1,
+# transcendental = 1; Philox/Box-Muller work is NOT counted.  O: 9/DOF, V: 2/DOF, R: 2/DOF,
+# one force evaluation (10 flops: x^5, sin, 2 FMA) per distinct position visited.
+F_FORCE_DW = 10
+
+
+def flops_per_step(splitting):
+    toks = splitting.split()
+    n_evals = 0
+    valid = False  # force known at current position? steady state: last op of previous step
+    seq = toks + toks  # second pass sees the steady-state validity
+    for i, t in enumerate(seq):
+        if t == "R":
+            valid = False
+        elif t == "V":
+            if not valid and i >= len(toks):
+                n_evals += 1
+            valid = True
+    return 9 * toks.count("O") + 2 * toks.count("V") + 2 * toks.count("R") + F_FORCE_DW * n_evals
+
+
+def clocks_sampler_start():
+    f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    try:
+        p = subprocess.Popen(["nvidia-smi", "--query-gpu=index,clocks.sm,clocks.max.sm,power.draw,"
+                              "clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                              "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                             stdout=f, stderr=subprocess.DEVNULL)
+    except OSError:
+        return None, f.name
+    return p, f.name
+
+
+def clocks_sampler_stop(p, path, gpu_index=0):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if p is not None:
+        p.terminate()
+        try:
+            p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            p.kill()
+    try:
+        rows = [r.split(",") for r in open(path).read().strip().splitlines() if r.strip()]
+        rows = [[c.strip() for c in r] for r in rows if len(r) >= 9 and r[0].strip() == str(gpu_index)]
+        sm = [float(r[1]) for r in rows]
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(rows[0][2])
+            out["samples"] = len(sm)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for j, nm in enumerate(names):
+                if any(r[5 + j].lower().startswith("active") for r in rows):
+                    out["reasons"].append(nm)
+    except Exception:  # noqa: BLE001
+        pass
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+    return out
+
+
+def cpu_port_throughput(n_replicas, protocol_length, repeats=1):
+    """CPU oracle port (OpenMP over replicas, all host cores) on the same workload."""
+    from oracle import oracle
+    cache = oracle.sample_equilibrium_scalar(SYSTEM, 20000, 100, seed=1)
+    steps = protocol_length - 1
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(repeats):
+        for name, s in SPLITTINGS.items():
+            oracle.toy_protocol(SYSTEM, s, DT, GAMMA, n_replicas, steps, mass=MASS, kT=1.0 / BETA, seed=1, x_cache=cache)
+            total += n_replicas * 2 * steps
+    dt = time.perf_counter() - t0
+    return total / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure
+    Python (numba closures / OpenMM) and cannot travel to the GPU box, so this arm times the CPU
+    oracle port (oracle/lsi_oracle.c, pinned to the reference's closures by tests/golden) with all
+    host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n_sample = args.ref_replicas
+    cores = os.cpu_count()
+    for _ in range(args.warmup):
+        cpu_port_throughput(max(n_sample // 8, 1024), args.protocol_length)
+    t0 = time.perf_counter()
+    total = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_port_throughput(n_sample, args.protocol_length)
+        total += v * dt
+    wall = time.perf_counter() - t0
+    value = total / wall
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": workload_config(args, args.replicas),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d replicas x 6 splittings x 2 legs x %d steps per bench step" %
+                                   (n_sample, args.protocol_length - 1)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_per_gpu):
+    return {"workload": "C2 double well (BASELINE configs[1]): %d replicas/GPU x protocol_length %d "
+                        "(%d steps/leg, 2 legs) x 6 splittings" % (n_per_gpu, args.protocol_length,
+                                                                    args.protocol_length - 1),
+            "system": SYSTEM, "mass": MASS, "beta": BETA, "gamma": GAMMA, "dt": DT, "marginal": "configuration",
+            "splittings": list(SPLITTINGS), "replicas_per_gpu": n_per_gpu, "protocol_length": args.protocol_length,
+            "equilibrium_cache": N_CACHE, "l2": "flushed between timed steps (256 MiB memset, untimed)",
+            "parallelism": "replica shards, no data-path collective; 48-double moment all-reduce per step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicas", type=int, default=1 << 20, help="replicas per GPU")
+    ap.add_argument("--protocol-length", type=int, default=10)
+    ap.add_argument("--ref-replicas", type=int, default=1 << 17)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import integrator_benchmark_b200 as ib
+    from integrator_benchmark_b200 import _cabi, engine, parallel
+    import ctypes
+
+    rank, world, local_rank = parallel.init_process_group()
+    engine.require_cuda()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    n = args.replicas
+    steps_per_leg = args.protocol_length - 1
+    replica0 = rank * n  # global replica ids: rank r owns [r n, (r + 1) n)
+    seed = 0x5EED0002
+
+    from integrator_benchmark_b200.testsystems import double_well
+    system = engine.ScalarSystem(SYSTEM, MASS)
+    programs = {k: engine.Program(s, DT, GAMMA) for k, s in SPLITTINGS.items()}
+    # equilibrium cache (input of the path, generated once on the GPU, same on every rank)
+    x_cache_host = torch.from_numpy(double_well.collect_equilibrium_samples(N_CACHE, n_burn=300, seed=seed)).pin_memory()
+    x_cache = x_cache_host.to(dev)
+    bufs = {k: {} for k in SPLITTINGS}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    moments_all = torch.zeros(len(SPLITTINGS), 8, dtype=torch.float64, device=dev)
+
+    def one_pass(x_cache_dev):
+        for j, (k, prog) in enumerate(programs.items()):
+            res = engine.run_protocol(system, prog, n, steps_per_leg, 1.0 / BETA, marginal="configuration", seed=seed,
+                                      replica0=replica0, x_cache=x_cache_dev, out=bufs[k])
+            moments_all[j].copy_(res["moments"], non_blocking=True)
+        parallel.all_reduce_moments(moments_all)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_pass(x_cache)
+    barrier()
+
+    # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed (untimed) in between
+    sampler, path = clocks_sampler_start() if rank == 0 else (None, None)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()
+        ev[s][0].record()
+        one_pass(x_cache)
+        ev[s][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = clocks_sampler_stop(sampler, path, local_rank) if rank == 0 else None
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms = float(tmax.item())
+    steps_per_pass = len(SPLITTINGS) * n * 2 * steps_per_leg  # replica-steps per rank per bench step
+    value = world * steps_per_pass * args.steps / (dev_ms * 1e-3)
+
+    # ---- dominant kernel alone: events around each protocol launch (kernel + 1-block finalize)
+    k_ms = {k: 0.0 for k in SPLITTINGS}
+    for s in range(args.steps):
+        for j, (k, prog) in enumerate(programs.items()):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            engine.run_protocol(system, prog, n, steps_per_leg, 1.0 / BETA, marginal="configuration", seed=seed,
+                                replica0=replica0, x_cache=x_cache, out=bufs[k])
+            b.record()
+            b.synchronize()
+            k_ms[k] += a.elapsed_time(b)
+    kernel_ms = {k: v / args.steps for k, v in k_ms.items()}
+
+    # ---- measured FMA peaks (same run, burst = best of 5)
+    sink = torch.zeros(8, dtype=torch.float64, device=dev)
+    peaks = {}
+    for prec, name in [(0, "fp64"), (1, "fp32")]:
+        blocks, iters = 148 * 8, 20000 if prec == 0 else 40000
+        best = 1e30
+        for _ in range(6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _cabi.check(_cabi.lib.lsi_microbench_fma(prec, iters, blocks, ctypes.c_void_p(sink.data_ptr()),
+                                                     engine.current_stream_ptr()))
+            b.record()
+            b.synchronize()
+            best = min(best, a.elapsed_time(b))
+        peaks[name] = blocks * 256 * iters * 16 / (best * 1e-3) / 1e12  # TFLOP/s
+
+    # ---- end to end through the public API with HOST buffers (pinned), every step:
+    #      H2D of the equilibrium cache, 6 launches, D2H of both work arrays per splitting
+    w_host = torch.empty(len(SPLITTINGS), 2, n, dtype=torch.float64).pin_memory()
+    m_host = torch.empty(len(SPLITTINGS), 8, dtype=torch.float64).pin_memory()
+    x_dev = torch.empty_like(x_cache)
+
+    def e2e_pass():
+        x_dev.copy_(x_cache_host, non_blocking=True)
+        for j, (k, prog) in enumerate(programs.items()):
+            res = engine.run_protocol(system, prog, n, steps_per_leg, 1.0 / BETA, marginal="configuration", seed=seed,
+                                      replica0=replica0, x_cache=x_dev, out=bufs[k])
+            w_host[j].copy_(res["W"], non_blocking=True)
+            moments_all[j].copy_(res["moments"], non_blocking=True)
+        parallel.all_reduce_moments(moments_all)
+        m_host.copy_(moments_all, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return [ib.evaluation.estimate_from_moments(m_host[j].numpy()) for j in range(len(SPLITTINGS))]
+
+    for _ in range(3):
+        e2e_pass()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        estimates = e2e_pass()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * steps_per_pass * e2e_steps / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    alg_flops = sum(flops_per_step(s) * n * 2 * steps_per_leg for s in SPLITTINGS.values())
+    kernel_s = sum(kernel_ms.values()) * 1e-3
+    achieved = alg_flops / kernel_s / 1e12
+    hbm_bytes = len(SPLITTINGS) * n * (8 + 16)  # per pass: gather x0 (8 B) + write W_F, W_R (16 B) per replica
+    peaks_file = {}
+    try:
+        peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
+    roofline = {
+        "bound": "fp64_fma", "kernel": "toy_protocol_kernel<double_well>", "achieved": achieved, "peak": peaks["fp64"],
+        "unit": "TFLOP/s", "frac": achieved / peaks["fp64"], "traffic": None,
+        "peak_source": "lsi_microbench_fma fp64, best of 6, measured in this run (fp32: %.1f TFLOP/s)" % peaks["fp32"],
+        "note": "algorithmic flops exclude the Philox + Box-Muller noise generation that dominates issue slots "
+                "(n_O Gaussians per replica-step); see profiles/ for sm__inst_executed and pipe utilisation",
+        "replica_steps_per_s_kernel_only": len(SPLITTINGS) * n * 2 * steps_per_leg / kernel_s,
+        "kernel_ms_per_splitting": kernel_ms,
+        "flops_per_replica_step": {k: flops_per_step(s) for k, s in SPLITTINGS.items()},
+        "hbm": {"achieved": hbm_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback"},
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, secs = cpu_port_throughput(args.ref_replicas * 2, args.protocol_length)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": "%d replicas x 6 splittings (1 pass, %.1f s, OpenMP over replicas)" % (args.ref_replicas * 2, secs)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, n),
+        "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_cache_host.numel() * 8),
+                "d2h_bytes_per_step": int(w_host.numel() * 8 + m_host.numel() * 8), "steps": e2e_steps},
+        "gpu_launches": args.steps * len(SPLITTINGS) * 2,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "DeltaF_neq": {k: {"estimate": e[0], "stderr": float(np.sqrt(max(e[1], 0.0)))} for k, e in zip(SPLITTINGS, estimates)},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,213 @@
+/*
+ * lsi.h -- C ABI of the B200 Langevin-splitting ensemble engine (liblsi.so).
+ *
+ * This is the drop-in boundary for ONE hot path of choderalab/integrator-benchmark:
+ * running ensembles of independent replicas through a Langevin splitting string
+ * and reducing the shadow work into the near-equilibrium DeltaF_neq estimate.
+ * Every entry point names the reference interface it replaces (paths relative
+ * to the reference repository).  The reference is pure Python on top of
+ * OpenMM / numba; its "FFI" for this path is therefore a ctypes binding, shown
+ * in INTEGRATION.md and implemented in integrator-benchmark_b200/_cabi.py.
+ *
+ * Conventions
+ *   - plain C types only; device buffers are raw CUDA device pointers
+ *     (e.g. torch.Tensor.data_ptr()); `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream)
+ *   - every call returns LSI_OK or a negative code; lsi_last_error() returns a
+ *     thread-local message for the last failure on the calling thread
+ *   - handles are opaque, owned by the caller, freed with the matching
+ *     *_destroy; one handle must not be used from two threads at once
+ *   - no call synchronises the stream or the device unless stated
+ *   - there is NO CPU fallback: compute calls fail with LSI_ERR_CUDA when no
+ *     device is usable
+ *   - units are OpenMM's: nm, ps, amu, kJ/mol, K, e   (toy systems: reduced units)
+ */
+#ifndef LSI_H_
+#define LSI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSI_ABI_VERSION 1
+
+/* error codes; the Python shim maps them to the exception types the reference raises */
+#define LSI_OK 0
+#define LSI_ERR_ASSERT (-1)      /* AssertionError   (langevin.py:110-115, 289-302)          */
+#define LSI_ERR_VALUE (-2)       /* ValueError       (langevin.py:119-121)                   */
+#define LSI_ERR_ARG (-3)         /* bad argument at this boundary (NULL, negative size ...)  */
+#define LSI_ERR_CUDA (-4)        /* CUDA runtime failure or no device                        */
+#define LSI_ERR_UNSUPPORTED (-5) /* NotImplementedError (bookkeepers.py:252-253 etc.)        */
+#define LSI_ERR_KEY (-6)         /* KeyError         (langevin.py:300-302, no bare "V" entry) */
+
+/* substep kinds of a compiled program */
+#define LSI_OP_R 0
+#define LSI_OP_V 1
+#define LSI_OP_O 2
+
+/* scalar (1-DOF) potentials: low_dimensional_systems.py:52-57,132-136 */
+#define LSI_POT_QUARTIC 0     /* U = x^4                      */
+#define LSI_POT_DOUBLE_WELL 1 /* U = x^6 + 2 cos(5 (x + 1))   */
+#define LSI_POT_HARMONIC 2    /* U = params[0]/2 x^2  (analytic checks) */
+
+/* marginal of the reverse leg: bookkeepers.py:267-270 */
+#define LSI_MARGINAL_CONFIGURATION 0
+#define LSI_MARGINAL_FULL 1
+
+/* arithmetic */
+#define LSI_PRECISION_DOUBLE 0 /* everything fp64 (OpenMM Reference platform, numba toy path)            */
+#define LSI_PRECISION_MIXED 1  /* fp64 state and accumulators, fp32 force evaluation (OpenMM "mixed")     */
+
+/* RNG stream tags (counter word 3 = tag << 28 | unit); DESIGN.md "RNG layout" */
+#define LSI_TAG_O 0
+#define LSI_TAG_V0 1
+#define LSI_TAG_VMID 2
+#define LSI_TAG_X0 3
+#define LSI_TAG_BOOT 4
+#define LSI_TAG_EQ 5
+
+typedef struct lsi_program lsi_program;
+typedef struct lsi_system lsi_system;
+
+const char* lsi_last_error(void);
+int lsi_abi_version(void);
+/* number of usable CUDA devices (0 if none); never fails */
+int lsi_device_count(void);
+
+/* ------------------------------------------------------------------ splitting compiler
+ * Replaces LangevinSplittingIntegrator.__init__ (benchmark/integrators/langevin.py:47-121,
+ * 189-220): tokenises `splitting`, counts substeps, detects multi-timestep force groups,
+ * applies the reference's checks (same accept/reject set; LSI_ERR_ASSERT / LSI_ERR_VALUE
+ * where the reference raises AssertionError / ValueError) and bakes the O coefficients
+ * a = exp(-gamma h), b = sqrt(1 - exp(-2 gamma h)), h = dt / max(1, n_O).
+ * Deviation: a string whose only V token is a single V<g>
+ * (reference emits "dt / 0") is rejected with LSI_ERR_VALUE.
+ * Host only: makes no CUDA call. */
+int lsi_compile(const char* splitting, double dt_ps, double gamma_per_ps,
+                int measure_shadow_work, int measure_heat, int override_splitting_checks,
+                lsi_program** out);
+
+/* Replaces ContinuousLangevinSplittingIntegrator.__init__ (langevin.py:234-408):
+ * explicit (token, fraction) pairs; zero-length substeps are dropped (:406-408). */
+int lsi_compile_continuous(const char* const* tokens, const double* fractions, int n_tokens,
+                           double dt_ps, double gamma_per_ps,
+                           int measure_shadow_work, int measure_heat, int override_splitting_checks,
+                           lsi_program** out);
+
+int lsi_program_num_ops(const lsi_program* p);
+int lsi_program_is_mts(const lsi_program* p);
+int lsi_program_num_O(const lsi_program* p);
+/* op i: kind (LSI_OP_*), force group (-1 = all forces), fraction of dt, and for O the baked a, b */
+int lsi_program_get_op(const lsi_program* p, int i, int* kind, int* group, double* fraction,
+                       double* a, double* b);
+/* CustomIntegrator.getStepSize / setStepSize.  As in the reference changing the
+ * step size rescales R and V substeps only; a and b keep their construction-time values. */
+double lsi_program_get_step_size(const lsi_program* p);
+int lsi_program_set_step_size(lsi_program* p, double dt_ps);
+int lsi_program_flags(const lsi_program* p, int* measure_shadow_work, int* measure_heat);
+void lsi_program_destroy(lsi_program* p);
+
+/* ------------------------------------------------------------------ systems */
+/* 1-DOF toy systems (NumbaBookkeepingSimulator, low_dimensional_systems.py:52-76) */
+int lsi_system_create_scalar(int potential_kind, const double params[4], double mass, lsi_system** out);
+void lsi_system_destroy(lsi_system* s);
+int lsi_system_num_dof(const lsi_system* s);
+
+/* ------------------------------------------------------------------ protocol
+ * Replaces NumbaNonequilibriumSimulator.collect_protocol_samples
+ * (low_dimensional_systems.py:160-184) / NonequilibriumSimulator.collect_protocol_samples
+ * and accumulate_shadow_work (bookkeepers.py:184-295) for a whole ensemble in one launch.
+ *
+ * Per replica r (global id replica0 + r, which alone keys its RNG streams):
+ *   leg 0: x0 = x0[r] if given, else x_cache[index drawn from TAG_X0];
+ *          v0 = v0[r] if given, else sqrt(kT/m) * N(0,1) from TAG_V0
+ *   leg l>0: x continues; v is redrawn from TAG_VMID (configuration) or kept (full)
+ *   each leg applies the program n_steps times and yields
+ *          W = ((E_end - E_start) - (heat_end - heat_start)) / kT
+ * Outputs are leg-major so that warps write coalesced: W[leg * n_replicas + r].
+ * Optional outputs may be NULL.  Traces hold n_steps + 1 entries per leg (entry 0 is the
+ * leg start): trace[(leg * (n_steps + 1) + s) * n_replicas + r]; trace_w is cumulative
+ * work in kT (numba_integrators.py:59-61).
+ * `moments` (device, 8 doubles, optional) receives, over replicas whose works are all
+ * finite: {count, sum wF, sum wR, sum wF^2, sum wR^2, sum wF wR, count_nonfinite, 0};
+ * it needs n_legs == 2.  Scratch for the block partials is taken from `workspace`
+ * (device, at least lsi_protocol_workspace_bytes(n_replicas) bytes). */
+typedef struct lsi_protocol_args {
+    uint64_t seed;
+    uint64_t replica0;
+    int64_t n_replicas;
+    int32_t n_steps;
+    int32_t n_legs;
+    int32_t marginal;
+    int32_t precision;
+    double kT;
+    /* inputs (device) */
+    const double* x_cache;
+    int64_t n_cache;
+    const double* x0;
+    const double* v0;
+    /* outputs (device) */
+    double* W;
+    double* heat;
+    double* W_direct; /* needs a program compiled with measure_shadow_work */
+    double* x_final;
+    double* v_final;
+    double* trace_x;
+    double* trace_v;
+    double* trace_w;
+    double* moments;
+    void* workspace;
+    int64_t workspace_bytes;
+} lsi_protocol_args;
+
+int64_t lsi_protocol_workspace_bytes(int64_t n_replicas);
+int lsi_run_protocol(const lsi_system* sys, const lsi_program* prog, const lsi_protocol_args* args,
+                     void* stream);
+
+/* Equilibrium configurations for a scalar system: n independent random-walk Metropolis chains
+ * (proposal N(0,1), acceptance q(x')/q(x) > u as in metropolis_hastings_factory,
+ * numba_integrators.py:229-252), each started from N(0,1) and run for n_burn steps; the final
+ * states are written to x_out (device, n doubles).  Replaces the single 10^6-step chain the
+ * reference caches in {name}_samples.npy (low_dimensional_systems.py:95-98) by independent
+ * samples.  Chain c uses Philox replica id replica0 + c, tag LSI_TAG_EQ, draw = step:
+ * lane 0/1 -> proposal normal (Box-Muller cos branch), lane 2 -> acceptance uniform. */
+int lsi_sample_equilibrium_scalar(const lsi_system* sys, double kT, int64_t n, int32_t n_burn,
+                                  uint64_t seed, uint64_t replica0, double* x_out, void* stream);
+
+/* ------------------------------------------------------------------ estimators
+ * lsi_reduce_moments: the six sums estimate_nonequilibrium_free_energy needs
+ * (benchmark/evaluation/analysis.py:8-17) from device arrays W_F, W_R of length n; same
+ * layout of `moments` as above.  The host-side formula (np.var ddof=0, np.cov ddof=1) is
+ * lsi_neq_free_energy. */
+int lsi_reduce_moments(const double* W_F, const double* W_R, int64_t n, double* moments,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+/* host arithmetic on a (possibly all-reduced) moment vector; N_eff <= 0 means "len(W)" */
+int lsi_neq_free_energy(const double moments[8], double N_eff, double* DeltaF_neq, double* squared_uncertainty);
+
+/* Row-wise log-mean-exp(-w) with the reference's stderr heuristic
+ * (compare_near_eq_and_exact.py:62-97): for each row i over w[row_offsets[i] : row_offsets[i+1]]
+ *   estimate[i] = log(mean(exp(-w)))       (computed stably; equal in exact arithmetic)
+ *   stdev[i]    = std(exp(-w)) / (mean(exp(-w)) sqrt(n))     (ddof = 0)
+ * All pointers are device pointers; row_offsets has n_rows + 1 entries. */
+int lsi_reduce_logmeanexp(const double* w, const int64_t* row_offsets, int64_t n_rows,
+                          double* estimate, double* stdev, void* stream);
+
+/* Two-level bootstrap of the nested estimator (compare_near_eq_and_exact.py:293-320):
+ * for each of n_boot replicates resample rows, then each row's columns, uniformly with
+ * replacement (Philox, TAG_BOOT), and write mean over rows of log-mean-exp(-w) to out[b]. */
+int lsi_bootstrap_nested(const double* w, const int64_t* row_offsets, int64_t n_rows, int32_t n_boot,
+                         uint64_t seed, double* out, void* stream);
+
+/* ------------------------------------------------------------------ measurement helper
+ * FMA-pipe microbenchmark (no reference counterpart): blocks x 256 threads, each running
+ * iters x 8 independent fused multiply-adds in fp64 (LSI_PRECISION_DOUBLE) or fp32;
+ * flops = blocks * 256 * iters * 16.  bench.py times it with CUDA events to obtain the
+ * measured non-tensor FMA peak that the FMA-bound kernels are held against. */
+int lsi_microbench_fma(int precision, int64_t iters, int blocks, void* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSI_H_ */

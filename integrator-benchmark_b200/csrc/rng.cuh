@@ -1,0 +1,72 @@
+// Counter-based Philox-4x32-10 noise (Salmon et al., SC'11) and Box-Muller normals.
+//
+// Canonical layout (DESIGN.md "RNG layout"; the CPU oracle restates the same layout
+// independently so a run can be replayed exactly):
+//     key     = (seed_lo, seed_hi)
+//     counter = (replica_lo, replica_hi, draw, (tag << 28) | unit)
+// One block gives four 32-bit words -> two Box-Muller pairs -> four normals:
+//     (r0, r1) -> (n0, n1) = rad(r0) * (cos, sin)(2 pi u(r1)),   (r2, r3) -> (n2, n3)
+// with u(r) = (r + 0.5) * 2^-32, rad(r) = sqrt(-2 ln u(r)).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lsi {
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c2 = hi0 ^ c3 ^ k1;
+        c1 = lo1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ Philox4 philox_block(uint64_t seed, uint64_t replica, uint32_t draw, uint32_t tag,
+                                                uint32_t unit)
+{
+    return philox4x32_10((uint32_t)replica, (uint32_t)(replica >> 32), draw, (tag << 28) | unit,
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// fp64 Box-Muller on one pair of words
+__device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, double& n0, double& n1)
+{
+    const double u1 = ((double)ra + 0.5) * 2.3283064365386962890625e-10;
+    const double u2x2 = ((double)rb + 0.5) * 4.656612873077392578125e-10;  // 2 * u2
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(u2x2, &s, &c);
+    n0 = rad * c;
+    n1 = rad * s;
+}
+
+// fp32 Box-Muller (mixed precision paths); accurate logf / sincospif, not the fast intrinsics
+__device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& n0, float& n1)
+{
+    const float u1 = ((float)(ra >> 8) + 0.5f) * 5.9604644775390625e-8f;         // 24 bits -> (0, 1)
+    const float u2x2 = ((float)(rb >> 8) + 0.5f) * 1.1920928955078125e-7f;       // 2 * u2
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(u2x2, &s, &c);
+    n0 = rad * c;
+    n1 = rad * s;
+}
+
+__device__ __forceinline__ int64_t cache_index(uint64_t seed, uint64_t replica, int64_t n)
+{
+    const Philox4 r = philox_block(seed, replica, 0u, LSI_TAG_X0, 0u);
+    return (int64_t)(((uint64_t)r.x * (uint64_t)n) >> 32);
+}
+
+}  // namespace lsi

@@ -1,0 +1,370 @@
+// K1: fused whole-protocol kernel for 1-DOF toy systems (quartic, double well).
+//
+// One thread = one replica.  A thread carries x, v, the heat accumulator, the energy
+// bookkeeping and its Philox noise buffer in registers through the WHOLE protocol
+// (forward leg, midpoint velocity redraw, reverse leg) -- the loop the reference runs in
+// Python around numba closures (benchmark/testsystems/low_dimensional_systems.py:160-184,
+// benchmark/integrators/numba_integrators.py:17-225).  HBM traffic is one read of the start
+// state and one write of the two works per replica; block-level fp64 partial moments for
+// estimate_nonequilibrium_free_energy (benchmark/evaluation/analysis.py:8-17) leave with
+// the same launch.
+//
+// The compiled splitting program travels as a __grid_constant__ kernel parameter: the
+// substep loop reads kinds and coefficients from the constant bank with warp-uniform
+// indices, so the interpreter adds only a uniform branch per substep.
+#include <cuda_runtime.h>
+
+#include "lsi_internal.h"
+#include "rng.cuh"
+
+namespace {
+
+constexpr int kMaxOps = 160;  // fits the 4 KB parameter space; longer programs use the global copy
+constexpr int kThreads = 256;
+
+struct ToyProgram {
+    int n_ops;
+    int n_O;
+    const unsigned char* ext_kind;  // non-NULL when n_ops > kMaxOps
+    const double* ext_c0;
+    const double* ext_c1;
+    unsigned char kind[kMaxOps];
+    double c0[kMaxOps];  // R: h      V: h / m     O: a
+    double c1[kMaxOps];  //                        O: b * sqrt(kT / m)
+};
+
+struct ToyParams {
+    uint64_t seed, replica0;
+    int64_t n;
+    int n_steps, n_legs, marginal;
+    double mass, kT, inv_kT, sigma, p0;
+    const double* x_cache;
+    int64_t n_cache;
+    const double* x0;
+    const double* v0;
+    double *W, *heat, *W_direct, *x_final, *v_final, *trace_x, *trace_v, *trace_w;
+    double* partials;  // [gridDim.x][8]
+};
+
+template <int POT>
+__device__ __forceinline__ double potential(double x, double p0)
+{
+    if (POT == LSI_POT_QUARTIC) {
+        const double x2 = x * x;
+        return x2 * x2;
+    } else if (POT == LSI_POT_DOUBLE_WELL) {
+        const double x2 = x * x;
+        return x2 * x2 * x2 + 2.0 * cos(5.0 * (x + 1.0));
+    } else {
+        return 0.5 * p0 * x * x;
+    }
+}
+
+template <int POT>
+__device__ __forceinline__ double force(double x, double p0)
+{
+    if (POT == LSI_POT_QUARTIC) {
+        return -4.0 * x * x * x;
+    } else if (POT == LSI_POT_DOUBLE_WELL) {
+        const double x2 = x * x;
+        return -(6.0 * x2 * x2 * x - 10.0 * sin(5.0 * (x + 1.0)));
+    } else {
+        return -p0 * x;
+    }
+}
+
+// Replica-private scalar noise stream: normal number k lives in block k >> 2, lane k & 3.
+struct ScalarStream {
+    uint64_t seed, replica;
+    uint32_t tag, k;
+    double n0, n1, n2, n3;
+    __device__ __forceinline__ void init(uint64_t s, uint64_t r, uint32_t t)
+    {
+        seed = s; replica = r; tag = t; k = 0;
+        n0 = n1 = n2 = n3 = 0.0;
+    }
+    __device__ __forceinline__ double next()
+    {
+        const uint32_t lane = k & 3u;  // warp-uniform: every replica is at the same draw
+        if (lane == 0u) {
+            const lsi::Philox4 r = lsi::philox_block(seed, replica, k >> 2, tag, 0u);
+            lsi::box_muller(r.x, r.y, n0, n1);
+            lsi::box_muller(r.z, r.w, n2, n3);
+        }
+        ++k;
+        return lane == 0u ? n0 : (lane == 1u ? n1 : (lane == 2u ? n2 : n3));
+    }
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int POT, bool DIRECT, bool TRACE>
+__global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_constant__ ToyProgram prog,
+                                                                const __grid_constant__ ToyParams P)
+{
+    const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool active = r < P.n;
+    double wF = 0.0, wR = 0.0;
+    bool finite = true;
+
+    if (active) {
+        const uint64_t rid = P.replica0 + (uint64_t)r;
+        double x = P.x0 ? P.x0[r] : P.x_cache[lsi::cache_index(P.seed, rid, P.n_cache)];
+        double v;
+        if (P.v0) {
+            v = P.v0[r];
+        } else {
+            const lsi::Philox4 q = lsi::philox_block(P.seed, rid, 0u, LSI_TAG_V0, 0u);
+            double a, b;
+            lsi::box_muller(q.x, q.y, a, b);
+            v = P.sigma * a;
+        }
+        ScalarStream noise;
+        noise.init(P.seed, rid, LSI_TAG_O);
+        double heat = 0.0;
+        const double half_m = 0.5 * P.mass;
+        const int64_t T = (int64_t)P.n_steps + 1;
+
+        for (int leg = 0; leg < P.n_legs; ++leg) {
+            if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION) {
+                // normal number (leg - 1) of the TAG_VMID scalar stream
+                const uint32_t kk = (uint32_t)(leg - 1);
+                const lsi::Philox4 q = lsi::philox_block(P.seed, rid, kk >> 2, LSI_TAG_VMID, 0u);
+                double a, b;
+                if ((kk & 2u) == 0u) lsi::box_muller(q.x, q.y, a, b);
+                else lsi::box_muller(q.z, q.w, a, b);
+                v = P.sigma * ((kk & 1u) ? b : a);
+            }
+            const double E0 = potential<POT>(x, P.p0) + half_m * v * v;
+            const double Q0 = heat;
+            double wd = 0.0;
+            if (TRACE) {
+                const int64_t base = ((int64_t)leg * T) * P.n + r;
+                if (P.trace_x) P.trace_x[base] = x;
+                if (P.trace_v) P.trace_v[base] = v;
+                if (P.trace_w) P.trace_w[base] = 0.0;
+            }
+            for (int s = 0; s < P.n_steps; ++s) {
+                for (int i = 0; i < prog.n_ops; ++i) {
+                    const int kind = prog.ext_kind ? prog.ext_kind[i] : prog.kind[i];
+                    const double c0 = prog.ext_kind ? prog.ext_c0[i] : prog.c0[i];
+                    if (kind == LSI_OP_R) {
+                        if (DIRECT) {
+                            const double pe_old = potential<POT>(x, P.p0);
+                            x = x + c0 * v;
+                            wd += potential<POT>(x, P.p0) - pe_old;
+                        } else {
+                            x = x + c0 * v;
+                        }
+                    } else if (kind == LSI_OP_V) {
+                        const double v_old = v;
+                        v = v + c0 * force<POT>(x, P.p0);
+                        if (DIRECT) wd += half_m * v * v - half_m * v_old * v_old;
+                    } else {
+                        const double c1 = prog.ext_kind ? prog.ext_c1[i] : prog.c1[i];
+                        const double ke_old = half_m * v * v;
+                        v = c0 * v + c1 * noise.next();
+                        heat += half_m * v * v - ke_old;
+                    }
+                }
+                if (TRACE) {
+                    const int64_t idx = ((int64_t)leg * T + s + 1) * P.n + r;
+                    if (P.trace_x) P.trace_x[idx] = x;
+                    if (P.trace_v) P.trace_v[idx] = v;
+                    if (P.trace_w) {
+                        const double E = potential<POT>(x, P.p0) + half_m * v * v;
+                        P.trace_w[idx] = ((E - E0) - (heat - Q0)) * P.inv_kT;
+                    }
+                }
+            }
+            const double E1 = potential<POT>(x, P.p0) + half_m * v * v;
+            const double w = ((E1 - E0) - (heat - Q0)) * P.inv_kT;
+            P.W[(int64_t)leg * P.n + r] = w;
+            if (P.heat) P.heat[(int64_t)leg * P.n + r] = heat - Q0;
+            if (DIRECT && P.W_direct) P.W_direct[(int64_t)leg * P.n + r] = wd * P.inv_kT;
+            if (leg == 0) wF = w;
+            if (leg == 1) wR = w;
+            finite = finite && isfinite(w);
+        }
+        if (P.x_final) P.x_final[r] = x;
+        if (P.v_final) P.v_final[r] = v;
+    }
+
+    if (P.partials) {  // block-uniform
+        const bool ok = active && finite;
+        double m[7];
+        m[0] = ok ? 1.0 : 0.0;
+        m[1] = ok ? wF : 0.0;
+        m[2] = ok ? wR : 0.0;
+        m[3] = ok ? wF * wF : 0.0;
+        m[4] = ok ? wR * wR : 0.0;
+        m[5] = ok ? wF * wR : 0.0;
+        m[6] = (active && !finite) ? 1.0 : 0.0;
+        __shared__ double sh[kThreads / 32][7];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const double s = warp_sum(m[j]);
+            if (lane == 0) sh[warp][j] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            double s = 0.0;
+            if (threadIdx.x < 7)
+                for (int w = 0; w < kThreads / 32; ++w) s += sh[w][threadIdx.x];
+            P.partials[(int64_t)blockIdx.x * 8 + threadIdx.x] = s;
+        }
+    }
+}
+
+template <int POT>
+__global__ void __launch_bounds__(kThreads) toy_metropolis_kernel(uint64_t seed, uint64_t replica0, int64_t n,
+                                                                  int n_burn, double inv_kT, double p0,
+                                                                  double* __restrict__ x_out)
+{
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    const uint64_t rid = replica0 + (uint64_t)c;
+    double n0, n1;
+    {
+        const lsi::Philox4 q = lsi::philox_block(seed, rid, 0u, LSI_TAG_EQ, 0u);
+        lsi::box_muller(q.x, q.y, n0, n1);
+    }
+    double x = n0;
+    double u_x = potential<POT>(x, p0);
+    for (int i = 1; i <= n_burn; ++i) {
+        const lsi::Philox4 q = lsi::philox_block(seed, rid, (uint32_t)i, LSI_TAG_EQ, 0u);
+        lsi::box_muller(q.x, q.y, n0, n1);
+        const double accept_eps = ((double)q.z + 0.5) * 2.3283064365386962890625e-10;
+        const double x_prop = x + n0;
+        const double u_prop = potential<POT>(x_prop, p0);
+        if (exp(-(u_prop - u_x) * inv_kT) > accept_eps) { x = x_prop; u_x = u_prop; }
+    }
+    x_out[c] = x;
+}
+
+template <int POT>
+cudaError_t launch(const ToyProgram& prog, const ToyParams& P, bool direct, bool trace, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((P.n + kThreads - 1) / kThreads);
+    if (direct && trace) toy_protocol_kernel<POT, true, true><<<grid, kThreads, 0, st>>>(prog, P);
+    else if (direct) toy_protocol_kernel<POT, true, false><<<grid, kThreads, 0, st>>>(prog, P);
+    else if (trace) toy_protocol_kernel<POT, false, true><<<grid, kThreads, 0, st>>>(prog, P);
+    else toy_protocol_kernel<POT, false, false><<<grid, kThreads, 0, st>>>(prog, P);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+LSI_EXPORT int64_t lsi_protocol_workspace_bytes(int64_t n_replicas)
+{
+    if (n_replicas < 0) return 0;
+    const int64_t blocks = (n_replicas + 31) / 32;  // upper bound over all kernels' block sizes
+    return (blocks * 8 + 8) * (int64_t)sizeof(double) + 3 * 1024 * (int64_t)sizeof(double);
+}
+
+LSI_EXPORT int lsi_sample_equilibrium_scalar(const lsi_system* sys, double kT, int64_t n, int32_t n_burn,
+                                             uint64_t seed, uint64_t replica0, double* x_out, void* stream)
+{
+    if (!sys || sys->kind != LSI_SYS_SCALAR || !x_out || n < 0 || n_burn < 0 || !(kT > 0.0))
+        return lsi_set_error(LSI_ERR_ARG, "lsi_sample_equilibrium_scalar: bad argument");
+    if (n == 0) return LSI_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
+    switch (sys->potential) {
+    case LSI_POT_QUARTIC:
+        toy_metropolis_kernel<LSI_POT_QUARTIC><<<grid, kThreads, 0, st>>>(seed, replica0, n, n_burn, 1.0 / kT, sys->params[0], x_out);
+        break;
+    case LSI_POT_DOUBLE_WELL:
+        toy_metropolis_kernel<LSI_POT_DOUBLE_WELL><<<grid, kThreads, 0, st>>>(seed, replica0, n, n_burn, 1.0 / kT, sys->params[0], x_out);
+        break;
+    default:
+        toy_metropolis_kernel<LSI_POT_HARMONIC><<<grid, kThreads, 0, st>>>(seed, replica0, n, n_burn, 1.0 / kT, sys->params[0], x_out);
+        break;
+    }
+    LSI_CUDA_CHECK(cudaGetLastError());
+    return LSI_OK;
+}
+
+int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const lsi_protocol_args* a, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->n_replicas == 0) return LSI_OK;
+    if (!a->W) return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol: W output is required");
+    if (!a->x0 && !(a->x_cache && a->n_cache > 0))
+        return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol: need x0 or a non-empty x_cache");
+    if (a->precision != LSI_PRECISION_DOUBLE)
+        return lsi_set_error(LSI_ERR_UNSUPPORTED, "scalar systems run in fp64 only (the reference's numba path is fp64)");
+    if (a->W_direct && !prog->measure_shadow_work)
+        return lsi_set_error(LSI_ERR_ARG, "W_direct needs a program compiled with measure_shadow_work");
+    for (const lsi_op& op : prog->ops)
+        if (op.kind == LSI_OP_V && op.group >= 0)
+            return lsi_set_error(LSI_ERR_UNSUPPORTED, "scalar systems have a single force group; got V%d", op.group);
+
+    ToyProgram tp;
+    const int n_ops = (int)prog->ops.size();
+    tp.n_ops = n_ops;
+    tp.n_O = prog->n_O;
+    tp.ext_kind = nullptr; tp.ext_c0 = nullptr; tp.ext_c1 = nullptr;
+    const double sigma = sqrt(a->kT / sys->mass);
+    std::vector<unsigned char> kinds(n_ops);
+    std::vector<double> c0(n_ops), c1(n_ops);
+    for (int i = 0; i < n_ops; ++i) {
+        const lsi_op& op = prog->ops[i];
+        kinds[i] = (unsigned char)op.kind;
+        if (op.kind == LSI_OP_R) { c0[i] = prog->dt * op.fraction; c1[i] = 0.0; }
+        else if (op.kind == LSI_OP_V) { c0[i] = prog->dt * op.fraction / sys->mass; c1[i] = 0.0; }
+        else { c0[i] = op.a; c1[i] = op.b * sigma; }
+    }
+    void* ext = nullptr;
+    if (n_ops <= kMaxOps) {
+        for (int i = 0; i < n_ops; ++i) { tp.kind[i] = kinds[i]; tp.c0[i] = c0[i]; tp.c1[i] = c1[i]; }
+    } else {
+        // long multi-timestep strings: stage the program in device memory (stream-ordered)
+        const size_t nb = (size_t)n_ops * (2 * sizeof(double)) + (size_t)n_ops;
+        LSI_CUDA_CHECK(cudaMallocAsync(&ext, nb, st));
+        double* d0 = (double*)ext;
+        double* d1 = d0 + n_ops;
+        unsigned char* dk = (unsigned char*)(d1 + n_ops);
+        LSI_CUDA_CHECK(cudaMemcpyAsync(d0, c0.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
+        LSI_CUDA_CHECK(cudaMemcpyAsync(d1, c1.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
+        LSI_CUDA_CHECK(cudaMemcpyAsync(dk, kinds.data(), n_ops, cudaMemcpyHostToDevice, st));
+        LSI_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors die at return
+        tp.ext_c0 = d0; tp.ext_c1 = d1; tp.ext_kind = dk;
+    }
+
+    ToyParams P;
+    P.seed = a->seed; P.replica0 = a->replica0; P.n = a->n_replicas;
+    P.n_steps = a->n_steps; P.n_legs = a->n_legs; P.marginal = a->marginal;
+    P.mass = sys->mass; P.kT = a->kT; P.inv_kT = 1.0 / a->kT; P.sigma = sigma; P.p0 = sys->params[0];
+    P.x_cache = a->x_cache; P.n_cache = a->n_cache; P.x0 = a->x0; P.v0 = a->v0;
+    P.W = a->W; P.heat = a->heat; P.W_direct = a->W_direct; P.x_final = a->x_final; P.v_final = a->v_final;
+    P.trace_x = a->trace_x; P.trace_v = a->trace_v; P.trace_w = a->trace_w;
+    P.partials = nullptr;
+    const int64_t grid = (a->n_replicas + kThreads - 1) / kThreads;
+    if (a->moments) {
+        if (a->n_legs != 2) return lsi_set_error(LSI_ERR_ARG, "moments need n_legs == 2");
+        if (!a->workspace || a->workspace_bytes < lsi_protocol_workspace_bytes(a->n_replicas))
+            return lsi_set_error(LSI_ERR_ARG, "workspace too small: need %lld bytes",
+                                 (long long)lsi_protocol_workspace_bytes(a->n_replicas));
+        P.partials = (double*)a->workspace;
+    }
+    const bool direct = a->W_direct != nullptr;
+    const bool trace = a->trace_x || a->trace_v || a->trace_w;
+    cudaError_t err;
+    switch (sys->potential) {
+    case LSI_POT_QUARTIC: err = launch<LSI_POT_QUARTIC>(tp, P, direct, trace, st); break;
+    case LSI_POT_DOUBLE_WELL: err = launch<LSI_POT_DOUBLE_WELL>(tp, P, direct, trace, st); break;
+    case LSI_POT_HARMONIC: err = launch<LSI_POT_HARMONIC>(tp, P, direct, trace, st); break;
+    default: return lsi_set_error(LSI_ERR_ARG, "unknown potential kind %d", sys->potential);
+    }
+    if (err != cudaSuccess) return lsi_set_error(LSI_ERR_CUDA, "toy_protocol_kernel launch failed: %s", cudaGetErrorString(err));
+    if (ext) LSI_CUDA_CHECK(cudaFreeAsync(ext, st));
+    if (a->moments) return lsi_finalize_moments(P.partials, (int)grid, a->moments, stream);
+    return LSI_OK;
+}

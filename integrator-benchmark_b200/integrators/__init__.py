@@ -1,0 +1,2 @@
+from .numba_integrators import (aboba_factory, baoab_factory, orvro_factory, splitting_factory,  # noqa: F401
+                                vvvr_factory)

@@ -1,0 +1,66 @@
+"""Multi-GPU plumbing: one process per GPU, replicas sharded by contiguous global id ranges.
+
+Replicas never exchange state, so the data path has no collective.  The only exchange is at
+the end of a protocol: the 8-double moment vector (count, sums, cross sums) is all-reduced
+with `torch.distributed` (NCCL over NVLink on GPUs, gloo in CPU tests) and every rank then
+evaluates estimate_nonequilibrium_free_energy on the global vector
+(reference: benchmark/evaluation/analysis.py:8-17).  Because Philox streams are keyed by the
+GLOBAL replica id, the per-replica works are bit-identical for any number of ranks.
+"""
+import os
+
+
+def world():
+    """(rank, world_size, local_rank) from the torchrun environment (1 process if absent)."""
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)),
+            int(os.environ.get("LOCAL_RANK", 0)))
+
+
+def shard_range(n_total, rank, world_size):
+    """Contiguous shard [lo, hi) of `n_total` replicas owned by `rank` (sizes differ by at most 1)."""
+    base, rem = divmod(int(n_total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def init_process_group(backend=None):
+    import torch
+    import torch.distributed as dist
+    rank, world_size, local_rank = world()
+    if world_size > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    return rank, world_size, local_rank
+
+
+def all_reduce_moments(moments):
+    """Sum moment vectors (or a stack of them, shape (..., 8)) over ranks, in place."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(moments, op=dist.ReduceOp.SUM)
+    return moments
+
+
+def all_reduce_logmeanexp(row_max, row_sumexp, row_count):
+    """Merge per-rank partial (max, sum exp(-w - max), count) of the rows of a nested estimator
+    (reference: compare_near_eq_and_exact.py:95-97) into the global log-mean-exp per row."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        gmax = row_max.clone()
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
+        scaled = row_sumexp * torch.exp(row_max - gmax)
+        scaled = torch.where(torch.isfinite(row_max), scaled, torch.zeros_like(scaled))
+        dist.all_reduce(scaled, op=dist.ReduceOp.SUM)
+        cnt = row_count.clone()
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        return torch.log(scaled / cnt) + gmax
+    return torch.log(row_sumexp / row_count) + row_max

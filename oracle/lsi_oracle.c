@@ -186,12 +186,15 @@ ORC_API int orc_toy_protocol(int pot_kind, const double* pot_params, double mass
     const double sigma = sqrt(kT / mass);
     const int64_t T = (int64_t)n_steps + 1;
 
+#pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < n_replicas; ++r) {
         const uint64_t rid = replica0 + (uint64_t)r;
         double x = x0_in ? x0_in[r] : x_cache[cache_index(seed, rid, n_cache)];
         double v = v0_in ? v0_in[r] : sigma * scalar_normal(seed, rid, TAG_V0, 0u);
         double heat = 0.0;
         uint32_t step_global = 0;
+        uint32_t blk_id = 0xFFFFFFFFu; /* O-stream block held in nblk (one Philox call per 4 draws) */
+        double nblk[4] = {0, 0, 0, 0};
         for (int leg = 0; leg < n_legs; ++leg) {
             if (leg > 0 && marginal == 0) v = sigma * scalar_normal(seed, rid, TAG_VMID, (uint32_t)(leg - 1));
             const double E0 = toy_potential(pot_kind, pot_params, x) + 0.5 * mass * v * v;
@@ -215,7 +218,14 @@ ORC_API int orc_toy_protocol(int pot_kind, const double* pot_params, double mass
                         wd += 0.5 * mass * v * v - ke_old;
                     } else {
                         const double ke_old = 0.5 * mass * v * v;
-                        const double xi = scalar_normal(seed, rid, TAG_O, step_global * (uint32_t)n_O + ordinal);
+                        const uint32_t k = step_global * (uint32_t)n_O + ordinal;
+                        if ((k >> 2) != blk_id) {
+                            uint32_t rr[4];
+                            blk_id = k >> 2;
+                            philox_block(seed, rid, blk_id, TAG_O, 0u, rr);
+                            normals4(rr, nblk);
+                        }
+                        const double xi = nblk[k & 3u];
                         v = op_a[i] * v + op_b[i] * sigma * xi;
                         heat += 0.5 * mass * v * v - ke_old;
                         ++ordinal;
@@ -268,5 +278,31 @@ ORC_API int orc_toy_replay(int pot_kind, const double* pot_params, double mass, 
         trace_w[s + 1] = ((toy_potential(pot_kind, pot_params, x) + 0.5 * mass * v * v - E0) - heat) / kT;
     }
     *Q_out = heat;
+    return 0;
+}
+
+/* Independent random-walk Metropolis chains (numba_integrators.py:229-252 run n times for
+ * n_burn steps from N(0,1) starts): chain c -> replica id replica0 + c, TAG_EQ, draw = step;
+ * proposal = first Box-Muller normal of the block, acceptance uniform = (word 2 + 0.5) 2^-32. */
+ORC_API int orc_sample_equilibrium_scalar(int pot_kind, const double* pot_params, double kT, int64_t n,
+                                          int n_burn, uint64_t seed, uint64_t replica0, double* x_out)
+{
+    for (int64_t c = 0; c < n; ++c) {
+        uint32_t r[4];
+        double nn[4];
+        philox_block(seed, replica0 + (uint64_t)c, 0u, TAG_EQ, 0u, r);
+        normals4(r, nn);
+        double x = nn[0];
+        for (int i = 1; i <= n_burn; ++i) {
+            philox_block(seed, replica0 + (uint64_t)c, (uint32_t)i, TAG_EQ, 0u, r);
+            normals4(r, nn);
+            const double accept_eps = ((double)r[2] + 0.5) * TWO_M32;
+            const double x_prop = x + nn[0];
+            const double ratio = exp(-toy_potential(pot_kind, pot_params, x_prop) / kT) /
+                                 exp(-toy_potential(pot_kind, pot_params, x) / kT);
+            if (ratio > accept_eps) x = x_prop;
+        }
+        x_out[c] = x;
+    }
     return 0;
 }

@@ -133,3 +133,11 @@ def toy_replay(potential, splitting, dt, gamma, x0, v0, n_steps, xi, mass=10.0, 
                          ctypes.c_double(dt), ctypes.c_double(x0), ctypes.c_double(v0), int(n_steps),
                          _dp(xi), _dp(tx), _dp(tv), _dp(tw), ctypes.byref(Q))
     return tx, tv, Q.value, tw
+
+
+def sample_equilibrium_scalar(potential, n, n_burn, kT=1.0, seed=0, replica0=0, pot_params=(0.0,)):
+    p = (ctypes.c_double * 4)(*(list(pot_params) + [0.0] * 4)[:4])
+    out = np.zeros(int(n))
+    lib().orc_sample_equilibrium_scalar(POT[potential], p, ctypes.c_double(kT), ctypes.c_int64(n), int(n_burn),
+                                        ctypes.c_uint64(seed), ctypes.c_uint64(replica0), _dp(out))
+    return out

@@ -1,0 +1,94 @@
+"""Host-side checks that need no GPU: the C-ABI library loads, exports what include/lsi.h
+declares, and its splitting compiler agrees with the reference's own constructor."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+
+import integrator_benchmark_b200 as ib
+from integrator_benchmark_b200 import _cabi, engine
+from tests.test_oracle_golden import _expected_ops_from_recorded
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "lsi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lsi_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "liblsi.so does not export %s" % n
+    # and the ctypes binding covers each of them
+    assert set(names) == set(_cabi.EXPORTED)
+    assert _cabi.lib.lsi_abi_version() == 1
+
+
+def test_compiler_matches_reference_constructor(golden_dir):
+    data = json.load(open(os.path.join(golden_dir, "programs.json")))
+    n_ok = n_err = 0
+    for e in data["entries"]:
+        kw = e["kwargs"]
+        args = dict(dt=kw["timestep"], gamma=kw["collision_rate"],
+                    override_splitting_checks=kw.get("override_splitting_checks", False),
+                    measure_shadow_work=kw.get("measure_shadow_work", False),
+                    measure_heat=kw.get("measure_heat", True))
+        splitting = e["splitting"] if e["kind"] == "discrete" else [tuple(t) for t in e["splitting"]]
+        if "error" in e:
+            with pytest.raises(Exception) as ei:
+                engine.Program(splitting, **args)
+            assert type(ei.value).__name__ == e["error"], (splitting, kw)
+            n_err += 1
+            continue
+        expected = _expected_ops_from_recorded(e)
+        if any(op[0] == _cabi.OP_V and op[2] == float("inf") for op in expected):
+            with pytest.raises(ValueError):  # documented deviation (lsi.h)
+                engine.Program(splitting, **args)
+            continue
+        ops = engine.Program(splitting, **args).ops()
+        assert len(ops) == len(expected), (splitting, ops, expected)
+        for got, exp in zip(ops, expected):
+            assert got[0] == exp[0] and got[1] == exp[1], (splitting, got, exp)
+            if exp[2] is not None:
+                assert got[2] == pytest.approx(exp[2], rel=1e-15)
+            if exp[0] == _cabi.OP_O:
+                assert got[3] == pytest.approx(exp[3], rel=1e-14) and got[4] == pytest.approx(exp[4], rel=1e-14)
+        n_ok += 1
+    assert n_ok > 60 and n_err > 20
+
+
+def test_set_step_size_keeps_O_coefficients():
+    """setStepSize rescales R and V only (langevin.py:192-196 bakes a, b)."""
+    p = engine.Program("V R O R V", 0.001, 10.0)
+    before = p.ops()
+    p.dt = 0.004
+    assert p.dt == 0.004
+    assert p.ops() == before
+
+
+def test_no_gpu_means_loud_failure():
+    if _cabi.lib.lsi_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_cabi.LsiCudaError):
+        engine.require_cuda()
+    from integrator_benchmark_b200.evaluation import estimate_nonequilibrium_free_energy
+    with pytest.raises(_cabi.LsiCudaError):
+        estimate_nonequilibrium_free_energy([0.0, 1.0], [1.0, 0.0])
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "integrator-benchmark_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                for pat in (r"^\s*(from|import)\s+oracle", r"liblsi_oracle", r"oracle[/.]", r"#include.*oracle"):
+                    assert not re.search(pat, text, flags=re.M), (pat, os.path.join(dirpath, f))
+    assert ib.__version__

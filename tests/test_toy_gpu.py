@@ -1,0 +1,208 @@
+"""GPU parity of the toy path (configs C1/C2) against the CPU oracle and the golden fixtures.
+Everything here goes through the C ABI (integrator_benchmark_b200 -> ctypes -> liblsi.so)."""
+import json
+import os
+from functools import partial
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIX = ["O V R V O", "O R V R O", "R V O V R", "R O V O R", "V R O R V", "V O R O V"]
+# fp64 on both sides, same Philox words; libm vs CUDA log/sincos differ in the last ulp
+RTOL, ATOL = 1e-9, 1e-11
+
+
+@pytest.fixture(scope="module")
+def ib():
+    import integrator_benchmark_b200 as ib
+    ib.engine.require_cuda()
+    return ib
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _cache(orc, kind, n=4096, seed=11):
+    return orc.sample_equilibrium_scalar(kind, n, 60, seed=seed)
+
+
+@pytest.mark.parametrize("kind", ["quartic", "double_well"])
+@pytest.mark.parametrize("marginal", ["configuration", "full"])
+def test_protocol_matches_oracle(ib, orc, kind, marginal):
+    cache = _cache(orc, kind)
+    system = ib.engine.ScalarSystem(kind, 10.0)
+    for j, splitting in enumerate(SIX + ["V R R O R R V", "O V R R V O", "V R O O R V"]):
+        gamma, dt, n_steps, n = [100.0, 10.0, 0.5][j % 3], [0.1, 0.35, 0.6][j % 3], 10 + j, 3001
+        prog = ib.engine.Program(splitting, dt, gamma, measure_shadow_work=True)
+        res = ib.engine.run_protocol(system, prog, n, n_steps, 1.0, marginal=marginal, seed=77 + j, replica0=12345,
+                                     x_cache=cache, want_heat=True, want_direct=True, want_final=True, traces=True)
+        ref = orc.toy_protocol(kind, splitting, dt, gamma, n, n_steps, marginal=marginal, seed=77 + j,
+                               replica0=12345, x_cache=cache, traces=True, want_direct=True)
+        W = res["W"].cpu().numpy().T
+        np.testing.assert_allclose(W, ref["W"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(res["heat"].cpu().numpy().T, ref["Q"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(res["W_direct"].cpu().numpy().T, ref["Wdirect"], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(res["x_final"].cpu().numpy(), ref["x_final"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(res["v_final"].cpu().numpy(), ref["v_final"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(res["trace_x"].cpu().numpy().transpose(2, 0, 1), ref["trace_x"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(res["trace_w"].cpu().numpy().transpose(2, 0, 1), ref["trace_w"], rtol=RTOL, atol=ATOL)
+        # the two bookkeeping routes agree (reference tests/test_shadow_work.py:30-42)
+        np.testing.assert_allclose(res["W_direct"].cpu().numpy(), res["W"].cpu().numpy(), rtol=1e-7, atol=1e-9)
+        # fused moments == moments of the returned works
+        m = res["moments"].cpu().numpy()
+        wf, wr = ref["W"][:, 0], ref["W"][:, 1]
+        np.testing.assert_allclose(m[:6], [n, wf.sum(), wr.sum(), (wf * wf).sum(), (wr * wr).sum(), (wf * wr).sum()],
+                                   rtol=1e-9, atol=1e-9)
+        assert m[6] == 0
+
+
+def test_replica_ids_key_the_streams(ib, orc):
+    """bit-exact replica indexing: a shard [a, b) of a run equals the same slice of the full run."""
+    cache = _cache(orc, "double_well")
+    system = ib.engine.ScalarSystem("double_well", 10.0)
+    prog = ib.engine.Program("V R O R V", 0.4, 10.0)
+    full = ib.engine.run_protocol(system, prog, 5000, 9, 1.0, seed=5, replica0=0, x_cache=cache)["W"].cpu().numpy()
+    for lo, hi in [(0, 1250), (1250, 2500), (2500, 5000), (4999, 5000)]:
+        part = ib.engine.run_protocol(system, prog, hi - lo, 9, 1.0, seed=5, replica0=lo, x_cache=cache)["W"].cpu().numpy()
+        assert np.array_equal(part, full[:, lo:hi])
+    # cache indices are the oracle's, bit for bit
+    res = ib.engine.run_protocol(system, prog, 64, 0, 1.0, seed=5, replica0=1 << 33, x_cache=cache, want_final=True)
+    idx = [orc.cache_index(5, (1 << 33) + r, len(cache)) for r in range(64)]
+    assert np.array_equal(res["x_final"].cpu().numpy(), cache[idx])
+
+
+def test_edge_cases(ib, orc):
+    system = ib.engine.ScalarSystem("quartic", 10.0)
+    prog = ib.engine.Program("O V R V O", 0.25, 100.0)
+    cache = _cache(orc, "quartic", 16)
+    # zero steps: W = 0 exactly; single replica; n not a multiple of the block size
+    for n, steps in [(1, 0), (1, 1), (255, 3), (257, 3)]:
+        res = ib.engine.run_protocol(system, prog, n, steps, 1.0, seed=1, x_cache=cache)
+        ref = orc.toy_protocol("quartic", "O V R V O", 0.25, 100.0, n, steps, seed=1, x_cache=cache)
+        np.testing.assert_allclose(res["W"].cpu().numpy().T, ref["W"], rtol=RTOL, atol=ATOL)
+    # empty ensemble is a no-op
+    ib.engine.run_protocol(system, prog, 0, 5, 1.0, seed=1, x_cache=cache)
+    # unstable step: non-finite works are counted, not summed
+    bad = ib.engine.Program("O V R V O", 5.0, 1.0)
+    res = ib.engine.run_protocol(system, bad, 512, 200, 1.0, seed=1, x0=np.full(512, 3.0), v0=np.full(512, 1.0))
+    m = res["moments"].cpu().numpy()
+    assert m[6] == 512 and m[0] == 0
+    # a program longer than the in-parameter table takes the staged path
+    long_s = " ".join(["V"] + ["R"] * 100 + ["O"] + ["R"] * 100 + ["V"])
+    res = ib.engine.run_protocol(system, ib.engine.Program(long_s, 0.3, 5.0), 100, 4, 1.0, seed=3, x_cache=cache)
+    ref = orc.toy_protocol("quartic", long_s, 0.3, 5.0, 100, 4, seed=3, x_cache=cache)
+    np.testing.assert_allclose(res["W"].cpu().numpy().T, ref["W"], rtol=RTOL, atol=ATOL)
+    with pytest.raises(NotImplementedError):
+        ib.engine.run_protocol(system, prog, 4, 2, 1.0, marginal="momentum", x_cache=cache)
+    with pytest.raises(NotImplementedError):
+        ib.engine.run_protocol(system, ib.engine.Program("V0 V1 R O R V1 V0", 0.1, 1.0), 4, 2, 1.0, x_cache=cache)
+
+
+def test_factories_reproduce_reference_closures(ib, golden_dir):
+    """`f(x0, v0, n_steps, gamma, dt)` against the reference's own numba closures: the golden
+    noise is the Philox stream of (seed, replica), so pinning both reproduces it on the GPU."""
+    from integrator_benchmark_b200.integrators import numba_integrators as ni
+    from integrator_benchmark_b200.testsystems import double_well, quartic
+    z = np.load(os.path.join(golden_dir, "toy_numba.npz"))
+    meta = json.loads(str(z["meta"]))
+    systems = {"quartic": quartic, "double_well": double_well}
+    factories = {"vvvr": ni.vvvr_factory, "orvro": ni.orvro_factory, "baoab": ni.baoab_factory, "aboba": ni.aboba_factory}
+    for c in meta:
+        eq = systems[c["system"]]
+        f = factories[c["scheme"]](eq.potential, eq.force, eq.velocity_scale, eq.mass)
+        ib.set_seed(c["seed"], next_replica=c["replica"])
+        xs, vs, Q, W = f(c["x0"], c["v0"], c["n_steps"], c["gamma"], c["dt"])
+        k = c["key"]
+        assert xs.shape == (c["n_steps"],)
+        np.testing.assert_allclose(xs, z[k + "_xs"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(vs, z[k + "_vs"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(W, z[k + "_W"], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(Q, float(z[k + "_Q"]), rtol=1e-8, atol=1e-10)
+
+
+def test_equilibrium_sampler_matches_oracle_and_target(ib, orc):
+    from integrator_benchmark_b200.testsystems import double_well
+    ib.set_seed(99)
+    xs = double_well.collect_equilibrium_samples(n_samples=200000, n_burn=300)
+    ref = orc.sample_equilibrium_scalar("double_well", 2000, 300, seed=99)
+    np.testing.assert_allclose(xs[:2000], ref, rtol=1e-9, atol=1e-11)
+    # histogram against exp(-U)/Z, Z = 4.4848163908 (notebooks/1D figures, updated.ipynb:415)
+    edges = np.linspace(-1.6, 1.6, 33)
+    hist = np.histogram(xs, bins=edges)[0] / len(xs)
+    grid = np.linspace(-1.6, 1.6, 32 * 200 + 1)
+    pdf = np.exp(-(grid ** 6 + 2 * np.cos(5 * (grid + 1)))) / 4.4848163908
+    expect = np.array([np.trapezoid(pdf[i * 200:(i + 1) * 200 + 1], grid[i * 200:(i + 1) * 200 + 1]) for i in range(32)])
+    assert np.max(np.abs(hist - expect)) < 4e-3
+
+
+def test_collect_protocol_samples_api_and_estimate(ib, orc):
+    """reference call pattern (experiments/toy/quartic_kl_validation.py:26-70) end to end."""
+    from integrator_benchmark_b200.evaluation import estimate_nonequilibrium_free_energy
+    from integrator_benchmark_b200.integrators import baoab_factory, vvvr_factory
+    from integrator_benchmark_b200.testsystems import NumbaNonequilibriumSimulator, quartic
+    ib.set_seed(2024)
+    eq = quartic
+    n, length = 20000, 25
+    for factory, string in [(baoab_factory, "V R O O R V"), (vvvr_factory, "O V R R V O")]:
+        scheme = factory(eq.potential, eq.force, eq.velocity_scale, eq.mass)
+        sim = NumbaNonequilibriumSimulator(eq, partial(scheme, gamma=0.5, dt=0.9))
+        ib.set_seed(2024, next_replica=1000)
+        W_F, W_R, xv_F, xv_R = sim.collect_protocol_samples(n, length, "configuration")
+        assert W_F.shape == (n, length) and xv_F.shape == (n, length, 2) and W_F[:, 0].max() == 0.0
+        ref = orc.toy_protocol("quartic", string, 0.9, 0.5, n, length - 1, seed=2024, replica0=1000,
+                               x_cache=eq.x_samples, traces=True)
+        np.testing.assert_allclose(W_F, ref["trace_w"][:, 0], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(W_R, ref["trace_w"][:, 1], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(xv_R[:, :, 0], ref["trace_x"][:, 1], rtol=RTOL, atol=ATOL)
+        dF, var = estimate_nonequilibrium_free_energy(W_F[:, -1], W_R[:, -1])
+        dF_ref = 0.5 * (np.mean(ref["W"][:, 0]) - np.mean(ref["W"][:, 1]))
+        var_ref = (np.var(ref["W"][:, 0]) + np.var(ref["W"][:, 1]) - 2 * np.cov(ref["W"][:, 0], ref["W"][:, 1])[0, 1]) / (4 * n)
+        assert dF == pytest.approx(dF_ref, rel=1e-9, abs=1e-12)
+        assert var == pytest.approx(var_ref, rel=1e-7)
+        # traces=False gives the same final works
+        ib.set_seed(2024, next_replica=1000)
+        W_F2, W_R2, _, _ = sim.collect_protocol_samples(n, length, "configuration", traces=False)
+        assert np.array_equal(W_F2[:, -1], W_F[:, -1]) and np.array_equal(W_R2[:, -1], W_R[:, -1])
+        dF2, var2 = ib.evaluation.estimate_from_moments(sim.last_moments.cpu().numpy())
+        assert dF2 == pytest.approx(dF, rel=1e-9, abs=1e-12) and var2 == pytest.approx(var, rel=1e-7)
+
+
+def test_estimators_match_reference_fixtures(ib, golden_dir):
+    from integrator_benchmark_b200.evaluation import estimate_nonequilibrium_free_energy
+    cases = json.load(open(os.path.join(golden_dir, "estimators.json")))
+    n = 0
+    for c in cases:
+        if c["kind"] != "neq":
+            continue
+        dF, var = estimate_nonequilibrium_free_energy(np.array(c["W_F"]), np.array(c["W_R"]), c["N_eff"])
+        assert dF == pytest.approx(c["DeltaF"], rel=1e-10, abs=1e-14)
+        assert var == pytest.approx(c["sq_unc"], rel=1e-7, abs=1e-16)
+        n += 1
+    assert n >= 8
+
+
+def test_full_size_properties(ib):
+    """BASELINE config 2 size (1 048 576 replicas x 10): size-independent properties.
+    (a) time-reversal/Crooks sanity: for the harmonic well at tiny dt both works vanish;
+    (b) the heat + shadow work identity Delta E = W + Q holds per replica (test_shadow_work.py);
+    (c) <exp(-W_F)> = 1 (Jarzynski equality for shadow work started in equilibrium)."""
+    from integrator_benchmark_b200.testsystems import double_well
+    ib.set_seed(7)
+    n = 1 << 20
+    system = ib.engine.ScalarSystem("double_well", 10.0)
+    cache = double_well.x_samples_device()
+    prog = ib.engine.Program("V R O R V", 0.3, 100.0, measure_shadow_work=True)
+    res = ib.engine.run_protocol(system, prog, n, 9, 1.0, marginal="full", seed=7, x_cache=cache, want_direct=True)
+    W = res["W"]
+    assert bool(ib.engine.torch().isfinite(W).all())
+    assert float((res["W_direct"] - W).abs().max()) < 1e-9
+    jarz = float(ib.engine.torch().exp(-W[0]).mean())
+    assert abs(jarz - 1.0) < 5e-3
+    m = res["moments"].cpu().numpy()
+    assert m[0] == n and m[6] == 0
+    assert m[1] == pytest.approx(float(W[0].sum()), rel=1e-10)
