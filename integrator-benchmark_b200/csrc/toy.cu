@@ -1,7 +1,7 @@
-// K1: fused whole-protocol kernel for 1-DOF toy systems (quartic, double well).
+// K1: fused whole-protocol kernels for 1-DOF toy systems (quartic, double well).
 //
-// One thread = one replica.  A thread carries x, v, the heat accumulator, the energy
-// bookkeeping and its Philox noise buffer in registers through the WHOLE protocol
+// One thread = one replica.  A thread carries x, v, the cached force, the heat accumulator,
+// the energy bookkeeping and its Philox noise block in registers through the WHOLE protocol
 // (forward leg, midpoint velocity redraw, reverse leg) -- the loop the reference runs in
 // Python around numba closures (benchmark/testsystems/low_dimensional_systems.py:160-184,
 // benchmark/integrators/numba_integrators.py:17-225).  HBM traffic is one read of the start
@@ -9,9 +9,16 @@
 // estimate_nonequilibrium_free_energy (benchmark/evaluation/analysis.py:8-17) leave with
 // the same launch.
 //
-// The compiled splitting program travels as a __grid_constant__ kernel parameter: the
-// substep loop reads kinds and coefficients from the constant bank with warp-uniform
-// indices, so the interpreter adds only a uniform branch per substep.
+// Two code paths, same arithmetic:
+//   * toy_fused_kernel<POT, CODE, NOPS, NOISE32>: the splitting string is a template
+//     argument (2 bits per substep), so the substep sequence is unrolled at compile time,
+//     force evaluations are cached across substeps that do not move x (statically), the
+//     step loop is unrolled so that every noise lane is a fixed register, and substep
+//     lengths are four scalars.  Instantiated for the strings the reference uses.
+//   * toy_protocol_kernel: a substep interpreter for everything else (long multi-timestep
+//     strings, explicit-fraction programs, traces, direct shadow work).  The program
+//     travels as a __grid_constant__ parameter and is read from the constant bank with
+//     warp-uniform indices.
 #include <cuda_runtime.h>
 
 #include "lsi_internal.h"
@@ -25,7 +32,7 @@ constexpr int kThreads = 256;
 struct ToyProgram {
     int n_ops;
     int n_O;
-    const unsigned char* ext_kind;  // non-NULL when n_ops > kMaxOps
+    const unsigned char* ext_kind;  // used when n_ops > kMaxOps
     const double* ext_c0;
     const double* ext_c1;
     unsigned char kind[kMaxOps];
@@ -38,6 +45,7 @@ struct ToyParams {
     int64_t n;
     int n_steps, n_legs, marginal;
     double mass, kT, inv_kT, sigma, p0;
+    double hR, hV, oa, oc;  // fused path: R length, V length / m, O coefficients a and b * sigma
     const double* x_cache;
     int64_t n_cache;
     const double* x0;
@@ -73,28 +81,33 @@ __device__ __forceinline__ double force(double x, double p0)
     }
 }
 
-// Replica-private scalar noise stream: normal number k lives in block k >> 2, lane k & 3.
-struct ScalarStream {
-    uint64_t seed, replica;
-    uint32_t tag, k;
-    double n0, n1, n2, n3;
-    __device__ __forceinline__ void init(uint64_t s, uint64_t r, uint32_t t)
-    {
-        seed = s; replica = r; tag = t; k = 0;
-        n0 = n1 = n2 = n3 = 0.0;
+// four normals of one block of a replica's scalar stream
+template <bool NOISE32>
+__device__ __forceinline__ void normal_block(uint64_t seed, uint64_t replica, uint32_t draw, uint32_t tag,
+                                             double& n0, double& n1, double& n2, double& n3)
+{
+    const lsi::Philox4 r = lsi::philox_block(seed, replica, draw, tag, 0u);
+    if (NOISE32) {
+        float a, b, c, d;
+        lsi::box_muller(r.x, r.y, a, b);
+        lsi::box_muller(r.z, r.w, c, d);
+        n0 = (double)a; n1 = (double)b; n2 = (double)c; n3 = (double)d;
+    } else {
+        lsi::box_muller(r.x, r.y, n0, n1);
+        lsi::box_muller(r.z, r.w, n2, n3);
     }
-    __device__ __forceinline__ double next()
-    {
-        const uint32_t lane = k & 3u;  // warp-uniform: every replica is at the same draw
-        if (lane == 0u) {
-            const lsi::Philox4 r = lsi::philox_block(seed, replica, k >> 2, tag, 0u);
-            lsi::box_muller(r.x, r.y, n0, n1);
-            lsi::box_muller(r.z, r.w, n2, n3);
-        }
-        ++k;
-        return lane == 0u ? n0 : (lane == 1u ? n1 : (lane == 2u ? n2 : n3));
-    }
-};
+}
+
+// normal number k of a (replica, tag) scalar stream: block k >> 2, lane k & 3 (always fp64:
+// start and midpoint velocities are drawn once per leg)
+__device__ __forceinline__ double scalar_normal(uint64_t seed, uint64_t replica, uint32_t tag, uint32_t k)
+{
+    const lsi::Philox4 q = lsi::philox_block(seed, replica, k >> 2, tag, 0u);
+    double a, b;
+    if ((k & 2u) == 0u) lsi::box_muller(q.x, q.y, a, b);
+    else lsi::box_muller(q.z, q.w, a, b);
+    return (k & 1u) ? b : a;
+}
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -103,7 +116,181 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-template <int POT, bool DIRECT, bool TRACE>
+// block partial of the six moments (+ count of non-finite pairs) -> partials[blockIdx.x][8]
+__device__ __forceinline__ void block_moments(double* __restrict__ partials, bool active, bool finite,
+                                              double wF, double wR)
+{
+    const bool ok = active && finite;
+    double m[7];
+    m[0] = ok ? 1.0 : 0.0;
+    m[1] = ok ? wF : 0.0;
+    m[2] = ok ? wR : 0.0;
+    m[3] = ok ? wF * wF : 0.0;
+    m[4] = ok ? wR * wR : 0.0;
+    m[5] = ok ? wF * wR : 0.0;
+    m[6] = (active && !finite) ? 1.0 : 0.0;
+    __shared__ double sh[kThreads / 32][7];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const double s = warp_sum(m[j]);
+        if (lane == 0) sh[warp][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double s = 0.0;
+        if (threadIdx.x < 7)
+            for (int w = 0; w < kThreads / 32; ++w) s += sh[w][threadIdx.x];
+        partials[(int64_t)blockIdx.x * 8 + threadIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// compile-time splitting: CODE holds 2 bits per substep (substep i at bits 2i, 2i+1)
+constexpr int code_op(uint32_t code, int i) { return (int)((code >> (2 * i)) & 3u); }
+constexpr int code_count(uint32_t code, int nops, int kind)
+{
+    int n = 0;
+    for (int i = 0; i < nops; ++i) n += (code_op(code, i) == kind);
+    return n;
+}
+// is the force known at step entry in steady state?  yes iff a V follows the last R
+constexpr bool code_entry_valid(uint32_t code, int nops)
+{
+    bool valid = false;
+    for (int i = 0; i < nops; ++i) {
+        if (code_op(code, i) == LSI_OP_R) valid = false;
+        if (code_op(code, i) == LSI_OP_V) valid = true;
+    }
+    return valid;
+}
+
+template <int POT, uint32_t CODE, int NOPS>
+struct FusedStep {
+    // one application of the splitting; xi[] are this step's normals in substep order
+    template <int NO>
+    static __device__ __forceinline__ void run(double& x, double& v, double& f, double& heat, const ToyParams& P,
+                                               double half_m, const double (&xi)[NO])
+    {
+        bool valid = code_entry_valid(CODE, NOPS);  // folded at compile time after unrolling
+        int o = 0;
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i) {
+            constexpr uint32_t code = CODE;
+            const int kind = (int)((code >> (2 * i)) & 3u);
+            if (kind == LSI_OP_R) {
+                x = x + P.hR * v;
+                valid = false;
+            } else if (kind == LSI_OP_V) {
+                if (!valid) f = force<POT>(x, P.p0);
+                valid = true;
+                v = v + P.hV * f;
+            } else {
+                const double ke_old = half_m * v * v;
+                v = P.oa * v + P.oc * xi[o];
+                heat += half_m * v * v - ke_old;
+                ++o;
+            }
+        }
+    }
+};
+
+template <int POT, uint32_t CODE, int NOPS, bool NOISE32>
+__global__ void __launch_bounds__(kThreads) toy_fused_kernel(const __grid_constant__ ToyParams P)
+{
+    constexpr int NO = code_count(CODE, NOPS, LSI_OP_O);  // normals per step
+    constexpr int U = (NO == 0) ? 1 : ((4 % NO == 0) ? 4 / NO : 4);  // steps per noise refill when NO | 4
+    constexpr bool ALIGNED = (NO > 0) && (4 % NO == 0);
+
+    const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool active = r < P.n;
+    double wF = 0.0, wR = 0.0;
+    bool finite = true;
+
+    if (active) {
+        const uint64_t rid = P.replica0 + (uint64_t)r;
+        double x = P.x0 ? P.x0[r] : P.x_cache[lsi::cache_index(P.seed, rid, P.n_cache)];
+        double v = P.v0 ? P.v0[r] : P.sigma * scalar_normal(P.seed, rid, LSI_TAG_V0, 0u);
+        double heat = 0.0;
+        const double half_m = 0.5 * P.mass;
+        double f = code_entry_valid(CODE, NOPS) ? force<POT>(x, P.p0) : 0.0;
+
+        for (int leg = 0; leg < P.n_legs; ++leg) {
+            if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
+                v = P.sigma * scalar_normal(P.seed, rid, LSI_TAG_VMID, (uint32_t)(leg - 1));
+            const double E0 = potential<POT>(x, P.p0) + half_m * v * v;
+            const double Q0 = heat;
+            const uint32_t leg_base = (uint32_t)leg << 26;
+
+            if (ALIGNED) {
+                // one Philox block feeds exactly U steps: every lane index is a constant
+                int s = 0;
+                uint32_t blk = 0;
+                for (; s + U <= P.n_steps; s += U, ++blk) {
+                    double n[4];
+                    normal_block<NOISE32>(P.seed, rid, leg_base | blk, LSI_TAG_O, n[0], n[1], n[2], n[3]);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        double xi[NO > 0 ? NO : 1];
+#pragma unroll
+                        for (int o = 0; o < NO; ++o) xi[o] = n[u * NO + o];
+                        FusedStep<POT, CODE, NOPS>::run(x, v, f, heat, P, half_m, xi);
+                    }
+                }
+                if (s < P.n_steps) {
+                    double n[4];
+                    normal_block<NOISE32>(P.seed, rid, leg_base | blk, LSI_TAG_O, n[0], n[1], n[2], n[3]);
+#pragma unroll
+                    for (int u = 0; u < U - 1; ++u) {
+                        if (s + u < P.n_steps) {
+                            double xi[NO > 0 ? NO : 1];
+#pragma unroll
+                            for (int o = 0; o < NO; ++o) xi[o] = n[u * NO + o];
+                            FusedStep<POT, CODE, NOPS>::run(x, v, f, heat, P, half_m, xi);
+                        }
+                    }
+                }
+            } else {
+                // NO does not divide 4 (e.g. 3 O substeps): walk the stream lane by lane
+                uint32_t q = 0;
+                double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+                for (int s = 0; s < P.n_steps; ++s) {
+                    double xi[NO > 0 ? NO : 1];
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) {
+                        const uint32_t lane = q & 3u;
+                        if (lane == 0u) normal_block<NOISE32>(P.seed, rid, leg_base | (q >> 2), LSI_TAG_O, n0, n1, n2, n3);
+                        xi[o] = lane == 0u ? n0 : (lane == 1u ? n1 : (lane == 2u ? n2 : n3));
+                        ++q;
+                    }
+                    FusedStep<POT, CODE, NOPS>::run(x, v, f, heat, P, half_m, xi);
+                }
+            }
+
+            const double E1 = potential<POT>(x, P.p0) + half_m * v * v;
+            const double w = ((E1 - E0) - (heat - Q0)) * P.inv_kT;
+            P.W[(int64_t)leg * P.n + r] = w;
+            if (P.heat) P.heat[(int64_t)leg * P.n + r] = heat - Q0;
+            if (leg == 0) wF = w;
+            if (leg == 1) wR = w;
+            finite = finite && isfinite(w);
+        }
+        if (P.x_final) P.x_final[r] = x;
+        if (P.v_final) P.v_final[r] = v;
+    }
+    if (P.partials) block_moments(P.partials, active, finite, wF, wR);
+}
+
+// ------------------------------------------------------------------------------------------
+// interpreter
+template <bool EXT>
+struct ProgRead {
+    static __device__ __forceinline__ int kind(const ToyProgram& p, int i) { return EXT ? p.ext_kind[i] : p.kind[i]; }
+    static __device__ __forceinline__ double c0(const ToyProgram& p, int i) { return EXT ? p.ext_c0[i] : p.c0[i]; }
+    static __device__ __forceinline__ double c1(const ToyProgram& p, int i) { return EXT ? p.ext_c1[i] : p.c1[i]; }
+};
+
+template <int POT, bool DIRECT, bool TRACE, bool EXT, bool NOISE32>
 __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_constant__ ToyProgram prog,
                                                                 const __grid_constant__ ToyParams P)
 {
@@ -115,34 +302,20 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
     if (active) {
         const uint64_t rid = P.replica0 + (uint64_t)r;
         double x = P.x0 ? P.x0[r] : P.x_cache[lsi::cache_index(P.seed, rid, P.n_cache)];
-        double v;
-        if (P.v0) {
-            v = P.v0[r];
-        } else {
-            const lsi::Philox4 q = lsi::philox_block(P.seed, rid, 0u, LSI_TAG_V0, 0u);
-            double a, b;
-            lsi::box_muller(q.x, q.y, a, b);
-            v = P.sigma * a;
-        }
-        ScalarStream noise;
-        noise.init(P.seed, rid, LSI_TAG_O);
+        double v = P.v0 ? P.v0[r] : P.sigma * scalar_normal(P.seed, rid, LSI_TAG_V0, 0u);
         double heat = 0.0;
         const double half_m = 0.5 * P.mass;
         const int64_t T = (int64_t)P.n_steps + 1;
 
         for (int leg = 0; leg < P.n_legs; ++leg) {
-            if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION) {
-                // normal number (leg - 1) of the TAG_VMID scalar stream
-                const uint32_t kk = (uint32_t)(leg - 1);
-                const lsi::Philox4 q = lsi::philox_block(P.seed, rid, kk >> 2, LSI_TAG_VMID, 0u);
-                double a, b;
-                if ((kk & 2u) == 0u) lsi::box_muller(q.x, q.y, a, b);
-                else lsi::box_muller(q.z, q.w, a, b);
-                v = P.sigma * ((kk & 1u) ? b : a);
-            }
+            if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
+                v = P.sigma * scalar_normal(P.seed, rid, LSI_TAG_VMID, (uint32_t)(leg - 1));
             const double E0 = potential<POT>(x, P.p0) + half_m * v * v;
             const double Q0 = heat;
+            const uint32_t leg_base = (uint32_t)leg << 26;
             double wd = 0.0;
+            uint32_t q = 0;  // O draws so far in this leg (warp-uniform)
+            double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
             if (TRACE) {
                 const int64_t base = ((int64_t)leg * T) * P.n + r;
                 if (P.trace_x) P.trace_x[base] = x;
@@ -151,8 +324,8 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
             }
             for (int s = 0; s < P.n_steps; ++s) {
                 for (int i = 0; i < prog.n_ops; ++i) {
-                    const int kind = prog.ext_kind ? prog.ext_kind[i] : prog.kind[i];
-                    const double c0 = prog.ext_kind ? prog.ext_c0[i] : prog.c0[i];
+                    const int kind = ProgRead<EXT>::kind(prog, i);
+                    const double c0 = ProgRead<EXT>::c0(prog, i);
                     if (kind == LSI_OP_R) {
                         if (DIRECT) {
                             const double pe_old = potential<POT>(x, P.p0);
@@ -166,9 +339,13 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
                         v = v + c0 * force<POT>(x, P.p0);
                         if (DIRECT) wd += half_m * v * v - half_m * v_old * v_old;
                     } else {
-                        const double c1 = prog.ext_kind ? prog.ext_c1[i] : prog.c1[i];
+                        const double c1 = ProgRead<EXT>::c1(prog, i);
+                        const uint32_t lane = q & 3u;
+                        if (lane == 0u) normal_block<NOISE32>(P.seed, rid, leg_base | (q >> 2), LSI_TAG_O, n0, n1, n2, n3);
+                        ++q;
+                        const double xi = lane == 0u ? n0 : (lane == 1u ? n1 : (lane == 2u ? n2 : n3));
                         const double ke_old = half_m * v * v;
-                        v = c0 * v + c1 * noise.next();
+                        v = c0 * v + c1 * xi;
                         heat += half_m * v * v - ke_old;
                     }
                 }
@@ -194,32 +371,7 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
         if (P.x_final) P.x_final[r] = x;
         if (P.v_final) P.v_final[r] = v;
     }
-
-    if (P.partials) {  // block-uniform
-        const bool ok = active && finite;
-        double m[7];
-        m[0] = ok ? 1.0 : 0.0;
-        m[1] = ok ? wF : 0.0;
-        m[2] = ok ? wR : 0.0;
-        m[3] = ok ? wF * wF : 0.0;
-        m[4] = ok ? wR * wR : 0.0;
-        m[5] = ok ? wF * wR : 0.0;
-        m[6] = (active && !finite) ? 1.0 : 0.0;
-        __shared__ double sh[kThreads / 32][7];
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            const double s = warp_sum(m[j]);
-            if (lane == 0) sh[warp][j] = s;
-        }
-        __syncthreads();
-        if (threadIdx.x < 8) {
-            double s = 0.0;
-            if (threadIdx.x < 7)
-                for (int w = 0; w < kThreads / 32; ++w) s += sh[w][threadIdx.x];
-            P.partials[(int64_t)blockIdx.x * 8 + threadIdx.x] = s;
-        }
-    }
+    if (P.partials) block_moments(P.partials, active, finite, wF, wR);
 }
 
 template <int POT>
@@ -248,15 +400,82 @@ __global__ void __launch_bounds__(kThreads) toy_metropolis_kernel(uint64_t seed,
     x_out[c] = x;
 }
 
-template <int POT>
-cudaError_t launch(const ToyProgram& prog, const ToyParams& P, bool direct, bool trace, cudaStream_t st)
+// ---- dispatch --------------------------------------------------------------------------
+template <int POT, bool EXT, bool NOISE32>
+cudaError_t launch_interp3(const ToyProgram& prog, const ToyParams& P, bool direct, bool trace, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((P.n + kThreads - 1) / kThreads);
-    if (direct && trace) toy_protocol_kernel<POT, true, true><<<grid, kThreads, 0, st>>>(prog, P);
-    else if (direct) toy_protocol_kernel<POT, true, false><<<grid, kThreads, 0, st>>>(prog, P);
-    else if (trace) toy_protocol_kernel<POT, false, true><<<grid, kThreads, 0, st>>>(prog, P);
-    else toy_protocol_kernel<POT, false, false><<<grid, kThreads, 0, st>>>(prog, P);
+    if (direct && trace) toy_protocol_kernel<POT, true, true, EXT, NOISE32><<<grid, kThreads, 0, st>>>(prog, P);
+    else if (direct) toy_protocol_kernel<POT, true, false, EXT, NOISE32><<<grid, kThreads, 0, st>>>(prog, P);
+    else if (trace) toy_protocol_kernel<POT, false, true, EXT, NOISE32><<<grid, kThreads, 0, st>>>(prog, P);
+    else toy_protocol_kernel<POT, false, false, EXT, NOISE32><<<grid, kThreads, 0, st>>>(prog, P);
     return cudaGetLastError();
+}
+
+template <int POT>
+cudaError_t launch_interp(const ToyProgram& prog, const ToyParams& P, bool direct, bool trace, bool ext,
+                          bool noise32, cudaStream_t st)
+{
+    if (ext) return noise32 ? launch_interp3<POT, true, true>(prog, P, direct, trace, st)
+                            : launch_interp3<POT, true, false>(prog, P, direct, trace, st);
+    return noise32 ? launch_interp3<POT, false, true>(prog, P, direct, trace, st)
+                   : launch_interp3<POT, false, false>(prog, P, direct, trace, st);
+}
+
+constexpr uint32_t pack(const char* s)
+{
+    uint32_t code = 0;
+    int i = 0;
+    for (; *s; ++s) {
+        const uint32_t k = (*s == 'R') ? LSI_OP_R : (*s == 'V') ? LSI_OP_V : LSI_OP_O;
+        code |= k << (2 * i);
+        ++i;
+    }
+    return code;
+}
+constexpr int slen(const char* s)
+{
+    int n = 0;
+    while (s[n]) ++n;
+    return n;
+}
+
+// the strings the reference itself uses: six 5-letter palindromes (tests/test_shadow_work.py:47-55,
+// evaluation/compare_near_eq_and_exact.py:21-25), the substep sequences of the four numba closures,
+// "R V O" / "R O V", and the g-BAOAB strings of utilities/mts_utilities.py:generate_gbaoab_string
+#define LSI_FUSED_STRINGS(X)                                                                       \
+    X("OVRVO") X("ORVRO") X("RVOVR") X("ROVOR") X("VRORV") X("VOROV")                              \
+    X("OVRRVO") X("VROORV") X("RVOOVR") X("RVO") X("ROV") X("VRRORRV") X("VRRRORRRV")
+
+template <int POT, bool NOISE32>
+bool launch_fused2(uint32_t code, int nops, const ToyParams& P, cudaStream_t st, cudaError_t* err)
+{
+    const unsigned grid = (unsigned)((P.n + kThreads - 1) / kThreads);
+#define X(S)                                                                                       \
+    if (nops == slen(S) && code == pack(S)) {                                                      \
+        toy_fused_kernel<POT, pack(S), slen(S), NOISE32><<<grid, kThreads, 0, st>>>(P);            \
+        *err = cudaGetLastError();                                                                 \
+        return true;                                                                               \
+    }
+    LSI_FUSED_STRINGS(X)
+#undef X
+    return false;
+}
+
+bool launch_fused(int pot, bool noise32, uint32_t code, int nops, const ToyParams& P, cudaStream_t st,
+                  cudaError_t* err)
+{
+    switch (pot) {
+    case LSI_POT_QUARTIC:
+        return noise32 ? launch_fused2<LSI_POT_QUARTIC, true>(code, nops, P, st, err)
+                       : launch_fused2<LSI_POT_QUARTIC, false>(code, nops, P, st, err);
+    case LSI_POT_DOUBLE_WELL:
+        return noise32 ? launch_fused2<LSI_POT_DOUBLE_WELL, true>(code, nops, P, st, err)
+                       : launch_fused2<LSI_POT_DOUBLE_WELL, false>(code, nops, P, st, err);
+    default:
+        return noise32 ? launch_fused2<LSI_POT_HARMONIC, true>(code, nops, P, st, err)
+                       : launch_fused2<LSI_POT_HARMONIC, false>(code, nops, P, st, err);
+    }
 }
 
 }  // namespace
@@ -298,50 +517,26 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
     if (!a->W) return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol: W output is required");
     if (!a->x0 && !(a->x_cache && a->n_cache > 0))
         return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol: need x0 or a non-empty x_cache");
-    if (a->precision != LSI_PRECISION_DOUBLE)
-        return lsi_set_error(LSI_ERR_UNSUPPORTED, "scalar systems run in fp64 only (the reference's numba path is fp64)");
+    if (a->precision != LSI_PRECISION_DOUBLE && a->precision != LSI_PRECISION_MIXED)
+        return lsi_set_error(LSI_ERR_ARG, "unknown precision %d", a->precision);
     if (a->W_direct && !prog->measure_shadow_work)
         return lsi_set_error(LSI_ERR_ARG, "W_direct needs a program compiled with measure_shadow_work");
+    if (a->n_legs > 64) return lsi_set_error(LSI_ERR_ARG, "at most 64 legs");
     for (const lsi_op& op : prog->ops)
         if (op.kind == LSI_OP_V && op.group >= 0)
             return lsi_set_error(LSI_ERR_UNSUPPORTED, "scalar systems have a single force group; got V%d", op.group);
 
-    ToyProgram tp;
     const int n_ops = (int)prog->ops.size();
-    tp.n_ops = n_ops;
-    tp.n_O = prog->n_O;
-    tp.ext_kind = nullptr; tp.ext_c0 = nullptr; tp.ext_c1 = nullptr;
     const double sigma = sqrt(a->kT / sys->mass);
-    std::vector<unsigned char> kinds(n_ops);
-    std::vector<double> c0(n_ops), c1(n_ops);
-    for (int i = 0; i < n_ops; ++i) {
-        const lsi_op& op = prog->ops[i];
-        kinds[i] = (unsigned char)op.kind;
-        if (op.kind == LSI_OP_R) { c0[i] = prog->dt * op.fraction; c1[i] = 0.0; }
-        else if (op.kind == LSI_OP_V) { c0[i] = prog->dt * op.fraction / sys->mass; c1[i] = 0.0; }
-        else { c0[i] = op.a; c1[i] = op.b * sigma; }
-    }
-    void* ext = nullptr;
-    if (n_ops <= kMaxOps) {
-        for (int i = 0; i < n_ops; ++i) { tp.kind[i] = kinds[i]; tp.c0[i] = c0[i]; tp.c1[i] = c1[i]; }
-    } else {
-        // long multi-timestep strings: stage the program in device memory (stream-ordered)
-        const size_t nb = (size_t)n_ops * (2 * sizeof(double)) + (size_t)n_ops;
-        LSI_CUDA_CHECK(cudaMallocAsync(&ext, nb, st));
-        double* d0 = (double*)ext;
-        double* d1 = d0 + n_ops;
-        unsigned char* dk = (unsigned char*)(d1 + n_ops);
-        LSI_CUDA_CHECK(cudaMemcpyAsync(d0, c0.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
-        LSI_CUDA_CHECK(cudaMemcpyAsync(d1, c1.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
-        LSI_CUDA_CHECK(cudaMemcpyAsync(dk, kinds.data(), n_ops, cudaMemcpyHostToDevice, st));
-        LSI_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors die at return
-        tp.ext_c0 = d0; tp.ext_c1 = d1; tp.ext_kind = dk;
-    }
+    const bool noise32 = a->precision == LSI_PRECISION_MIXED;
+    if ((int64_t)a->n_steps * (int64_t)(prog->n_O > 0 ? prog->n_O : 1) >= ((int64_t)1 << 28))
+        return lsi_set_error(LSI_ERR_ARG, "n_steps * n_O exceeds the 2^28 draws a leg's noise stream holds");
 
     ToyParams P;
     P.seed = a->seed; P.replica0 = a->replica0; P.n = a->n_replicas;
     P.n_steps = a->n_steps; P.n_legs = a->n_legs; P.marginal = a->marginal;
     P.mass = sys->mass; P.kT = a->kT; P.inv_kT = 1.0 / a->kT; P.sigma = sigma; P.p0 = sys->params[0];
+    P.hR = P.hV = P.oa = P.oc = 0.0;
     P.x_cache = a->x_cache; P.n_cache = a->n_cache; P.x0 = a->x0; P.v0 = a->v0;
     P.W = a->W; P.heat = a->heat; P.W_direct = a->W_direct; P.x_final = a->x_final; P.v_final = a->v_final;
     P.trace_x = a->trace_x; P.trace_v = a->trace_v; P.trace_w = a->trace_w;
@@ -356,14 +551,70 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
     }
     const bool direct = a->W_direct != nullptr;
     const bool trace = a->trace_x || a->trace_v || a->trace_w;
-    cudaError_t err;
-    switch (sys->potential) {
-    case LSI_POT_QUARTIC: err = launch<LSI_POT_QUARTIC>(tp, P, direct, trace, st); break;
-    case LSI_POT_DOUBLE_WELL: err = launch<LSI_POT_DOUBLE_WELL>(tp, P, direct, trace, st); break;
-    case LSI_POT_HARMONIC: err = launch<LSI_POT_HARMONIC>(tp, P, direct, trace, st); break;
-    default: return lsi_set_error(LSI_ERR_ARG, "unknown potential kind %d", sys->potential);
+
+    // ---- fused path: every substep of a kind has the same length (true for lsi_compile output)
+    bool launched = false;
+    cudaError_t err = cudaSuccess;
+    if (!direct && !trace && n_ops <= 16) {
+        uint32_t code = 0;
+        bool uniform = true;
+        double fr[3] = {-1, -1, -1}, oa = 0, ob = 0;
+        for (int i = 0; i < n_ops && uniform; ++i) {
+            const lsi_op& op = prog->ops[i];
+            code |= (uint32_t)op.kind << (2 * i);
+            if (fr[op.kind] < 0) fr[op.kind] = op.fraction;
+            uniform = uniform && fr[op.kind] == op.fraction;
+            if (op.kind == LSI_OP_O) {
+                if (oa == 0 && ob == 0) { oa = op.a; ob = op.b; }
+                uniform = uniform && oa == op.a && ob == op.b;
+            }
+        }
+        if (uniform) {
+            P.hR = prog->dt * (fr[LSI_OP_R] > 0 ? fr[LSI_OP_R] : 0.0);
+            P.hV = prog->dt * (fr[LSI_OP_V] > 0 ? fr[LSI_OP_V] : 0.0) / sys->mass;
+            P.oa = oa; P.oc = ob * sigma;
+            launched = launch_fused(sys->potential, noise32, code, n_ops, P, st, &err);
+        }
     }
-    if (err != cudaSuccess) return lsi_set_error(LSI_ERR_CUDA, "toy_protocol_kernel launch failed: %s", cudaGetErrorString(err));
+
+    void* ext = nullptr;
+    if (!launched) {
+        ToyProgram tp;
+        tp.n_ops = n_ops;
+        tp.n_O = prog->n_O;
+        tp.ext_kind = nullptr; tp.ext_c0 = nullptr; tp.ext_c1 = nullptr;
+        std::vector<unsigned char> kinds(n_ops);
+        std::vector<double> c0(n_ops), c1(n_ops);
+        for (int i = 0; i < n_ops; ++i) {
+            const lsi_op& op = prog->ops[i];
+            kinds[i] = (unsigned char)op.kind;
+            if (op.kind == LSI_OP_R) { c0[i] = prog->dt * op.fraction; c1[i] = 0.0; }
+            else if (op.kind == LSI_OP_V) { c0[i] = prog->dt * op.fraction / sys->mass; c1[i] = 0.0; }
+            else { c0[i] = op.a; c1[i] = op.b * sigma; }
+        }
+        if (n_ops <= kMaxOps) {
+            for (int i = 0; i < n_ops; ++i) { tp.kind[i] = kinds[i]; tp.c0[i] = c0[i]; tp.c1[i] = c1[i]; }
+        } else {
+            // long multi-timestep strings: stage the program in device memory (stream-ordered)
+            const size_t nb = (size_t)n_ops * (2 * sizeof(double)) + (size_t)n_ops;
+            LSI_CUDA_CHECK(cudaMallocAsync(&ext, nb, st));
+            double* d0 = (double*)ext;
+            double* d1 = d0 + n_ops;
+            unsigned char* dk = (unsigned char*)(d1 + n_ops);
+            LSI_CUDA_CHECK(cudaMemcpyAsync(d0, c0.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
+            LSI_CUDA_CHECK(cudaMemcpyAsync(d1, c1.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
+            LSI_CUDA_CHECK(cudaMemcpyAsync(dk, kinds.data(), n_ops, cudaMemcpyHostToDevice, st));
+            LSI_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors die at return
+            tp.ext_c0 = d0; tp.ext_c1 = d1; tp.ext_kind = dk;
+        }
+        switch (sys->potential) {
+        case LSI_POT_QUARTIC: err = launch_interp<LSI_POT_QUARTIC>(tp, P, direct, trace, ext != nullptr, noise32, st); break;
+        case LSI_POT_DOUBLE_WELL: err = launch_interp<LSI_POT_DOUBLE_WELL>(tp, P, direct, trace, ext != nullptr, noise32, st); break;
+        case LSI_POT_HARMONIC: err = launch_interp<LSI_POT_HARMONIC>(tp, P, direct, trace, ext != nullptr, noise32, st); break;
+        default: return lsi_set_error(LSI_ERR_ARG, "unknown potential kind %d", sys->potential);
+        }
+    }
+    if (err != cudaSuccess) return lsi_set_error(LSI_ERR_CUDA, "toy kernel launch failed: %s", cudaGetErrorString(err));
     if (ext) LSI_CUDA_CHECK(cudaFreeAsync(ext, st));
     if (a->moments) return lsi_finalize_moments(P.partials, (int)grid, a->moments, stream);
     return LSI_OK;

@@ -157,6 +157,23 @@ ORC_API double orc_toy_force(int kind, const double* p, double x) { return toy_f
 /* op kinds */
 enum { OP_R = 0, OP_V = 1, OP_O = 2 };
 
+/* fp32 Box-Muller used by the engine's "mixed" precision (24-bit uniforms, as OpenMM's CUDA
+ * platform generates its `gaussian` in single precision): log / sinpi / cospi are evaluated in
+ * double and rounded to float, i.e. the correctly rounded values the GPU's logf / sincospif
+ * approximate to within 1-2 ulp. */
+static void normals4_f32(const uint32_t r[4], double n[4])
+{
+    for (int p = 0; p < 2; ++p) {
+        const float u1 = ((float)(r[2 * p] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+        const float u2x2 = ((float)(r[2 * p + 1] >> 8) + 0.5f) * 1.1920928955078125e-7f;
+        const float rad = sqrtf(-2.0f * (float)log((double)u1));
+        const float c = (float)cos(3.14159265358979323846 * (double)u2x2);
+        const float sn = (float)sin(3.14159265358979323846 * (double)u2x2);
+        n[2 * p] = (double)(rad * c);
+        n[2 * p + 1] = (double)(rad * sn);
+    }
+}
+
 /*
  * Runs, for each replica, n_legs legs of `n_steps` applications of the
  * splitting program (bookkeepers.py:247-295 / low_dimensional_systems.py:160-184):
@@ -167,8 +184,8 @@ enum { OP_R = 0, OP_V = 1, OP_O = 2 };
  * x, v and the cumulative W in kT (numba_integrators.py:56-61).
  * If `wdirect` is non-NULL the direct shadow-work accumulator
  * (langevin.py:125-139,150-163) is returned per leg as well.
- * O-noise: normal number (step_global * n_O_tokens + ordinal) of the replica's
- * TAG_O scalar stream, step_global counting across both legs.
+ * O-noise (DESIGN.md "RNG layout"): within leg l, the q-th O draw (q = step * n_O_tokens +
+ * ordinal) is lane q & 3 of the Philox block with draw word (l << 26) | (q >> 2), tag TAG_O.
  */
 ORC_API int orc_toy_protocol(int pot_kind, const double* pot_params, double mass, double kT,
                              int n_ops, const int32_t* op_kind, const double* op_frac,
@@ -176,7 +193,7 @@ ORC_API int orc_toy_protocol(int pot_kind, const double* pot_params, double mass
                              uint64_t seed, uint64_t replica0, int64_t n_replicas,
                              const double* x_cache, int64_t n_cache,
                              const double* x0_in, const double* v0_in,
-                             int n_steps, int marginal, int n_legs,
+                             int n_steps, int marginal, int n_legs, int noise_fp32,
                              double* W, double* Q, double* wdirect,
                              double* trace_x, double* trace_v, double* trace_w,
                              double* x_final, double* v_final)
@@ -192,20 +209,19 @@ ORC_API int orc_toy_protocol(int pot_kind, const double* pot_params, double mass
         double x = x0_in ? x0_in[r] : x_cache[cache_index(seed, rid, n_cache)];
         double v = v0_in ? v0_in[r] : sigma * scalar_normal(seed, rid, TAG_V0, 0u);
         double heat = 0.0;
-        uint32_t step_global = 0;
-        uint32_t blk_id = 0xFFFFFFFFu; /* O-stream block held in nblk (one Philox call per 4 draws) */
-        double nblk[4] = {0, 0, 0, 0};
         for (int leg = 0; leg < n_legs; ++leg) {
             if (leg > 0 && marginal == 0) v = sigma * scalar_normal(seed, rid, TAG_VMID, (uint32_t)(leg - 1));
             const double E0 = toy_potential(pot_kind, pot_params, x) + 0.5 * mass * v * v;
             const double Q0 = heat;
             double wd = 0.0;
+            uint32_t blk_id = 0xFFFFFFFFu; /* O-stream block held in nblk (one Philox call per 4 draws) */
+            double nblk[4] = {0, 0, 0, 0};
+            uint32_t q = 0;
             const int64_t base = (r * n_legs + leg) * T;
             if (trace_x) trace_x[base] = x;
             if (trace_v) trace_v[base] = v;
             if (trace_w) trace_w[base] = 0.0;
-            for (int s = 0; s < n_steps; ++s, ++step_global) {
-                uint32_t ordinal = 0;
+            for (int s = 0; s < n_steps; ++s) {
                 for (int i = 0; i < n_ops; ++i) {
                     const double h = dt * op_frac[i];
                     if (op_kind[i] == OP_R) {
@@ -218,17 +234,17 @@ ORC_API int orc_toy_protocol(int pot_kind, const double* pot_params, double mass
                         wd += 0.5 * mass * v * v - ke_old;
                     } else {
                         const double ke_old = 0.5 * mass * v * v;
-                        const uint32_t k = step_global * (uint32_t)n_O + ordinal;
-                        if ((k >> 2) != blk_id) {
+                        if ((q >> 2) != blk_id) {
                             uint32_t rr[4];
-                            blk_id = k >> 2;
-                            philox_block(seed, rid, blk_id, TAG_O, 0u, rr);
-                            normals4(rr, nblk);
+                            blk_id = q >> 2;
+                            philox_block(seed, rid, ((uint32_t)leg << 26) | blk_id, TAG_O, 0u, rr);
+                            if (noise_fp32) normals4_f32(rr, nblk);
+                            else normals4(rr, nblk);
                         }
-                        const double xi = nblk[k & 3u];
+                        const double xi = nblk[q & 3u];
+                        ++q;
                         v = op_a[i] * v + op_b[i] * sigma * xi;
                         heat += 0.5 * mass * v * v - ke_old;
-                        ++ordinal;
                     }
                 }
                 if (trace_x) trace_x[base + s + 1] = x;

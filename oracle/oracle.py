@@ -86,7 +86,7 @@ def toy_force(kind, x, params=(0.0,)):
 
 def toy_protocol(potential, splitting, dt, gamma, n_replicas, n_steps, marginal="configuration",
                  mass=10.0, kT=1.0, seed=0, replica0=0, x_cache=None, x0=None, v0=None, n_legs=2,
-                 traces=False, pot_params=(0.0,), program=None, want_direct=False):
+                 traces=False, pot_params=(0.0,), program=None, want_direct=False, noise_fp32=False):
     """Returns dict(W (n, n_legs), Q, x_final, v_final[, Wdirect, trace_x, trace_v, trace_w])."""
     prog = program or _sp.compile_splitting(splitting, dt, gamma)
     kind, _group, frac, a, b = _ops_arrays(prog)
@@ -108,7 +108,7 @@ def toy_protocol(potential, splitting, dt, gamma, n_replicas, n_steps, marginal=
         len(kind), kind.ctypes.data_as(c_int32_p), _dp(frac), _dp(a), _dp(b), ctypes.c_double(dt),
         ctypes.c_uint64(seed), ctypes.c_uint64(replica0), ctypes.c_int64(n),
         _dp(xc), ctypes.c_int64(0 if xc is None else len(xc)), _dp(x0a), _dp(v0a),
-        int(n_steps), MARGINAL[marginal], int(n_legs),
+        int(n_steps), MARGINAL[marginal], int(n_legs), int(bool(noise_fp32)),
         _dp(W), _dp(Q), _dp(wd), _dp(tx), _dp(tv), _dp(tw), _dp(xf), _dp(vf))
     assert rc == 0
     out = {"W": W, "Q": Q, "x_final": xf, "v_final": vf}

@@ -10,8 +10,10 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 SIX = ["O V R V O", "O R V R O", "R V O V R", "R O V O R", "V R O R V", "V O R O V"]
-# fp64 on both sides, same Philox words; libm vs CUDA log/sincos differ in the last ulp
-RTOL, ATOL = 1e-9, 1e-11
+# fp64 on both sides, same Philox words; libm vs CUDA log/sincos differ in the last ulp and the
+# double well amplifies that over a trajectory (observed worst case 8e-9 relative) -- still
+# three orders inside the 1e-5 parity bar of BASELINE.json
+RTOL, ATOL = 1e-7, 1e-9
 
 
 @pytest.fixture(scope="module")
@@ -55,10 +57,37 @@ def test_protocol_matches_oracle(ib, orc, kind, marginal):
         np.testing.assert_allclose(res["W_direct"].cpu().numpy(), res["W"].cpu().numpy(), rtol=1e-7, atol=1e-9)
         # fused moments == moments of the returned works
         m = res["moments"].cpu().numpy()
-        wf, wr = ref["W"][:, 0], ref["W"][:, 1]
-        np.testing.assert_allclose(m[:6], [n, wf.sum(), wr.sum(), (wf * wf).sum(), (wr * wr).sum(), (wf * wr).sum()],
-                                   rtol=1e-9, atol=1e-9)
-        assert m[6] == 0
+        ok = np.isfinite(ref["W"]).all(axis=1)  # unstable replicas (large dt) are counted, not summed
+        wf, wr = ref["W"][ok, 0], ref["W"][ok, 1]
+        np.testing.assert_allclose(m[:6], [ok.sum(), wf.sum(), wr.sum(), (wf * wf).sum(), (wr * wr).sum(), (wf * wr).sum()],
+                                   rtol=1e-6, atol=1e-9)
+        assert m[6] == n - ok.sum()
+        # the fused (compile-time splitting) kernel and the interpreter agree with the oracle alike:
+        # without traces / direct work the whitelisted strings take the fused path
+        res2 = ib.engine.run_protocol(system, ib.engine.Program(splitting, dt, gamma), n, n_steps, 1.0, marginal=marginal,
+                                      seed=77 + j, replica0=12345, x_cache=cache, want_heat=True, want_final=True)
+        np.testing.assert_allclose(res2["W"].cpu().numpy().T, ref["W"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(res2["heat"].cpu().numpy().T, ref["Q"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(res2["x_final"].cpu().numpy(), ref["x_final"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(res2["moments"].cpu().numpy()[:7], m[:7], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", ["quartic", "double_well"])
+def test_mixed_precision_noise_matches_oracle(ib, orc, kind):
+    """precision="mixed": fp32 Box-Muller noise (as OpenMM's CUDA platform draws `gaussian`), fp64 state.
+    Tolerance 1e-5 relative as BASELINE.json states; the works are differences of O(1) energies, so
+    they are held to 1e-5 of the energy scale."""
+    cache = _cache(orc, kind)
+    system = ib.engine.ScalarSystem(kind, 10.0)
+    for j, splitting in enumerate(SIX + ["V R R O R R V", "V0 R O R V0".replace("0", "")]):
+        gamma, dt, n_steps, n = [100.0, 10.0, 1.0][j % 3], [0.1, 0.3, 0.2][j % 3], 7 + j, 2049
+        for traces in (False, True):  # fused kernel / interpreter
+            res = ib.engine.run_protocol(system, ib.engine.Program(splitting, dt, gamma), n, n_steps, 1.0, seed=j,
+                                         x_cache=cache, precision="mixed", want_final=True, traces=traces)
+            ref = orc.toy_protocol(kind, splitting, dt, gamma, n, n_steps, seed=j, x_cache=cache, noise_fp32=True)
+            np.testing.assert_allclose(res["x_final"].cpu().numpy(), ref["x_final"], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(res["v_final"].cpu().numpy(), ref["v_final"], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(res["W"].cpu().numpy().T, ref["W"], rtol=1e-5, atol=1e-5)
 
 
 def test_replica_ids_key_the_streams(ib, orc):
@@ -167,7 +196,9 @@ def test_collect_protocol_samples_api_and_estimate(ib, orc):
         # traces=False gives the same final works
         ib.set_seed(2024, next_replica=1000)
         W_F2, W_R2, _, _ = sim.collect_protocol_samples(n, length, "configuration", traces=False)
-        assert np.array_equal(W_F2[:, -1], W_F[:, -1]) and np.array_equal(W_R2[:, -1], W_R[:, -1])
+        # (fused kernel vs interpreter: same arithmetic up to fma contraction of the cached force)
+        np.testing.assert_allclose(W_F2[:, -1], W_F[:, -1], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(W_R2[:, -1], W_R[:, -1], rtol=RTOL, atol=ATOL)
         dF2, var2 = ib.evaluation.estimate_from_moments(sim.last_moments.cpu().numpy())
         assert dF2 == pytest.approx(dF, rel=1e-9, abs=1e-12) and var2 == pytest.approx(var, rel=1e-7)
 
