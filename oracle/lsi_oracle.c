@@ -322,3 +322,543 @@ ORC_API int orc_sample_equilibrium_scalar(int pot_kind, const double* pot_params
     }
     return 0;
 }
+
+/* =========================================================================================
+ * Particle systems (water cluster, alanine dipeptide, tiny waterbox)
+ *
+ * Force field terms follow the OpenMM force classes the reference's systems are built from
+ * ([ext]: OpenMM is not available here, the functional forms are restated from its
+ * documentation): NonbondedForce (Lennard-Jones with Lorentz-Berthelot combination + Coulomb,
+ * NoCutoff or CutoffPeriodic with reaction field, exclusions and 1-4 exceptions),
+ * HarmonicBondForce, HarmonicAngleForce, PeriodicTorsionForce, and the CustomExternalForce
+ * (K/2)(x^2+y^2+z^2) of benchmark/testsystems/watercluster.py:70-80.
+ * Substeps with constraints: benchmark/integrators/langevin.py:124-175
+ *   R: x += h v; constrain positions; v += (x - x_unconstrained)/h; constrain velocities
+ *   V: v += h f_g/m; constrain velocities        O: v = a v + b sqrt(kT/m) xi; constrain velocities
+ * Protocol: benchmark/testsystems/bookkeepers.py:184-295.
+ * ========================================================================================= */
+
+#define ONE_4PI_EPS0 138.935456 /* kJ nm / (mol e^2); benchmark/integrators/kyle/constants.py:8 */
+
+typedef struct {
+    int32_t n_atoms;
+    const double* mass;
+    const double* charge;
+    const double* sigma;
+    const double* epsilon;
+    int32_t nonbonded_method; /* 0 NoCutoff, 1 CutoffPeriodic (reaction field) */
+    double cutoff;
+    double box[3];
+    double rf_dielectric;
+    int32_t n_exclusions;
+    const int32_t* exclusions; /* [n][2] */
+    int32_t n_exceptions;
+    const int32_t* exception_atoms; /* [n][2] */
+    const double* exception_params; /* [n][3] chargeProd, sigma, epsilon */
+    int32_t n_bonds;
+    const int32_t* bond_atoms;
+    const double* bond_params; /* [n][2] r0, k */
+    int32_t n_angles;
+    const int32_t* angle_atoms;
+    const double* angle_params; /* [n][2] theta0, k */
+    int32_t n_torsions;
+    const int32_t* torsion_atoms;
+    const double* torsion_params; /* [n][3] periodicity, phase, k */
+    double restraint_k;
+    int32_t group_nonbonded, group_bonds, group_angles, group_torsions, group_restraint;
+    int32_t n_settle;
+    const int32_t* settle_atoms; /* [n][3] O, H1, H2 */
+    double settle_oh, settle_hh;
+    int32_t n_constraints;
+    const int32_t* constraint_atoms; /* [n][2] */
+    const double* constraint_dist;
+    double constraint_tolerance;
+} OrcParticles;
+
+static inline int in_group(int term_group, int g) { return g < 0 || term_group == g; }
+
+static void min_image(const OrcParticles* S, double d[3])
+{
+    if (S->nonbonded_method == 1)
+        for (int c = 0; c < 3; ++c) d[c] -= S->box[c] * floor(d[c] / S->box[c] + 0.5);
+}
+
+/* forces (3N, overwritten) and energy of the force classes selected by group g (-1 = all) */
+static double particles_forces(const OrcParticles* S, const double* x, int g, double* f)
+{
+    const int N = S->n_atoms;
+    double E = 0.0;
+    memset(f, 0, sizeof(double) * 3 * N);
+    if (in_group(S->group_nonbonded, g)) {
+        /* exclusion lookup (dense; N is at most a few hundred) */
+        unsigned char* ex = (unsigned char*)calloc((size_t)N * N, 1);
+        for (int k = 0; k < S->n_exclusions; ++k) {
+            const int i = S->exclusions[2 * k], j = S->exclusions[2 * k + 1];
+            ex[(size_t)i * N + j] = ex[(size_t)j * N + i] = 1;
+        }
+        for (int k = 0; k < S->n_exceptions; ++k) {
+            const int i = S->exception_atoms[2 * k], j = S->exception_atoms[2 * k + 1];
+            ex[(size_t)i * N + j] = ex[(size_t)j * N + i] = 1;
+        }
+        const double rc = S->cutoff, rc2 = rc * rc;
+        const double eps_rf = S->rf_dielectric;
+        const double krf = S->nonbonded_method == 1 ? (1.0 / (rc * rc * rc)) * (eps_rf - 1.0) / (2.0 * eps_rf + 1.0) : 0.0;
+        const double crf = S->nonbonded_method == 1 ? (1.0 / rc) * (3.0 * eps_rf) / (2.0 * eps_rf + 1.0) : 0.0;
+        for (int i = 0; i < N; ++i)
+            for (int j = i + 1; j < N; ++j) {
+                if (ex[(size_t)i * N + j]) continue;
+                double d[3] = {x[3 * j] - x[3 * i], x[3 * j + 1] - x[3 * i + 1], x[3 * j + 2] - x[3 * i + 2]};
+                min_image(S, d);
+                const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                if (S->nonbonded_method == 1 && r2 >= rc2) continue;
+                const double r = sqrt(r2), inv_r = 1.0 / r;
+                const double sig = 0.5 * (S->sigma[i] + S->sigma[j]);
+                const double eps = sqrt(S->epsilon[i] * S->epsilon[j]);
+                const double sr2 = sig * sig / r2, sr6 = sr2 * sr2 * sr2;
+                const double qq = ONE_4PI_EPS0 * S->charge[i] * S->charge[j];
+                /* dE/dr * (1/r): LJ 4 eps (12 sr12 - 6 sr6)/r^2 ; Coulomb qq (1/r^3 - 2 krf) */
+                const double fr = 4.0 * eps * (12.0 * sr6 * sr6 - 6.0 * sr6) / r2 + qq * (inv_r * inv_r * inv_r - 2.0 * krf);
+                E += 4.0 * eps * (sr6 * sr6 - sr6) + qq * (inv_r + krf * r2 - crf);
+                for (int c = 0; c < 3; ++c) {
+                    f[3 * i + c] -= fr * d[c];
+                    f[3 * j + c] += fr * d[c];
+                }
+            }
+        /* exceptions: plain Coulomb + LJ with their own parameters (no reaction field) */
+        for (int k = 0; k < S->n_exceptions; ++k) {
+            const int i = S->exception_atoms[2 * k], j = S->exception_atoms[2 * k + 1];
+            const double qq = ONE_4PI_EPS0 * S->exception_params[3 * k], sig = S->exception_params[3 * k + 1],
+                         eps = S->exception_params[3 * k + 2];
+            double d[3] = {x[3 * j] - x[3 * i], x[3 * j + 1] - x[3 * i + 1], x[3 * j + 2] - x[3 * i + 2]};
+            min_image(S, d);
+            const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            if (S->nonbonded_method == 1 && r2 >= rc2) continue;
+            const double inv_r = 1.0 / sqrt(r2);
+            const double sr2 = sig * sig / r2, sr6 = sr2 * sr2 * sr2;
+            const double fr = 4.0 * eps * (12.0 * sr6 * sr6 - 6.0 * sr6) / r2 + qq * inv_r * inv_r * inv_r;
+            E += 4.0 * eps * (sr6 * sr6 - sr6) + qq * inv_r;
+            for (int c = 0; c < 3; ++c) {
+                f[3 * i + c] -= fr * d[c];
+                f[3 * j + c] += fr * d[c];
+            }
+        }
+        free(ex);
+    }
+    if (in_group(S->group_bonds, g))
+        for (int k = 0; k < S->n_bonds; ++k) {
+            const int i = S->bond_atoms[2 * k], j = S->bond_atoms[2 * k + 1];
+            const double r0 = S->bond_params[2 * k], kb = S->bond_params[2 * k + 1];
+            double d[3] = {x[3 * j] - x[3 * i], x[3 * j + 1] - x[3 * i + 1], x[3 * j + 2] - x[3 * i + 2]};
+            const double r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            E += 0.5 * kb * (r - r0) * (r - r0);
+            const double fr = kb * (r - r0) / r; /* dE/dr / r */
+            for (int c = 0; c < 3; ++c) {
+                f[3 * i + c] += fr * d[c];
+                f[3 * j + c] -= fr * d[c];
+            }
+        }
+    if (in_group(S->group_angles, g))
+        for (int k = 0; k < S->n_angles; ++k) {
+            const int i = S->angle_atoms[3 * k], j = S->angle_atoms[3 * k + 1], l = S->angle_atoms[3 * k + 2];
+            const double th0 = S->angle_params[2 * k], ka = S->angle_params[2 * k + 1];
+            double a[3], b[3];
+            for (int c = 0; c < 3; ++c) {
+                a[c] = x[3 * i + c] - x[3 * j + c];
+                b[c] = x[3 * l + c] - x[3 * j + c];
+            }
+            const double ra2 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2], rb2 = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+            const double ra = sqrt(ra2), rb = sqrt(rb2);
+            double ct = (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) / (ra * rb);
+            if (ct > 1.0) ct = 1.0;
+            if (ct < -1.0) ct = -1.0;
+            const double th = acos(ct);
+            E += 0.5 * ka * (th - th0) * (th - th0);
+            const double dEdth = ka * (th - th0);
+            double st = sqrt(1.0 - ct * ct);
+            if (st < 1e-12) st = 1e-12;
+            /* dtheta/da = -(b/(ra rb) - ct a/ra^2)/sin(theta) */
+            for (int c = 0; c < 3; ++c) {
+                const double dth_da = -(b[c] / (ra * rb) - ct * a[c] / ra2) / st;
+                const double dth_db = -(a[c] / (ra * rb) - ct * b[c] / rb2) / st;
+                f[3 * i + c] -= dEdth * dth_da;
+                f[3 * l + c] -= dEdth * dth_db;
+                f[3 * j + c] += dEdth * (dth_da + dth_db);
+            }
+        }
+    if (in_group(S->group_torsions, g))
+        for (int k = 0; k < S->n_torsions; ++k) {
+            const int a1 = S->torsion_atoms[4 * k], a2 = S->torsion_atoms[4 * k + 1], a3 = S->torsion_atoms[4 * k + 2],
+                      a4 = S->torsion_atoms[4 * k + 3];
+            const double n = S->torsion_params[3 * k], ph = S->torsion_params[3 * k + 1], kt = S->torsion_params[3 * k + 2];
+            double b1[3], b2[3], b3[3];
+            for (int c = 0; c < 3; ++c) {
+                b1[c] = x[3 * a2 + c] - x[3 * a1 + c];
+                b2[c] = x[3 * a3 + c] - x[3 * a2 + c];
+                b3[c] = x[3 * a4 + c] - x[3 * a3 + c];
+            }
+            /* n1 = b1 x b2, n2 = b2 x b3; phi = atan2(|b2| b1.n2, n1.n2)  (IUPAC sign) */
+            const double n1[3] = {b1[1] * b2[2] - b1[2] * b2[1], b1[2] * b2[0] - b1[0] * b2[2], b1[0] * b2[1] - b1[1] * b2[0]};
+            const double n2[3] = {b2[1] * b3[2] - b2[2] * b3[1], b2[2] * b3[0] - b2[0] * b3[2], b2[0] * b3[1] - b2[1] * b3[0]};
+            const double b2n = sqrt(b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2]);
+            const double yy = b2n * (b1[0] * n2[0] + b1[1] * n2[1] + b1[2] * n2[2]);
+            const double xx = n1[0] * n2[0] + n1[1] * n2[1] + n1[2] * n2[2];
+            const double phi = atan2(yy, xx);
+            E += kt * (1.0 + cos(n * phi - ph));
+            const double dEdphi = -kt * n * sin(n * phi - ph);
+            /* gradient of phi (Blondel & Karplus 1996) */
+            const double n1sq = n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2];
+            const double n2sq = n2[0] * n2[0] + n2[1] * n2[1] + n2[2] * n2[2];
+            const double b1b2 = b1[0] * b2[0] + b1[1] * b2[1] + b1[2] * b2[2];
+            const double b3b2 = b3[0] * b2[0] + b3[1] * b2[1] + b3[2] * b2[2];
+            for (int c = 0; c < 3; ++c) {
+                const double g1 = -b2n / n1sq * n1[c];
+                const double g4 = b2n / n2sq * n2[c];
+                const double g2 = -g1 - (b1b2 / (b2n * b2n)) * g1 + (b3b2 / (b2n * b2n)) * g4;
+                const double g3 = -g4 + (b1b2 / (b2n * b2n)) * g1 - (b3b2 / (b2n * b2n)) * g4;
+                f[3 * a1 + c] -= dEdphi * g1;
+                f[3 * a2 + c] -= dEdphi * g2;
+                f[3 * a3 + c] -= dEdphi * g3;
+                f[3 * a4 + c] -= dEdphi * g4;
+            }
+        }
+    if (in_group(S->group_restraint, g) && S->restraint_k != 0.0)
+        for (int i = 0; i < 3 * N; ++i) {
+            E += 0.5 * S->restraint_k * x[i] * x[i];
+            f[i] -= S->restraint_k * x[i];
+        }
+    return E;
+}
+
+ORC_API double orc_particles_energy_forces(const OrcParticles* S, const double* x, int group, double* f)
+{
+    return particles_forces(S, x, group, f);
+}
+
+/* ---- constraints ----------------------------------------------------------------------- */
+/* SETTLE (Miyamoto & Kollman 1992) for one rigid three-site water: x0 = reference (constrained)
+ * positions, x1 = unconstrained new positions (overwritten with the constrained ones). */
+static void settle_positions(const double* x0, double* x1, const int32_t at[3], double mO, double mH,
+                             double dOH, double dHH)
+{
+    const double *a0 = x0 + 3 * at[0], *b0 = x0 + 3 * at[1], *c0 = x0 + 3 * at[2];
+    double *a1 = x1 + 3 * at[0], *b1 = x1 + 3 * at[1], *c1 = x1 + 3 * at[2];
+    const double mtot = mO + 2.0 * mH;
+    double xb0[3], xc0[3], xcom[3], xa1[3], xb1[3], xc1[3];
+    for (int c = 0; c < 3; ++c) {
+        xb0[c] = b0[c] - a0[c];
+        xc0[c] = c0[c] - a0[c];
+        xcom[c] = (mO * a1[c] + mH * b1[c] + mH * c1[c]) / mtot;
+        xa1[c] = a1[c] - xcom[c];
+        xb1[c] = b1[c] - xcom[c];
+        xc1[c] = c1[c] - xcom[c];
+    }
+    /* orthonormal frame: Z normal to the reference triangle, X = xa1 x Z, Y = Z x X */
+    double Z[3] = {xb0[1] * xc0[2] - xb0[2] * xc0[1], xb0[2] * xc0[0] - xb0[0] * xc0[2], xb0[0] * xc0[1] - xb0[1] * xc0[0]};
+    double X[3] = {xa1[1] * Z[2] - xa1[2] * Z[1], xa1[2] * Z[0] - xa1[0] * Z[2], xa1[0] * Z[1] - xa1[1] * Z[0]};
+    double Y[3] = {Z[1] * X[2] - Z[2] * X[1], Z[2] * X[0] - Z[0] * X[2], Z[0] * X[1] - Z[1] * X[0]};
+    const double nz = 1.0 / sqrt(Z[0] * Z[0] + Z[1] * Z[1] + Z[2] * Z[2]);
+    const double nx = 1.0 / sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2]);
+    const double ny = 1.0 / sqrt(Y[0] * Y[0] + Y[1] * Y[1] + Y[2] * Y[2]);
+    for (int c = 0; c < 3; ++c) { X[c] *= nx; Y[c] *= ny; Z[c] *= nz; }
+#define DOT3(u, w) ((u)[0] * (w)[0] + (u)[1] * (w)[1] + (u)[2] * (w)[2])
+    const double xb0d = DOT3(X, xb0), yb0d = DOT3(Y, xb0), xc0d = DOT3(X, xc0), yc0d = DOT3(Y, xc0);
+    const double za1d = DOT3(Z, xa1);
+    const double xb1d = DOT3(X, xb1), yb1d = DOT3(Y, xb1), zb1d = DOT3(Z, xb1);
+    const double xc1d = DOT3(X, xc1), yc1d = DOT3(Y, xc1), zc1d = DOT3(Z, xc1);
+    /* canonical triangle: ra = distance O - COM, rb = distance COM - HH midpoint, rc = half HH */
+    const double rc = 0.5 * dHH;
+    const double hgt = sqrt(dOH * dOH - rc * rc);
+    const double ra = hgt * 2.0 * mH / mtot, rb = hgt - ra;
+    const double sinphi = za1d / ra, cosphi = sqrt(1.0 - sinphi * sinphi);
+    const double sinpsi = (zb1d - zc1d) / (2.0 * rc * cosphi), cospsi = sqrt(1.0 - sinpsi * sinpsi);
+    const double ya2d = ra * cosphi;
+    const double xb2d = -rc * cospsi;
+    const double yb2d = -rb * cosphi - rc * sinpsi * sinphi;
+    const double yc2d = -rb * cosphi + rc * sinpsi * sinphi;
+    const double alpha = xb2d * (xb0d - xc0d) + yb0d * yb2d + yc0d * yc2d;
+    const double beta = xb2d * (yc0d - yb0d) + xb0d * yb2d + xc0d * yc2d;
+    const double gamma = xb0d * yb1d - xb1d * yb0d + xc0d * yc1d - xc1d * yc0d;
+    const double al2be2 = alpha * alpha + beta * beta;
+    const double sintheta = (alpha * gamma - beta * sqrt(al2be2 - gamma * gamma)) / al2be2;
+    const double costheta = sqrt(1.0 - sintheta * sintheta);
+    const double xa3d = -ya2d * sintheta, ya3d = ya2d * costheta, za3d = za1d;
+    const double xb3d = xb2d * costheta - yb2d * sintheta, yb3d = xb2d * sintheta + yb2d * costheta, zb3d = zb1d;
+    const double xc3d = -xb2d * costheta - yc2d * sintheta, yc3d = -xb2d * sintheta + yc2d * costheta, zc3d = zc1d;
+    for (int c = 0; c < 3; ++c) {
+        a1[c] = xcom[c] + X[c] * xa3d + Y[c] * ya3d + Z[c] * za3d;
+        b1[c] = xcom[c] + X[c] * xb3d + Y[c] * yb3d + Z[c] * zb3d;
+        c1[c] = xcom[c] + X[c] * xc3d + Y[c] * yc3d + Z[c] * zc3d;
+    }
+}
+
+/* exact velocity projection for a rigid triangle: solve the 3x3 system for the impulses along
+ * the three edges so that every edge's relative velocity along itself vanishes */
+static void settle_velocities(const double* x, double* v, const int32_t at[3], double mO, double mH)
+{
+    const int ia[3] = {at[0], at[1], at[2]};
+    const double im[3] = {1.0 / mO, 1.0 / mH, 1.0 / mH};
+    const int e[3][2] = {{0, 1}, {1, 2}, {2, 0}};
+    double u[3][3], b[3], A[3][3];
+    for (int k = 0; k < 3; ++k) {
+        double n2 = 0.0;
+        for (int c = 0; c < 3; ++c) {
+            u[k][c] = x[3 * ia[e[k][1]] + c] - x[3 * ia[e[k][0]] + c];
+            n2 += u[k][c] * u[k][c];
+        }
+        const double inv = 1.0 / sqrt(n2);
+        b[k] = 0.0;
+        for (int c = 0; c < 3; ++c) {
+            u[k][c] *= inv;
+            b[k] += (v[3 * ia[e[k][1]] + c] - v[3 * ia[e[k][0]] + c]) * u[k][c];
+        }
+    }
+    /* impulse lambda_l along edge l changes v_p by  -lambda_l u_l / m_p (p = tail), +... (p = head) */
+    for (int k = 0; k < 3; ++k)
+        for (int l = 0; l < 3; ++l) {
+            double coef = 0.0; /* d(relative velocity of edge k along u_k)/d lambda_l */
+            const double ukul = DOT3(u[k], u[l]);
+            if (e[k][1] == e[l][1]) coef += im[e[k][1]];
+            if (e[k][1] == e[l][0]) coef -= im[e[k][1]];
+            if (e[k][0] == e[l][1]) coef -= im[e[k][0]];
+            if (e[k][0] == e[l][0]) coef += im[e[k][0]];
+            A[k][l] = coef * ukul;
+        }
+    /* solve A lambda = -b (Cramer) */
+    const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                       A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+    const double r0 = -b[0], r1 = -b[1], r2 = -b[2];
+    const double l0 = (r0 * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (r1 * A[2][2] - A[1][2] * r2) +
+                       A[0][2] * (r1 * A[2][1] - A[1][1] * r2)) / det;
+    const double l1 = (A[0][0] * (r1 * A[2][2] - A[1][2] * r2) - r0 * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                       A[0][2] * (A[1][0] * r2 - r1 * A[2][0])) / det;
+    const double l2 = (A[0][0] * (A[1][1] * r2 - r1 * A[2][1]) - A[0][1] * (A[1][0] * r2 - r1 * A[2][0]) +
+                       r0 * (A[1][0] * A[2][1] - A[1][1] * A[2][0])) / det;
+    const double lam[3] = {l0, l1, l2};
+    for (int l = 0; l < 3; ++l)
+        for (int c = 0; c < 3; ++c) {
+            v[3 * ia[e[l][1]] + c] += lam[l] * u[l][c] * im[e[l][1]];
+            v[3 * ia[e[l][0]] + c] -= lam[l] * u[l][c] * im[e[l][0]];
+        }
+}
+#undef DOT3
+
+/* SHAKE: Gauss-Seidel sweeps over the distance constraints, displacements along the reference
+ * bond vectors, until every |r^2 - d^2| <= 2 tol d^2 */
+static int shake_positions(const OrcParticles* S, const double* x0, double* x1)
+{
+    const double tol = S->constraint_tolerance;
+    for (int it = 0; it < 500; ++it) {
+        int done = 1;
+        for (int k = 0; k < S->n_constraints; ++k) {
+            const int i = S->constraint_atoms[2 * k], j = S->constraint_atoms[2 * k + 1];
+            const double d2 = S->constraint_dist[k] * S->constraint_dist[k];
+            double r[3], s[3];
+            for (int c = 0; c < 3; ++c) {
+                r[c] = x1[3 * i + c] - x1[3 * j + c];
+                s[c] = x0[3 * i + c] - x0[3 * j + c];
+            }
+            const double diff = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] - d2;
+            if (fabs(diff) > 2.0 * tol * d2) done = 0;
+            const double rs = r[0] * s[0] + r[1] * s[1] + r[2] * s[2];
+            const double gl = diff / (2.0 * rs * (1.0 / S->mass[i] + 1.0 / S->mass[j]));
+            for (int c = 0; c < 3; ++c) {
+                x1[3 * i + c] -= gl * s[c] / S->mass[i];
+                x1[3 * j + c] += gl * s[c] / S->mass[j];
+            }
+        }
+        if (done) return it;
+    }
+    return -1;
+}
+
+static int rattle_velocities(const OrcParticles* S, const double* x, double* v)
+{
+    const double tol = S->constraint_tolerance;
+    for (int it = 0; it < 500; ++it) {
+        int done = 1;
+        for (int k = 0; k < S->n_constraints; ++k) {
+            const int i = S->constraint_atoms[2 * k], j = S->constraint_atoms[2 * k + 1];
+            const double d2 = S->constraint_dist[k] * S->constraint_dist[k];
+            double r[3], w[3];
+            for (int c = 0; c < 3; ++c) {
+                r[c] = x[3 * i + c] - x[3 * j + c];
+                w[c] = v[3 * i + c] - v[3 * j + c];
+            }
+            const double rv = r[0] * w[0] + r[1] * w[1] + r[2] * w[2];
+            const double gl = rv / (d2 * (1.0 / S->mass[i] + 1.0 / S->mass[j]));
+            if (fabs(gl) > tol) done = 0; /* impulse per unit mass-distance, in 1/ps */
+            for (int c = 0; c < 3; ++c) {
+                v[3 * i + c] -= gl * r[c] / S->mass[i];
+                v[3 * j + c] += gl * r[c] / S->mass[j];
+            }
+        }
+        if (done) return it;
+    }
+    return -1;
+}
+
+static void constrain_positions(const OrcParticles* S, const double* x0, double* x1)
+{
+    for (int w = 0; w < S->n_settle; ++w) {
+        const int32_t* at = S->settle_atoms + 3 * w;
+        settle_positions(x0, x1, at, S->mass[at[0]], S->mass[at[1]], S->settle_oh, S->settle_hh);
+    }
+    if (S->n_constraints) shake_positions(S, x0, x1);
+}
+
+static void constrain_velocities(const OrcParticles* S, const double* x, double* v)
+{
+    for (int w = 0; w < S->n_settle; ++w) {
+        const int32_t* at = S->settle_atoms + 3 * w;
+        settle_velocities(x, v, at, S->mass[at[0]], S->mass[at[1]]);
+    }
+    if (S->n_constraints) rattle_velocities(S, x, v);
+}
+
+ORC_API void orc_constrain_positions(const OrcParticles* S, const double* x0, double* x1) { constrain_positions(S, x0, x1); }
+ORC_API void orc_constrain_velocities(const OrcParticles* S, const double* x, double* v) { constrain_velocities(S, x, v); }
+
+static double kinetic_energy(const OrcParticles* S, const double* v)
+{
+    double ke = 0.0;
+    for (int i = 0; i < S->n_atoms; ++i)
+        ke += 0.5 * S->mass[i] * (v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]);
+    return ke;
+}
+
+static void atom_normals(uint64_t seed, uint64_t rid, uint32_t draw, uint32_t tag, int N, int noise_fp32, double* out)
+{
+    for (int i = 0; i < N; ++i) {
+        uint32_t r[4];
+        double n[4];
+        philox_block(seed, rid, draw, tag, (uint32_t)i, r);
+        if (noise_fp32) normals4_f32(r, n);
+        else normals4(r, n);
+        out[3 * i] = n[0]; out[3 * i + 1] = n[1]; out[3 * i + 2] = n[2];
+    }
+}
+
+/* flags */
+#define ORC_FLAG_ROUND_MIDPOINT_X_FP32 1 /* bookkeepers.py:266,298-305: x passes through a float32 frame */
+
+/*
+ * Protocol for particle systems (bookkeepers.py:184-295).  x_cache: [n_cache][N][3];
+ * x0_in / v0_in: [n][N][3].  Per leg: set state, apply position then velocity constraints
+ * (:206-208), E0 = PE + KE, run n_steps, W = ((E1 - E0) - (heat1 - heat0)) / kT.
+ * O noise: atom i, q-th O draw of leg l -> Philox(replica, draw = (l << 26) | q, TAG_O, unit i),
+ * lanes 0..2 = x, y, z.  Start / midpoint velocities: TAG_V0 draw 0 / TAG_VMID draw (l - 1).
+ * traces (optional): trace_x/v [n][n_legs][n_steps+1][N][3], trace_pe/ke/heat/wdir [n][n_legs][n_steps+1]
+ */
+ORC_API int orc_particles_protocol(const OrcParticles* S, double kT, int n_ops, const int32_t* op_kind,
+                                   const int32_t* op_group, const double* op_frac, const double* op_a,
+                                   const double* op_b, double dt, uint64_t seed, uint64_t replica0,
+                                   int64_t n_replicas, const double* x_cache, int64_t n_cache,
+                                   const double* x0_in, const double* v0_in, int n_steps, int marginal,
+                                   int n_legs, int noise_fp32, int flags, double* W, double* Q, double* wdirect,
+                                   double* x_final, double* v_final, double* trace_x, double* trace_v,
+                                   double* trace_pe, double* trace_ke, double* trace_heat, double* trace_wdir)
+{
+    const int N = S->n_atoms, D = 3 * N;
+    int n_O = 0;
+    for (int i = 0; i < n_ops; ++i) n_O += (op_kind[i] == OP_O);
+    const int64_t T = (int64_t)n_steps + 1;
+    int rc_all = 0;
+
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t r = 0; r < n_replicas; ++r) {
+        const uint64_t rid = replica0 + (uint64_t)r;
+        double* x = (double*)malloc(sizeof(double) * D);
+        double* v = (double*)malloc(sizeof(double) * D);
+        double* f = (double*)malloc(sizeof(double) * D);
+        double* xu = (double*)malloc(sizeof(double) * D);
+        double* xi = (double*)malloc(sizeof(double) * D);
+        const double* xs = x0_in ? x0_in + r * D : x_cache + cache_index(seed, rid, n_cache) * D;
+        memcpy(x, xs, sizeof(double) * D);
+        if (v0_in) memcpy(v, v0_in + r * D, sizeof(double) * D);
+        else {
+            atom_normals(seed, rid, 0u, TAG_V0, N, 0, xi);
+            for (int i = 0; i < D; ++i) v[i] = sqrt(kT / S->mass[i / 3]) * xi[i];
+        }
+        double heat = 0.0;
+        double* fcache[34] = {0};
+        char fvalid[34] = {0};
+        const int want_direct = wdirect != NULL || trace_wdir != NULL;
+        for (int leg = 0; leg < n_legs; ++leg) {
+            memset(fvalid, 0, sizeof(fvalid));
+            if (leg > 0) {
+                if (flags & ORC_FLAG_ROUND_MIDPOINT_X_FP32)
+                    for (int i = 0; i < D; ++i) x[i] = (double)(float)x[i];
+                if (marginal == 0) {
+                    atom_normals(seed, rid, (uint32_t)(leg - 1), TAG_VMID, N, 0, xi);
+                    for (int i = 0; i < D; ++i) v[i] = sqrt(kT / S->mass[i / 3]) * xi[i];
+                }
+            }
+            /* context.applyConstraints / applyVelocityConstraints (bookkeepers.py:206-208) */
+            memcpy(xu, x, sizeof(double) * D);
+            constrain_positions(S, xu, x);
+            constrain_velocities(S, x, v);
+            double pe = particles_forces(S, x, -1, f);
+            const double E0 = pe + kinetic_energy(S, v);
+            const double Q0 = heat;
+            double wd = 0.0;
+            uint32_t q = 0;
+            const int64_t tb = (r * n_legs + leg) * T;
+            if (trace_x) memcpy(trace_x + tb * D, x, sizeof(double) * D);
+            if (trace_v) memcpy(trace_v + tb * D, v, sizeof(double) * D);
+            if (trace_pe) trace_pe[tb] = pe;
+            if (trace_ke) trace_ke[tb] = kinetic_energy(S, v);
+            if (trace_heat) trace_heat[tb] = 0.0;
+            if (trace_wdir) trace_wdir[tb] = 0.0;
+            for (int s = 0; s < n_steps; ++s) {
+                for (int i = 0; i < n_ops; ++i) {
+                    const double h = dt * op_frac[i];
+                    if (op_kind[i] == OP_R) {
+                        const double e_old = want_direct ? particles_forces(S, x, -1, f) + kinetic_energy(S, v) : 0.0;
+                        memset(fvalid, 0, sizeof(fvalid));
+                        memcpy(xu, x, sizeof(double) * D); /* reference positions for the constraints */
+                        for (int k = 0; k < D; ++k) x[k] = x[k] + h * v[k];
+                        memcpy(xi, x, sizeof(double) * D); /* x1: unconstrained */
+                        constrain_positions(S, xu, x);
+                        for (int k = 0; k < D; ++k) v[k] = v[k] + (x[k] - xi[k]) / h;
+                        constrain_velocities(S, x, v);
+                        if (want_direct) wd += particles_forces(S, x, -1, f) + kinetic_energy(S, v) - e_old;
+                    } else if (op_kind[i] == OP_V) {
+                        const double ke_old = kinetic_energy(S, v);
+                        /* forces of a group are reused until the positions change (as OpenMM caches them) */
+                        const int gi = op_group[i] + 1;
+                        if (!fcache[gi]) fcache[gi] = (double*)malloc(sizeof(double) * D);
+                        if (!fvalid[gi]) { particles_forces(S, x, op_group[i], fcache[gi]); fvalid[gi] = 1; }
+                        const double* fg = fcache[gi];
+                        for (int k = 0; k < D; ++k) v[k] = v[k] + h * fg[k] / S->mass[k / 3];
+                        constrain_velocities(S, x, v);
+                        wd += kinetic_energy(S, v) - ke_old;
+                    } else {
+                        const double ke_old = kinetic_energy(S, v);
+                        atom_normals(seed, rid, ((uint32_t)leg << 26) | q, TAG_O, N, noise_fp32, xi);
+                        ++q;
+                        for (int k = 0; k < D; ++k) v[k] = op_a[i] * v[k] + op_b[i] * sqrt(kT / S->mass[k / 3]) * xi[k];
+                        constrain_velocities(S, x, v);
+                        heat += kinetic_energy(S, v) - ke_old;
+                    }
+                }
+                const int64_t ti = tb + s + 1;
+                if (trace_x) memcpy(trace_x + ti * D, x, sizeof(double) * D);
+                if (trace_v) memcpy(trace_v + ti * D, v, sizeof(double) * D);
+                if (trace_pe) trace_pe[ti] = particles_forces(S, x, -1, f);
+                if (trace_ke) trace_ke[ti] = kinetic_energy(S, v);
+                if (trace_heat) trace_heat[ti] = heat - Q0;
+                if (trace_wdir) trace_wdir[ti] = wd;
+            }
+            pe = particles_forces(S, x, -1, f);
+            const double E1 = pe + kinetic_energy(S, v);
+            W[r * n_legs + leg] = ((E1 - E0) - (heat - Q0)) / kT;
+            if (Q) Q[r * n_legs + leg] = heat - Q0;
+            if (wdirect) wdirect[r * n_legs + leg] = wd / kT;
+        }
+        if (x_final) memcpy(x_final + r * D, x, sizeof(double) * D);
+        if (v_final) memcpy(v_final + r * D, v, sizeof(double) * D);
+        free(x); free(v); free(f); free(xu); free(xi);
+        for (int k = 0; k < 34; ++k) free(fcache[k]);
+    }
+    return rc_all;
+}

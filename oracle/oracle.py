@@ -141,3 +141,146 @@ def sample_equilibrium_scalar(potential, n, n_burn, kT=1.0, seed=0, replica0=0, 
     lib().orc_sample_equilibrium_scalar(POT[potential], p, ctypes.c_double(kT), ctypes.c_int64(n), int(n_burn),
                                         ctypes.c_uint64(seed), ctypes.c_uint64(replica0), _dp(out))
     return out
+
+
+# ----------------------------------------------------------------------------- particle systems
+c_int32_pp = ctypes.POINTER(ctypes.c_int32)
+
+
+class OrcParticles(ctypes.Structure):
+    _fields_ = [
+        ("n_atoms", ctypes.c_int32), ("mass", c_double_p), ("charge", c_double_p), ("sigma", c_double_p),
+        ("epsilon", c_double_p), ("nonbonded_method", ctypes.c_int32), ("cutoff", ctypes.c_double),
+        ("box", ctypes.c_double * 3), ("rf_dielectric", ctypes.c_double),
+        ("n_exclusions", ctypes.c_int32), ("exclusions", c_int32_pp),
+        ("n_exceptions", ctypes.c_int32), ("exception_atoms", c_int32_pp), ("exception_params", c_double_p),
+        ("n_bonds", ctypes.c_int32), ("bond_atoms", c_int32_pp), ("bond_params", c_double_p),
+        ("n_angles", ctypes.c_int32), ("angle_atoms", c_int32_pp), ("angle_params", c_double_p),
+        ("n_torsions", ctypes.c_int32), ("torsion_atoms", c_int32_pp), ("torsion_params", c_double_p),
+        ("restraint_k", ctypes.c_double),
+        ("group_nonbonded", ctypes.c_int32), ("group_bonds", ctypes.c_int32), ("group_angles", ctypes.c_int32),
+        ("group_torsions", ctypes.c_int32), ("group_restraint", ctypes.c_int32),
+        ("n_settle", ctypes.c_int32), ("settle_atoms", c_int32_pp), ("settle_oh", ctypes.c_double),
+        ("settle_hh", ctypes.c_double),
+        ("n_constraints", ctypes.c_int32), ("constraint_atoms", c_int32_pp), ("constraint_dist", c_double_p),
+        ("constraint_tolerance", ctypes.c_double),
+    ]
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a if a is not None else [], dtype=np.float64)
+    return a.reshape(shape) if shape is not None else a
+
+
+def _i32(a, cols):
+    a = np.ascontiguousarray(a if a is not None else [], dtype=np.int32)
+    return a.reshape(-1, cols)
+
+
+def make_particles(desc):
+    """desc: plain dict of arrays (see integrator_benchmark_b200.testsystems.systems.describe).
+    Returns (struct, keepalive)."""
+    keep = {}
+    S = OrcParticles()
+    n = int(desc["n_atoms"])
+    S.n_atoms = n
+    for name in ("mass", "charge", "sigma", "epsilon"):
+        keep[name] = _f64(desc.get(name, np.zeros(n)))
+        assert keep[name].shape == (n,)
+        setattr(S, name, _dp(keep[name]))
+    S.nonbonded_method = {"NoCutoff": 0, "CutoffPeriodic": 1}[desc.get("nonbonded_method", "NoCutoff")]
+    S.cutoff = float(desc.get("cutoff", 0.0))
+    box = list(desc.get("box", (0.0, 0.0, 0.0)))
+    S.box = (ctypes.c_double * 3)(*box)
+    S.rf_dielectric = float(desc.get("rf_dielectric", 78.3))
+
+    def ilist(key, cols):
+        a = _i32(desc.get(key), cols)
+        keep[key] = a
+        return len(a), a.ctypes.data_as(c_int32_pp)
+
+    def dlist(key, cols):
+        a = _f64(desc.get(key)).reshape(-1, cols) if cols else _f64(desc.get(key))
+        keep[key] = a
+        return _dp(a)
+
+    S.n_exclusions, S.exclusions = ilist("exclusions", 2)
+    S.n_exceptions, S.exception_atoms = ilist("exception_atoms", 2)
+    S.exception_params = dlist("exception_params", 3)
+    S.n_bonds, S.bond_atoms = ilist("bond_atoms", 2)
+    S.bond_params = dlist("bond_params", 2)
+    S.n_angles, S.angle_atoms = ilist("angle_atoms", 3)
+    S.angle_params = dlist("angle_params", 2)
+    S.n_torsions, S.torsion_atoms = ilist("torsion_atoms", 4)
+    S.torsion_params = dlist("torsion_params", 3)
+    S.restraint_k = float(desc.get("restraint_k", 0.0))
+    groups = desc.get("groups", {})
+    for k in ("nonbonded", "bonds", "angles", "torsions", "restraint"):
+        setattr(S, "group_" + k, int(groups.get(k, 0)))
+    S.n_settle, S.settle_atoms = ilist("settle_atoms", 3)
+    S.settle_oh = float(desc.get("settle_oh", 0.0))
+    S.settle_hh = float(desc.get("settle_hh", 0.0))
+    S.n_constraints, S.constraint_atoms = ilist("constraint_atoms", 2)
+    S.constraint_dist = dlist("constraint_dist", 0)
+    S.constraint_tolerance = float(desc.get("constraint_tolerance", 1e-8))
+    return S, keep
+
+
+def particles_energy_forces(desc, x, group=-1):
+    S, _keep = make_particles(desc)
+    x = _f64(x).reshape(-1)
+    f = np.zeros_like(x)
+    fn = lib().orc_particles_energy_forces
+    fn.restype = ctypes.c_double
+    e = fn(ctypes.byref(S), _dp(x), int(group), _dp(f))
+    return e, f.reshape(-1, 3)
+
+
+def constrain_positions(desc, x_ref, x_new):
+    S, _keep = make_particles(desc)
+    x0 = _f64(x_ref).reshape(-1).copy()
+    x1 = _f64(x_new).reshape(-1).copy()
+    lib().orc_constrain_positions(ctypes.byref(S), _dp(x0), _dp(x1))
+    return x1.reshape(-1, 3)
+
+
+def constrain_velocities(desc, x, v):
+    S, _keep = make_particles(desc)
+    x = _f64(x).reshape(-1).copy()
+    v = _f64(v).reshape(-1).copy()
+    lib().orc_constrain_velocities(ctypes.byref(S), _dp(x), _dp(v))
+    return v.reshape(-1, 3)
+
+
+def particles_protocol(desc, splitting, dt, gamma, kT, n_replicas, n_steps, marginal="configuration", seed=0,
+                       replica0=0, x_cache=None, x0=None, v0=None, n_legs=2, traces=False, want_direct=False,
+                       noise_fp32=False, round_midpoint=False, program=None):
+    prog = program or _sp.compile_splitting(splitting, dt, gamma)
+    kind, group, frac, a, b = _ops_arrays(prog)
+    S, _keep = make_particles(desc)
+    n, N = int(n_replicas), int(desc["n_atoms"])
+    W, Q = np.zeros((n, n_legs)), np.zeros((n, n_legs))
+    wd = np.zeros((n, n_legs)) if want_direct else None
+    xf, vf = np.zeros((n, N, 3)), np.zeros((n, N, 3))
+    T = n_steps + 1
+    tx = np.zeros((n, n_legs, T, N, 3)) if traces else None
+    tv = np.zeros((n, n_legs, T, N, 3)) if traces else None
+    tpe, tke, th, twd = [np.zeros((n, n_legs, T)) if traces else None for _ in range(4)]
+    xc = None if x_cache is None else _f64(x_cache).reshape(-1, N, 3)
+    x0a = None if x0 is None else _f64(x0).reshape(n, N, 3)
+    v0a = None if v0 is None else _f64(v0).reshape(n, N, 3)
+    assert xc is not None or x0a is not None
+    rc = lib().orc_particles_protocol(
+        ctypes.byref(S), ctypes.c_double(kT), len(kind), kind.ctypes.data_as(c_int32_p),
+        group.ctypes.data_as(c_int32_p), _dp(frac), _dp(a), _dp(b), ctypes.c_double(dt),
+        ctypes.c_uint64(seed), ctypes.c_uint64(replica0), ctypes.c_int64(n),
+        _dp(xc), ctypes.c_int64(0 if xc is None else len(xc)), _dp(x0a), _dp(v0a),
+        int(n_steps), MARGINAL[marginal], int(n_legs), int(bool(noise_fp32)), int(bool(round_midpoint)),
+        _dp(W), _dp(Q), _dp(wd), _dp(xf), _dp(vf), _dp(tx), _dp(tv), _dp(tpe), _dp(tke), _dp(th), _dp(twd))
+    assert rc == 0
+    out = {"W": W, "Q": Q, "x_final": xf, "v_final": vf}
+    if want_direct:
+        out["Wdirect"] = wd
+    if traces:
+        out.update(trace_x=tx, trace_v=tv, trace_pe=tpe, trace_ke=tke, trace_heat=th, trace_wdir=twd)
+    return out

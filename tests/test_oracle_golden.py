@@ -136,3 +136,101 @@ def test_splitting_compiler_matches_reference_constructor(golden_dir):
                 assert got[3] == pytest.approx(exp[3], rel=1e-15) and got[4] == pytest.approx(exp[4], rel=1e-15)
         n_checked += 1
     assert n_checked > 60
+
+
+# ----------------------------------------------------------------------------- particle oracle
+def chain_desc(z, constrained, meta):
+    bonds = z["bonds"]
+    cons = meta["constraints"] if constrained else []
+    keep = [b for b in bonds if (int(b[0]), int(b[1])) not in [(c[0], c[1]) for c in cons]]
+    return dict(n_atoms=len(z["masses"]), mass=z["masses"], restraint_k=float(z["K"]),
+                bond_atoms=[(int(b[0]), int(b[1])) for b in keep], bond_params=[(b[2], b[3]) for b in keep],
+                groups=dict(restraint=0, bonds=1, nonbonded=0, angles=1, torsions=1),
+                constraint_atoms=[(c[0], c[1]) for c in cons], constraint_dist=[c[2] for c in cons],
+                constraint_tolerance=1e-13)
+
+
+def test_particle_oracle_matches_interpreted_reference_programs(golden_dir):
+    """The reference's own CustomIntegrator step programs (recorded from langevin.py and interpreted
+    with numpy in make_golden.py) against the oracle's substep loop: R/V/V{g}/O order, constraint
+    placement, heat and shadow-work bookkeeping (langevin.py:124-175)."""
+    z = np.load(os.path.join(golden_dir, "lsi_trajectories.npz"))
+    meta = json.loads(str(z["meta"]))
+    assert len(meta) == 12
+    for m in meta:
+        k = m["key"]
+        desc = chain_desc(z, m["constrained"], m)
+        out = orc.particles_protocol(desc, m["splitting"], m["timestep"], m["collision_rate"], m["kT"], 1, m["n_steps"],
+                                     seed=m["seed"], replica0=m["replica"], x0=z[k + "_x0"][None], v0=z[k + "_v0"][None],
+                                     n_legs=1, traces=True, want_direct=True)
+        np.testing.assert_allclose(out["trace_x"][0, 0, 1:], z[k + "_x"], rtol=1e-9, atol=1e-11, err_msg=m["splitting"])
+        np.testing.assert_allclose(out["trace_v"][0, 0, 1:], z[k + "_v"], rtol=1e-8, atol=1e-10, err_msg=m["splitting"])
+        np.testing.assert_allclose(out["trace_pe"][0, 0, 1:], z[k + "_pe"], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(out["trace_ke"][0, 0, 1:], z[k + "_ke"], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(out["trace_heat"][0, 0, 1:], z[k + "_heat"], rtol=1e-8, atol=1e-8)
+        np.testing.assert_allclose(out["trace_wdir"][0, 0, 1:], z[k + "_shadow_work"], rtol=1e-8, atol=1e-8)
+        # energy bookkeeping identity of the reference's tests/test_shadow_work.py:30-42
+        dE = (out["trace_pe"][0, 0] + out["trace_ke"][0, 0]) - (out["trace_pe"][0, 0, 0] + out["trace_ke"][0, 0, 0])
+        np.testing.assert_allclose(dE - out["trace_heat"][0, 0], out["trace_wdir"][0, 0], atol=1e-6)
+
+
+def test_particle_oracle_forces_are_gradients():
+    rng = np.random.RandomState(3)
+    N = 9
+    x = rng.randn(N, 3) * 0.12 + np.repeat(np.array([[0, 0, 0], [0.35, 0, 0.1], [0, 0.4, -0.1]]), 3, axis=0)
+    desc = dict(n_atoms=N, mass=np.ones(N), charge=np.tile([-0.834, 0.417, 0.417], 3),
+                sigma=np.tile([0.315075, 0.1, 0.1], 3), epsilon=np.tile([0.635968, 0.05, 0.05], 3),
+                exclusions=[(0, 1), (0, 2), (1, 2), (3, 4), (3, 5), (4, 5), (6, 7), (6, 8), (7, 8)], restraint_k=1.5,
+                bond_atoms=[(0, 1), (0, 2)], bond_params=[(0.09572, 462750.4)] * 2,
+                angle_atoms=[(1, 0, 2)], angle_params=[(1.82421813, 836.8)],
+                torsion_atoms=[(1, 0, 3, 4), (2, 0, 3, 5)], torsion_params=[(3, 0.3, 5.0), (2, 3.14159, 2.5)],
+                exception_atoms=[(1, 4)], exception_params=[(0.1, 0.25, 0.3)])
+    for extra in [{}, dict(nonbonded_method="CutoffPeriodic", cutoff=0.45, box=(1.1, 1.2, 1.3))]:
+        d = dict(desc, **extra)
+        e, f = orc.particles_energy_forces(d, x)
+        h = 1e-6
+        for i in range(N):
+            for c in range(3):
+                xp, xm = x.copy(), x.copy()
+                xp[i, c] += h
+                xm[i, c] -= h
+                fd = -(orc.particles_energy_forces(d, xp)[0] - orc.particles_energy_forces(d, xm)[0]) / (2 * h)
+                assert abs(fd - f[i, c]) < 2e-5 * max(1.0, abs(fd)), (extra, i, c, fd, f[i, c])
+
+
+def test_settle_equals_converged_shake():
+    """analytic SETTLE (positions) and the triangle velocity projection solve the same equations as
+    SHAKE / RATTLE iterated to machine precision on the three edges."""
+    rng = np.random.RandomState(5)
+    oh, hh, mO, mH = 0.09572, 0.15139, 15.99943, 1.007947
+    s, c = hh / 2, np.sqrt(oh ** 2 - (hh / 2) ** 2)
+    tri = np.array([[0, 0, 0], [s, c, 0], [-s, c, 0]])
+    xs = []
+    for w in range(4):
+        R = np.linalg.qr(rng.randn(3, 3))[0]
+        xs.append(tri @ R.T + rng.randn(3) * 0.4)
+    x0 = np.concatenate(xs)
+    n = len(x0)
+    mass = np.tile([mO, mH, mH], 4)
+    settle = dict(n_atoms=n, mass=mass, settle_atoms=[(3 * w, 3 * w + 1, 3 * w + 2) for w in range(4)], settle_oh=oh, settle_hh=hh)
+    cons = []
+    for w in range(4):
+        cons += [(3 * w, 3 * w + 1, oh), (3 * w, 3 * w + 2, oh), (3 * w + 1, 3 * w + 2, hh)]
+    shake = dict(n_atoms=n, mass=mass, constraint_atoms=[(a, b) for a, b, _ in cons], constraint_dist=[d for _, _, d in cons],
+                 constraint_tolerance=1e-15)
+    x1 = x0 + 0.006 * rng.randn(n, 3)
+    a, b = orc.constrain_positions(settle, x0, x1), orc.constrain_positions(shake, x0, x1)
+    np.testing.assert_allclose(a, b, atol=1e-13)
+    v = rng.randn(n, 3)
+    np.testing.assert_allclose(orc.constrain_velocities(settle, a, v), orc.constrain_velocities(shake, a, v), atol=1e-12)
+
+
+def test_waterbox_fixture_geometry(golden_dir):
+    """data/tiny_waterbox_constrained_samples.h5: 4 frames x 102 rigid TIP3P waters."""
+    z = np.load(os.path.join(golden_dir, "waterbox_frames.npz"))
+    xyz = z["xyz"].astype(np.float64)
+    assert xyz.shape == (4, 306, 3)
+    oh1 = np.linalg.norm(xyz[:, 1::3] - xyz[:, 0::3], axis=-1)
+    hh = np.linalg.norm(xyz[:, 1::3] - xyz[:, 2::3], axis=-1)
+    assert np.abs(oh1 - 0.09572).max() < 2e-6 and np.abs(hh - 0.15139).max() < 2e-6
+    np.testing.assert_allclose(z["potential_energy"], [-4136.6406, -4029.0005, -4030.8572, -4068.7595], atol=1e-3)
