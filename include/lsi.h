@@ -112,6 +112,64 @@ void lsi_program_destroy(lsi_program* p);
 /* ------------------------------------------------------------------ systems */
 /* 1-DOF toy systems (NumbaBookkeepingSimulator, low_dimensional_systems.py:52-76) */
 int lsi_system_create_scalar(int potential_kind, const double params[4], double mass, lsi_system** out);
+
+/* Particle systems.  The description mirrors the OpenMM System objects the reference builds in
+ * benchmark/testsystems/{watercluster.py:10-84, waterbox.py:36-48, alanine_dipeptide.py:12-21}:
+ * NonbondedForce (Lennard-Jones, Lorentz-Berthelot combination, Coulomb constant 138.935456;
+ * NoCutoff, or CutoffPeriodic = minimum image + reaction field with `rf_dielectric`, plain LJ
+ * truncation), its exclusions and 1-4 exceptions, HarmonicBondForce 1/2 k (r - r0)^2,
+ * HarmonicAngleForce 1/2 k (theta - theta0)^2, PeriodicTorsionForce k (1 + cos(n phi - phase)),
+ * the restraint (K/2) |x|^2 on every atom (watercluster.py:70-80), force-group ids per force
+ * class ("Nonbonded -> 0, else -> 1", experiments/submission_scripts/4_mts_integrator_splittings.py:36-42),
+ * rigid three-site waters (SETTLE) and pair distance constraints (HBonds), tolerance as
+ * CustomIntegrator.setConstraintTolerance (langevin.py:202).  Masses are plain numbers, so
+ * hydrogen-mass repartitioning (utilities/openmm_utilities.py:223-269) is a different `mass`.
+ * All arrays are HOST pointers and are copied; device tables are built on first use. */
+#define LSI_NB_NOCUTOFF 0
+#define LSI_NB_CUTOFF_PERIODIC 1
+typedef struct lsi_particles_desc {
+    int32_t n_atoms;
+    const double* mass;    /* [n_atoms] amu */
+    const double* charge;  /* [n_atoms] e */
+    const double* sigma;   /* [n_atoms] nm */
+    const double* epsilon; /* [n_atoms] kJ/mol */
+    int32_t nonbonded_method;
+    double cutoff; /* nm */
+    double box[3]; /* orthorhombic box edge lengths, nm */
+    double rf_dielectric;
+    int32_t n_exclusions;
+    const int32_t* exclusions; /* [n][2] */
+    int32_t n_exceptions;
+    const int32_t* exception_atoms;  /* [n][2] */
+    const double* exception_params;  /* [n][3] chargeProd (e^2), sigma, epsilon */
+    int32_t n_bonds;
+    const int32_t* bond_atoms;  /* [n][2] */
+    const double* bond_params;  /* [n][2] r0, k */
+    int32_t n_angles;
+    const int32_t* angle_atoms; /* [n][3] */
+    const double* angle_params; /* [n][2] theta0 (rad), k */
+    int32_t n_torsions;
+    const int32_t* torsion_atoms; /* [n][4] */
+    const double* torsion_params; /* [n][3] periodicity, phase (rad), k */
+    double restraint_k;
+    int32_t group_nonbonded, group_bonds, group_angles, group_torsions, group_restraint;
+    int32_t n_settle;
+    const int32_t* settle_atoms; /* [n][3] O, H1, H2 */
+    double settle_oh, settle_hh;
+    int32_t n_constraints;
+    const int32_t* constraint_atoms; /* [n][2] */
+    const double* constraint_dist;   /* [n] nm */
+    double constraint_tolerance;
+} lsi_particles_desc;
+
+int lsi_system_create_particles(const lsi_particles_desc* desc, lsi_system** out);
+/* potential energy (kJ/mol) and forces of force group `group` (-1 = all) for n configurations:
+ * x [n][n_atoms][3] -> energy [n], forces [n][n_atoms][3] (either output may be NULL); device
+ * pointers.  Replaces Context.getState(getEnergy / getForces) as used by
+ * utilities/openmm_utilities.py:10-18. */
+int lsi_particles_energy_forces(const lsi_system* sys, int32_t precision, int32_t group, int64_t n,
+                                const double* x, double* energy, double* forces, void* stream);
+
 void lsi_system_destroy(lsi_system* s);
 int lsi_system_num_dof(const lsi_system* s);
 
@@ -126,6 +184,8 @@ int lsi_system_num_dof(const lsi_system* s);
  *   leg l>0: x continues; v is redrawn from TAG_VMID (configuration) or kept (full)
  *   each leg applies the program n_steps times and yields
  *          W = ((E_end - E_start) - (heat_end - heat_start)) / kT
+ * Particle systems: states are [replica][atom][3] (x_cache [n_cache][atom][3]); before each leg
+ * positions then velocities are projected onto the constraints (bookkeepers.py:206-208).
  * Outputs are leg-major so that warps write coalesced: W[leg * n_replicas + r].
  * Optional outputs may be NULL.  Traces hold n_steps + 1 entries per leg (entry 0 is the
  * leg start): trace[(leg * (n_steps + 1) + s) * n_replicas + r]; trace_w is cumulative
@@ -134,6 +194,9 @@ int lsi_system_num_dof(const lsi_system* s);
  * finite: {count, sum wF, sum wR, sum wF^2, sum wR^2, sum wF wR, count_nonfinite, 0};
  * it needs n_legs == 2.  Scratch for the block partials is taken from `workspace`
  * (device, at least lsi_protocol_workspace_bytes(n_replicas) bytes). */
+/* flags: positions pass through a float32 frame at the midpoint, as the reference's mdtraj
+ * round trip does (bookkeepers.py:266,298-305).  Particle systems only. */
+#define LSI_FLAG_ROUND_MIDPOINT_X_FP32 1
 typedef struct lsi_protocol_args {
     uint64_t seed;
     uint64_t replica0;
@@ -142,6 +205,8 @@ typedef struct lsi_protocol_args {
     int32_t n_legs;
     int32_t marginal;
     int32_t precision;
+    int32_t flags; /* LSI_FLAG_* */
+    int32_t reserved;
     double kT;
     /* inputs (device) */
     const double* x_cache;

@@ -30,12 +30,36 @@ class ProtocolArgs(ctypes.Structure):
     _fields_ = [
         ("seed", ctypes.c_uint64), ("replica0", ctypes.c_uint64), ("n_replicas", ctypes.c_int64),
         ("n_steps", ctypes.c_int32), ("n_legs", ctypes.c_int32), ("marginal", ctypes.c_int32),
-        ("precision", ctypes.c_int32), ("kT", ctypes.c_double),
+        ("precision", ctypes.c_int32), ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32), ("kT", ctypes.c_double),
         ("x_cache", ctypes.c_void_p), ("n_cache", ctypes.c_int64), ("x0", ctypes.c_void_p), ("v0", ctypes.c_void_p),
         ("W", ctypes.c_void_p), ("heat", ctypes.c_void_p), ("W_direct", ctypes.c_void_p),
         ("x_final", ctypes.c_void_p), ("v_final", ctypes.c_void_p),
         ("trace_x", ctypes.c_void_p), ("trace_v", ctypes.c_void_p), ("trace_w", ctypes.c_void_p),
         ("moments", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
+    ]
+
+
+c_int32_pp = ctypes.POINTER(ctypes.c_int32)
+
+
+class ParticlesDesc(ctypes.Structure):
+    """struct lsi_particles_desc (include/lsi.h)"""
+    _fields_ = [
+        ("n_atoms", ctypes.c_int32), ("mass", c_double_p), ("charge", c_double_p), ("sigma", c_double_p),
+        ("epsilon", c_double_p), ("nonbonded_method", ctypes.c_int32), ("cutoff", ctypes.c_double),
+        ("box", ctypes.c_double * 3), ("rf_dielectric", ctypes.c_double),
+        ("n_exclusions", ctypes.c_int32), ("exclusions", c_int32_pp),
+        ("n_exceptions", ctypes.c_int32), ("exception_atoms", c_int32_pp), ("exception_params", c_double_p),
+        ("n_bonds", ctypes.c_int32), ("bond_atoms", c_int32_pp), ("bond_params", c_double_p),
+        ("n_angles", ctypes.c_int32), ("angle_atoms", c_int32_pp), ("angle_params", c_double_p),
+        ("n_torsions", ctypes.c_int32), ("torsion_atoms", c_int32_pp), ("torsion_params", c_double_p),
+        ("restraint_k", ctypes.c_double),
+        ("group_nonbonded", ctypes.c_int32), ("group_bonds", ctypes.c_int32), ("group_angles", ctypes.c_int32),
+        ("group_torsions", ctypes.c_int32), ("group_restraint", ctypes.c_int32),
+        ("n_settle", ctypes.c_int32), ("settle_atoms", c_int32_pp), ("settle_oh", ctypes.c_double),
+        ("settle_hh", ctypes.c_double),
+        ("n_constraints", ctypes.c_int32), ("constraint_atoms", c_int32_pp), ("constraint_dist", c_double_p),
+        ("constraint_tolerance", ctypes.c_double),
     ]
 
 
@@ -65,6 +89,8 @@ def _load():
         "lsi_program_flags": (i32, [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]),
         "lsi_program_destroy": (None, [vp]),
         "lsi_system_create_scalar": (i32, [i32, c_double_p, dbl, ctypes.POINTER(vp)]),
+        "lsi_system_create_particles": (i32, [ctypes.POINTER(ParticlesDesc), ctypes.POINTER(vp)]),
+        "lsi_particles_energy_forces": (i32, [vp, ctypes.c_int32, ctypes.c_int32, i64, vp, vp, vp, vp]),
         "lsi_system_destroy": (None, [vp]),
         "lsi_system_num_dof": (i32, [vp]),
         "lsi_protocol_workspace_bytes": (i64, [i64]),

@@ -110,13 +110,114 @@ class ScalarSystem:
     n_dof = 1
 
 
+class ParticleSystem:
+    """Particle system (lsi_system*, LSI_SYS_PARTICLES) built from a plain description dict:
+
+        n_atoms, mass, charge, sigma, epsilon,
+        nonbonded_method ("NoCutoff" | "CutoffPeriodic"), cutoff, box, rf_dielectric,
+        exclusions (n,2), exception_atoms (n,2), exception_params (n,3: chargeProd, sigma, epsilon),
+        bond_atoms (n,2), bond_params (n,2: r0, k), angle_atoms (n,3), angle_params (n,2: theta0, k),
+        torsion_atoms (n,4), torsion_params (n,3: periodicity, phase, k), restraint_k,
+        groups {nonbonded, bonds, angles, torsions, restraint -> force group id},
+        settle_atoms (n,3: O, H1, H2), settle_oh, settle_hh,
+        constraint_atoms (n,2), constraint_dist (n,), constraint_tolerance
+
+    (OpenMM units).  The same dict is what testsystems/*.py produce for the reference's systems."""
+
+    def __init__(self, desc):
+        self.desc = dict(desc)
+        n = int(desc["n_atoms"])
+        keep = []
+        d = _cabi.ParticlesDesc()
+        d.n_atoms = n
+
+        def dbl(key, cols=None, default=None):
+            a = desc.get(key, default)
+            a = np.ascontiguousarray([] if a is None else a, dtype=np.float64)
+            if cols:
+                a = a.reshape(-1, cols)
+            keep.append(a)
+            return a, a.ctypes.data_as(_cabi.c_double_p)
+
+        def i32(key, cols):
+            a = np.ascontiguousarray(desc.get(key) if desc.get(key) is not None else [], dtype=np.int32).reshape(-1, cols)
+            keep.append(a)
+            return a, a.ctypes.data_as(_cabi.c_int32_pp)
+
+        for name, default in (("mass", None), ("charge", np.zeros(n)), ("sigma", np.ones(n)), ("epsilon", np.zeros(n))):
+            a, ptr = dbl(name, default=default)
+            if a.shape != (n,):
+                raise ValueError("%s must have shape (n_atoms,)" % name)
+            setattr(d, name, ptr)
+        d.nonbonded_method = {"NoCutoff": 0, "CutoffPeriodic": 1}[desc.get("nonbonded_method", "NoCutoff")]
+        d.cutoff = float(desc.get("cutoff", 0.0))
+        d.box = (ctypes.c_double * 3)(*[float(b) for b in desc.get("box", (0.0, 0.0, 0.0))])
+        d.rf_dielectric = float(desc.get("rf_dielectric", 78.3))
+        a, d.exclusions = i32("exclusions", 2)
+        d.n_exclusions = len(a)
+        a, d.exception_atoms = i32("exception_atoms", 2)
+        d.n_exceptions = len(a)
+        b, d.exception_params = dbl("exception_params", 3)
+        assert len(a) == len(b)
+        for kind, cols, pcols in (("bond", 2, 2), ("angle", 3, 2), ("torsion", 4, 3)):
+            a, ptr = i32(kind + "_atoms", cols)
+            b, pptr = dbl(kind + "_params", pcols)
+            if len(a) != len(b):
+                raise ValueError("%s_atoms and %s_params disagree" % (kind, kind))
+            setattr(d, "n_%ss" % kind, len(a))
+            setattr(d, kind + "_atoms", ptr)
+            setattr(d, kind + "_params", pptr)
+        d.restraint_k = float(desc.get("restraint_k", 0.0))
+        groups = desc.get("groups", {})
+        for k in ("nonbonded", "bonds", "angles", "torsions", "restraint"):
+            setattr(d, "group_" + k, int(groups.get(k, 0)))
+        a, d.settle_atoms = i32("settle_atoms", 3)
+        d.n_settle = len(a)
+        d.settle_oh = float(desc.get("settle_oh", 0.0))
+        d.settle_hh = float(desc.get("settle_hh", 0.0))
+        a, d.constraint_atoms = i32("constraint_atoms", 2)
+        d.n_constraints = len(a)
+        b, d.constraint_dist = dbl("constraint_dist")
+        assert len(a) == len(b)
+        d.constraint_tolerance = float(desc.get("constraint_tolerance", 1e-8))
+        h = ctypes.c_void_p()
+        check(lib.lsi_system_create_particles(ctypes.byref(d), ctypes.byref(h)))
+        self._h = h
+        self.n_atoms = n
+        self.n_dof = 3 * n
+        self.mass = np.array(desc["mass"], dtype=np.float64)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.lsi_system_destroy(h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def energy_forces(self, x, group=-1, precision="double", want_forces=True):
+        """potential energy [n] and forces [n, N, 3] (CUDA tensors) of configurations x [n, N, 3]."""
+        require_cuda()
+        t = torch()
+        x = _to_cuda64(x).reshape(-1, self.n_atoms, 3)
+        n = x.shape[0]
+        e = t.empty(n, dtype=t.float64, device=x.device)
+        f = t.empty_like(x) if want_forces else None
+        with t.cuda.device(x.device):
+            check(lib.lsi_particles_energy_forces(self._h, _cabi.PRECISION[precision], int(group), n, _ptr(x), _ptr(e),
+                                                  _ptr(f), current_stream_ptr()))
+        return e, f
+
+
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
 def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configuration", n_legs=2, seed=0,
                  replica0=0, x_cache=None, x0=None, v0=None, precision="double", want_heat=False,
-                 want_direct=False, want_final=False, traces=False, want_moments=True, device=None, out=None):
+                 want_direct=False, want_final=False, traces=False, want_moments=True, device=None, out=None,
+                 round_midpoint=False):
     """One launch of the whole protocol for `n_replicas` replicas (lsi_run_protocol).
 
     Tensors in/out are float64 CUDA tensors; outputs are leg-major: W[leg, replica],
@@ -143,8 +244,10 @@ def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configurati
         return a.to(device=dev, dtype=t.float64).contiguous()
 
     x_cache, x0, v0 = as_dev(x_cache), as_dev(x0), as_dev(v0)
-    state_shape = (n,) if dof == 1 else (n, dof)
+    scalar = isinstance(system, ScalarSystem)
+    state_shape = (n,) if scalar else (n, dof // 3, 3)
     a = _cabi.ProtocolArgs()
+    a.flags = 1 if (round_midpoint and not scalar) else 0
     a.seed, a.replica0, a.n_replicas = int(seed), int(replica0), n
     a.n_steps, a.n_legs = int(n_steps), int(n_legs)
     if marginal not in _cabi.MARGINAL:
@@ -162,11 +265,11 @@ def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configurati
         a.x_final = _ptr(buf("x_final", *state_shape))
         a.v_final = _ptr(buf("v_final", *state_shape))
     if traces:
-        tshape = (n_legs, n_steps + 1, n) if dof == 1 else (n_legs, n_steps + 1, n, dof)
+        tshape = (n_legs, n_steps + 1, n) if scalar else (n_legs, n_steps + 1, n, dof // 3, 3)
         a.trace_x = _ptr(buf("trace_x", *tshape))
         a.trace_v = _ptr(buf("trace_v", *tshape))
         a.trace_w = _ptr(buf("trace_w", n_legs, n_steps + 1, n))
-    if want_moments and n_legs == 2:
+    if want_moments and n_legs == 2 and scalar:
         a.moments = _ptr(buf("moments", 8))
         nbytes = lib.lsi_protocol_workspace_bytes(n)
         ws = out.get("_workspace")
@@ -177,6 +280,14 @@ def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configurati
     out["_keepalive"] = (x_cache, x0, v0)
     with t.cuda.device(dev):
         check(lib.lsi_run_protocol(system.handle, program.handle, ctypes.byref(a), current_stream_ptr()))
+        if want_moments and n_legs == 2 and not scalar and n > 0:
+            m = buf("moments", 8)
+            ws = out.get("_workspace")
+            if ws is None or ws.numel() < 1024 * 8 or ws.device != dev:
+                ws = t.empty(1024 * 8, dtype=t.float64, device=dev)
+                out["_workspace"] = ws
+            check(lib.lsi_reduce_moments(_ptr(out["W"][0]), _ptr(out["W"][1]), n, _ptr(m), _ptr(ws), ws.numel() * 8,
+                                         current_stream_ptr()))
     return out
 
 
