@@ -54,47 +54,59 @@ def flops_per_step(splitting):
     return 9 * toks.count("O") + 2 * toks.count("V") + 2 * toks.count("R") + F_FORCE_DW * n_evals
 
 
-def clocks_sampler_start():
-    f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-    try:
-        p = subprocess.Popen(["nvidia-smi", "--query-gpu=index,clocks.sm,clocks.max.sm,power.draw,"
-                              "clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-                              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                              "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
-                             stdout=f, stderr=subprocess.DEVNULL)
-    except OSError:
-        return None, f.name
-    return p, f.name
+class ClockSampler:
+    """SM clock + clock-event reasons sampled DURING the timed region (NVML from a thread, every
+    ~2 ms; the nvidia-smi -lms loop of the profiling recipe cannot resolve a region this short)."""
 
+    def __init__(self, gpu_index=0, period_s=0.002):
+        import threading
+        self.rows, self.marks, self._stop = [], [], threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            return
+        self.period = period_s
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-def clocks_sampler_stop(p, path, gpu_index=0):
-    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-    if p is not None:
-        p.terminate()
-        try:
-            p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            p.kill()
-    try:
-        rows = [r.split(",") for r in open(path).read().strip().splitlines() if r.strip()]
-        rows = [[c.strip() for c in r] for r in rows if len(r) >= 9 and r[0].strip() == str(gpu_index)]
-        sm = [float(r[1]) for r in rows]
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-            out["sm_max_mhz"] = float(rows[0][2])
-            out["samples"] = len(sm)
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for j, nm in enumerate(names):
-                if any(r[5 + j].lower().startswith("active") for r in rows):
-                    out["reasons"].append(nm)
-    except Exception:  # noqa: BLE001
-        pass
-    finally:
-        try:
-            os.unlink(path)
-        except OSError:
-            pass
-    return out
+    def _run(self):
+        nv = self.nv
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                  int(reasons_fn(self.h))))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml"}
+        if not self.ok:
+            return out
+        self._stop.set()
+        self.t.join(timeout=2)
+        lo, hi = (self.marks[0], self.marks[-1]) if len(self.marks) >= 2 else (0.0, 1e30)
+        rows = [r for r in self.rows if lo <= r[0] <= hi]
+        out["sm_max_mhz"] = self.max_mhz
+        if rows:
+            out["sm_mhz"] = float(np.median([r[1] for r in rows]))
+            out["samples"] = len(rows)
+            bits = 0
+            for r in rows:
+                bits |= r[2]
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            out["reasons"] = [n for b, n in names.items() if bits & b]
+        return out
 
 
 def cpu_port_throughput(n_replicas, protocol_length, repeats=1):
@@ -158,8 +170,8 @@ def workload_config(args, n_per_gpu):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=1 << 20, help="replicas per GPU")
     ap.add_argument("--protocol-length", type=int, default=10)
@@ -214,9 +226,11 @@ def main():
     barrier()
 
     # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed (untimed) in between
-    sampler, path = clocks_sampler_start() if rank == 0 else (None, None)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    if sampler:
+        sampler.mark()
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
         flush.zero_()
@@ -225,8 +239,10 @@ def main():
         ev[s][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    if sampler:
+        sampler.mark()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = clocks_sampler_stop(sampler, path, local_rank) if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

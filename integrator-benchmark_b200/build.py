@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building liblsi.so")
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart", "-ccbin",
+    subprocess.check_call([_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ccbin",
                           "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"])
     return LIB
 

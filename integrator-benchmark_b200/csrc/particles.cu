@@ -220,6 +220,19 @@ __device__ __forceinline__ void load_lj(const PKParams& P, const Smem<real>& s)
     }
 }
 
+// minimum image of a displacement (positions are staged wrapped into the box, so every bonded
+// displacement needs it too; equals the unwrapped displacement OpenMM's bonded forces use as long as
+// bonded atoms are closer than half a box edge)
+template <typename real, bool PERIODIC>
+__device__ __forceinline__ void min_image(const PKParams& P, real& dx, real& dy, real& dz)
+{
+    if (PERIODIC) {
+        dx -= (real)P.box[0] * rint_(dx * (real)P.inv_box[0]);
+        dy -= (real)P.box[1] * rint_(dy * (real)P.inv_box[1]);
+        dz -= (real)P.box[2] * rint_(dz * (real)P.inv_box[2]);
+    }
+}
+
 // gradient pieces of one bonded term / exception for the atom in `role`; energy returned in full
 template <typename real, bool PERIODIC>
 __device__ __forceinline__ real term_force(const PKParams& P, const Smem<real>& s, const TermInst& t, real& fx,
@@ -228,11 +241,7 @@ __device__ __forceinline__ real term_force(const PKParams& P, const Smem<real>& 
     const typename R4<real>::type p0 = s.xq[t.a[0]], p1 = s.xq[t.a[1]];
     if (t.kind == TERM_BOND || t.kind == TERM_EXCEPTION) {
         real dx = p1.x - p0.x, dy = p1.y - p0.y, dz = p1.z - p0.z;  // from atom 0 to atom 1
-        if (PERIODIC) {
-            dx -= (real)P.box[0] * rint_(dx * (real)P.inv_box[0]);
-            dy -= (real)P.box[1] * rint_(dy * (real)P.inv_box[1]);
-            dz -= (real)P.box[2] * rint_(dz * (real)P.inv_box[2]);
-        }
+        min_image<real, PERIODIC>(P, dx, dy, dz);
         const real r2 = dx * dx + dy * dy + dz * dz;
         real fr, e;
         if (t.kind == TERM_BOND) {
@@ -254,8 +263,10 @@ __device__ __forceinline__ real term_force(const PKParams& P, const Smem<real>& 
     }
     const typename R4<real>::type p2 = s.xq[t.a[2]];
     if (t.kind == TERM_ANGLE) {
-        const real ax = p0.x - p1.x, ay = p0.y - p1.y, az = p0.z - p1.z;
-        const real bx = p2.x - p1.x, by = p2.y - p1.y, bz = p2.z - p1.z;
+        real ax = p0.x - p1.x, ay = p0.y - p1.y, az = p0.z - p1.z;
+        real bx = p2.x - p1.x, by = p2.y - p1.y, bz = p2.z - p1.z;
+        min_image<real, PERIODIC>(P, ax, ay, az);
+        min_image<real, PERIODIC>(P, bx, by, bz);
         const real ra2 = ax * ax + ay * ay + az * az, rb2 = bx * bx + by * by + bz * bz;
         const real ira = rsqrt_(ra2), irb = rsqrt_(rb2);
         real ct = (ax * bx + ay * by + az * bz) * ira * irb;
@@ -278,9 +289,12 @@ __device__ __forceinline__ real term_force(const PKParams& P, const Smem<real>& 
     }
     // periodic torsion
     const typename R4<real>::type p3 = s.xq[t.a[3]];
-    const real b1x = p1.x - p0.x, b1y = p1.y - p0.y, b1z = p1.z - p0.z;
-    const real b2x = p2.x - p1.x, b2y = p2.y - p1.y, b2z = p2.z - p1.z;
-    const real b3x = p3.x - p2.x, b3y = p3.y - p2.y, b3z = p3.z - p2.z;
+    real b1x = p1.x - p0.x, b1y = p1.y - p0.y, b1z = p1.z - p0.z;
+    real b2x = p2.x - p1.x, b2y = p2.y - p1.y, b2z = p2.z - p1.z;
+    real b3x = p3.x - p2.x, b3y = p3.y - p2.y, b3z = p3.z - p2.z;
+    min_image<real, PERIODIC>(P, b1x, b1y, b1z);
+    min_image<real, PERIODIC>(P, b2x, b2y, b2z);
+    min_image<real, PERIODIC>(P, b3x, b3y, b3z);
     const real n1x = b1y * b2z - b1z * b2y, n1y = b1z * b2x - b1x * b2z, n1z = b1x * b2y - b1y * b2x;
     const real n2x = b2y * b3z - b2z * b3y, n2y = b2z * b3x - b2x * b3z, n2z = b2x * b3y - b2y * b3x;
     const real b2sq = b2x * b2x + b2y * b2y + b2z * b2z;
@@ -703,6 +717,7 @@ __global__ void __launch_bounds__(512) particles_protocol_kernel(const __grid_co
                     if (P.has_constraints) {
                         __syncthreads();
                         constrain_velocities(P, s.x, s.v);
+                        __syncthreads();  // projections are written per water / cluster, read per atom
                     }
                     heat += kinetic_energy(P, s.v, s.red) - ke_old;
                 }
