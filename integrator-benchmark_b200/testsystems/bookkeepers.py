@@ -1,0 +1,233 @@
+"""Drop-in for benchmark/testsystems/bookkeepers.py:45-320 (molecular systems).
+
+`EquilibriumSimulator` owns a system description and its equilibrium-configuration cache;
+`NonequilibriumSimulator` runs the forward / reverse protocol and returns shadow works.  The
+reference drives one OpenMM Context from a Python loop over protocol samples; here the whole
+ensemble of `n_protocol_samples` replicas is ONE launch of the fused protocol kernel
+(lsi_run_protocol), each replica keyed by its global id.  There is no OpenMM, no mdtraj and no
+CPU path: frames are plain (n_atoms, 3) arrays in nm (an object with an `.xyz` attribute, as an
+mdtraj frame has, is accepted too).
+"""
+import numpy as np
+
+from .. import _rngstate, engine, unit
+from ..constants import kB
+
+
+def _frame_xyz(frame):
+    xyz = getattr(frame, "xyz", frame)
+    xyz = np.asarray(xyz.value_in_unit(unit.nanometer) if unit.is_quantity(xyz) else xyz, dtype=np.float64)
+    if xyz.ndim == 3:
+        if xyz.shape[0] != 1:
+            raise TypeError("Expected length-1 frame, got length {}".format(xyz.shape[0]))
+        xyz = xyz[0]
+    return xyz
+
+
+class EquilibriumSimulator:
+    """Equilibrium side of a molecular test system (reference :45-156).
+
+    `system` is the plain description dict of testsystems/systems.py (the counterpart of the OpenMM
+    System the reference passes); `platform` and `topology` are carried for callers that read them."""
+
+    def __init__(self, platform, topology, system, positions, temperature, timestep, burn_in_length, n_samples,
+                 thinning_interval, name):
+        self.platform = platform
+        self.topology = topology
+        self.system = system
+        self.positions = np.asarray(positions, dtype=np.float64)
+        self.temperature = temperature
+        self.timestep = timestep
+        self.burn_in_length = burn_in_length
+        self.n_samples = n_samples
+        self.thinning_interval = thinning_interval
+        self.name = name
+        self.cached = False
+        self.constraint_tolerance = 1e-8
+        self.steps_per_hmc = 10
+        self.kT = self.temperature * kB
+        self.samples = None
+        self._samples_dev = None
+        self._engine_system = None
+        # sampler settings (GPU Langevin equilibration; see collect_equilibrium_samples)
+        self.equilibration_collision_rate = 5.0  # 1/ps
+        self.max_equilibration_steps = 20000
+
+    # ---- engine handles
+    @property
+    def kT_value(self):
+        return self.kT.value_in_unit(unit.kilojoule_per_mole) if unit.is_quantity(self.kT) else float(self.kT)
+
+    def engine_system(self):
+        if self._engine_system is None:
+            desc = dict(self.system)
+            desc["constraint_tolerance"] = self.constraint_tolerance
+            self._engine_system = engine.ParticleSystem(desc)
+        return self._engine_system
+
+    # ---- equilibrium cache
+    def collect_equilibrium_samples(self, seed=None):
+        """x ~ pi for the cache.  The reference runs one XC-GHMC chain (steps_per_hmc = 10, 15 extra
+        chances) and keeps every `thinning_interval`-th state (:66-113).  Here `n_samples` INDEPENDENT
+        replicas start from `positions`, relax with a short small-step high-friction Langevin leg, then run
+        VRORV Langevin dynamics at `timestep` for min(burn_in_length, max_equilibration_steps) steps; the
+        final configurations are the cache.  (Langevin samples carry the O(dt^2) configuration bias that
+        this package measures -- ~1e-4 kT at 1 fs for rigid water; the Metropolised
+        sampler is the "next" row 8f-1 of the scope table.)  Returns (n_samples, n_atoms, 3) in nm."""
+        engine.require_cuda()
+        t = engine.torch()
+        system = self.engine_system()
+        n = int(self.n_samples)
+        seed = _rngstate.get_seed() if seed is None else int(seed)
+        dt = self.timestep.value_in_unit(unit.picosecond) if unit.is_quantity(self.timestep) else float(self.timestep)
+        x = t.as_tensor(np.ascontiguousarray(self.positions))[None].expand(n, -1, -1).contiguous().cuda()
+        stages = [(0.1 * dt, 100.0, 500), (0.5 * dt, 20.0, 500),
+                  (dt, self.equilibration_collision_rate, int(min(self.burn_in_length, self.max_equilibration_steps)))]
+        for k, (h, gamma, n_steps) in enumerate(stages):
+            prog = engine.Program("V R O R V", h, gamma)
+            res = engine.run_protocol(system, prog, n, n_steps, self.kT_value, n_legs=1, seed=seed + 7919 * (k + 1),
+                                      replica0=0, x0=x, want_final=True, want_moments=False, precision="double")
+            x = res["x_final"]
+        ok = t.isfinite(x).all(dim=(1, 2))
+        if not bool(ok.all()):
+            x = x[ok]
+        self._samples_dev = x.contiguous()
+        self.samples = self._samples_dev.cpu().numpy()
+        self.cached = True
+        return self.samples
+
+    def load_or_simulate_samples(self):
+        if not self.cached:
+            self.collect_equilibrium_samples()
+
+    def set_samples(self, samples):
+        """Install an externally produced cache, e.g. the frames of the reference's
+        data/tiny_waterbox_constrained_samples.h5 (tests/golden/waterbox_frames.npz)."""
+        xyz = np.asarray(getattr(samples, "xyz", samples), dtype=np.float64)
+        self.samples = np.ascontiguousarray(xyz[None] if xyz.ndim == 2 else xyz)
+        self._samples_dev = None
+        self.cached = True
+
+    def samples_device(self):
+        self.load_or_simulate_samples()
+        if self._samples_dev is None:
+            self._samples_dev = engine.torch().as_tensor(self.samples).cuda()
+        return self._samples_dev
+
+    def sample_x_from_equilibrium(self):
+        """Draw sample (uniformly, with replacement) from cache of configuration samples (:127-131)"""
+        self.load_or_simulate_samples()
+        return self.samples[np.random.randint(len(self.samples))]
+
+    def sample_v_given_x(self, x, seed=None):
+        """Maxwell-Boltzmann velocities projected onto the velocity constraints at x (:133-140)."""
+        return _sample_v(self, x, self.constraint_tolerance, seed)
+
+
+def _sample_v(eq, x, tol, seed=None):
+    system = eq.engine_system()
+    prog = engine.Program("V R O R V", 0.001, 1.0)
+    seed = _rngstate.get_seed() if seed is None else int(seed)
+    rid = _rngstate.reserve_replicas(1)
+    res = engine.run_protocol(system, prog, 1, 0, eq.kT_value, n_legs=1, seed=seed, replica0=rid,
+                              x0=_frame_xyz(x)[None], want_final=True, want_moments=False)
+    return res["v_final"][0].cpu().numpy() * (unit.nanometer / unit.picosecond)
+
+
+class NonequilibriumSimulator:
+    """Nonequilibrium simulator, supporting shadow_work accumulation, and drawing x, v, from
+    equilibrium (reference :159-295)."""
+
+    def __init__(self, equilibrium_simulator, integrator, precision="mixed", round_midpoint=True):
+        self.equilibrium_simulator, self.integrator = equilibrium_simulator, integrator
+        self.constraint_tolerance = self.integrator.getConstraintTolerance()
+        # "mixed" mirrors how the reference configures OpenMM's CUDA platform
+        # (testsystems/configuration.py:42-45); "double" mirrors the Reference platform
+        self.precision = precision
+        # positions pass through a float32 frame between the legs, as in the reference (:266,298-305)
+        self.round_midpoint = round_midpoint
+        self._buffers = {}
+        self._last = None  # final (x, v) of the most recent single-trajectory call
+        eq = self.equilibrium_simulator
+        if abs(eq.constraint_tolerance - self.constraint_tolerance) > 0 or eq._engine_system is None:
+            eq.constraint_tolerance = self.constraint_tolerance
+            eq._engine_system = None
+
+    # ---- sampling
+    def sample_x_from_equilibrium(self):
+        return self.equilibrium_simulator.sample_x_from_equilibrium()
+
+    def sample_v_given_x(self, x):
+        return _sample_v(self.equilibrium_simulator, x, self.constraint_tolerance)
+
+    def _kT(self):
+        return self.equilibrium_simulator.kT_value
+
+    # ---- one trajectory (the reference's unit of work; here a 1-replica launch)
+    def accumulate_shadow_work(self, x_0, v_0, n_steps, store_potential_energy=False, store_W_shad_trace=False):
+        """Run the integrator for n_steps and return a dictionary containing "W_shad" (kT) and optionally
+        "potential_energies" (length n_steps + 1, kJ/mol) and "W_shad_trace" (per-step increments, length
+        n_steps).  Non-finite start states give an empty dictionary (:199-204)."""
+        result = {}
+        x0 = _frame_xyz(x_0)
+        v0 = np.asarray(v_0.value_in_unit(unit.nanometer / unit.picosecond) if unit.is_quantity(v_0) else v_0,
+                        dtype=np.float64)
+        if not (np.isfinite(x0).all() and np.isfinite(v0).all()):
+            print("Error setting positions or velocities!")
+            return result
+        eq = self.equilibrium_simulator
+        traces = bool(store_potential_energy or store_W_shad_trace)
+        rid = _rngstate.reserve_replicas(1)
+        direct = self.integrator._measure_shadow_work
+        res = engine.run_protocol(eq.engine_system(), self.integrator.program, 1, int(n_steps), self._kT(), n_legs=1,
+                                  seed=_rngstate.get_seed(), replica0=rid, x0=x0[None], v0=v0[None],
+                                  precision=self.precision, want_heat=True, want_direct=direct, want_final=True,
+                                  traces=traces, want_moments=False, out={})
+        kT = self._kT()
+        self.integrator._accumulate(heat=res["heat"][0, 0].item(),
+                                    shadow_work=res["W_direct"][0, 0].item() * kT if direct else None)
+        self._last = (res["x_final"][0].cpu().numpy(), res["v_final"][0].cpu().numpy())
+        if store_potential_energy:
+            frames = res["trace_x"][0, :, 0]
+            pe, _ = eq.engine_system().energy_forces(frames, precision=self.precision, want_forces=False)
+            result["potential_energies"] = pe.cpu().numpy() * unit.kilojoule_per_mole
+        if store_W_shad_trace:
+            result["W_shad_trace"] = np.diff(res["trace_w"][0, :, 0].cpu().numpy())
+        result["W_shad"] = res["W"][0, 0].item()
+        return result
+
+    # ---- the ensemble
+    def collect_protocol_samples(self, n_protocol_samples, protocol_length, marginal="configuration",
+                                 store_potential_energy_traces=False, store_W_shad_traces=False, seed=None,
+                                 as_numpy=True):
+        """Perform nonequilibrium measurements, aimed at measuring the free energy difference for the
+        chosen marginal (:247-295): per sample, x_0 ~ cache, v_0 ~ MB, forward leg of `protocol_length`
+        steps -> W_F; v redrawn ("configuration") or kept ("full"); reverse leg -> W_R.
+        Returns {"W_shads_F", "W_shads_R"[, "W_shad_traces", "potential_energies"]} in kT."""
+        if marginal not in ["configuration", "full"]:
+            raise NotImplementedError("`marginal` must be either 'configuration' or 'full'")
+        eq = self.equilibrium_simulator
+        n = int(n_protocol_samples)
+        traces = bool(store_potential_energy_traces or store_W_shad_traces)
+        seed = _rngstate.get_seed() if seed is None else int(seed)
+        rid = _rngstate.reserve_replicas(n)
+        res = engine.run_protocol(eq.engine_system(), self.integrator.program, n, int(protocol_length), self._kT(),
+                                  marginal=marginal, n_legs=2, seed=seed, replica0=rid, x_cache=eq.samples_device(),
+                                  precision=self.precision, want_heat=True, traces=traces, out=self._buffers,
+                                  round_midpoint=self.round_midpoint)
+        self.last_moments = res.get("moments")
+        W = res["W"]
+        self.integrator._accumulate(heat=res["heat"].nan_to_num(0.0).sum().item())
+        conv = (lambda a: a.cpu().numpy()) if as_numpy else (lambda a: a)
+        result = {"W_shads_F": conv(W[0]), "W_shads_R": conv(W[1])}
+        if store_W_shad_traces:
+            tw = res["trace_w"]  # (leg, step, replica), cumulative
+            inc = (tw[:, 1:] - tw[:, :-1]).permute(2, 0, 1)  # (replica, leg, step)
+            inc = conv(inc)
+            result["W_shad_traces"] = [(inc[i, 0], inc[i, 1]) for i in range(n)]
+        if store_potential_energy_traces:
+            frames = res["trace_x"][1].reshape(-1, eq.engine_system().n_atoms, 3)
+            pe, _ = eq.engine_system().energy_forces(frames, precision=self.precision, want_forces=False)
+            pe = conv(pe.reshape(int(protocol_length) + 1, n).transpose(0, 1))
+            result["potential_energies"] = [pe[i] for i in range(n)]
+        return result

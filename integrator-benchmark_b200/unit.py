@@ -11,6 +11,8 @@ _DIMS = ("length", "time", "mass", "temperature", "charge", "amount")
 
 
 class Unit:
+    __array_priority__ = 100  # ndarray * Unit -> one Quantity holding the array (not an object array)
+
     def __init__(self, factor, dims, name):
         self.factor = float(factor)
         self.dims = tuple(dims)
