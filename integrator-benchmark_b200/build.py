@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "liblsi.so")
-SOURCES = ["program.cpp", "api.cu", "toy.cu", "reduce.cu", "particles.cu", "microbench.cu"]
+SOURCES = ["program.cpp", "api.cu", "toy.cu", "reduce.cu", "particles.cu", "particles_f32.cu", "particles_f64.cu",
+           "microbench.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3", "--expt-relaxed-constexpr",

@@ -1,0 +1,1196 @@
+// K2/K3: whole-protocol kernel for particle systems (water cluster, alanine dipeptide, tiny water
+// box).  Included by particles_f32.cu / particles_f64.cu, which instantiate it for one `real`.
+//
+// Reference semantics (paths relative to the reference repository):
+//   substeps R / V / V{g} / O with constraints     benchmark/integrators/langevin.py:124-175
+//   protocol, work = (dE - dheat)/kT               benchmark/testsystems/bookkeepers.py:184-295
+//   systems                                        benchmark/testsystems/{watercluster,waterbox,alanine_dipeptide}.py
+// OpenMM supplies forces, SETTLE/CCMA and the `gaussian` stream there.  Here:
+//
+//   * a replica belongs to a TEAM: one warp when N <= 64 (several replicas per CTA, only
+//     __syncwarp between phases), otherwise one CTA.  Its state (x, v fp64) stays in shared memory
+//     for the whole protocol (forward leg, midpoint, reverse leg).
+//   * FORCE phases are atom-mapped: a lane owns APL atoms (LJ-active atoms packed into the first
+//     lanes) and runs a full-shell loop over all partners, whose positions {x, y, z, q sqrt(K)} are
+//     shared-memory broadcasts (one LDS.128 feeds APL pair evaluations).  Forces accumulate in
+//     registers: no atomics, no cross-thread reduction, bit-reproducible.  The Lennard-Jones part
+//     is behind a warp-uniform branch on the partner (skipped for TIP3P hydrogens); exclusions are
+//     per-atom bitmasks; minimum image by magic-number rounding (full-rate FP32).
+//   * bonded terms and 1-4 exceptions: one lane per TERM computes all role gradients once into a
+//     shared buffer; every atom then gathers its entries in a fixed order (deterministic).
+//     Periodic torsions use cos/sin of the dihedral and the multiple-angle recurrence (no atan2).
+//   * R / V-kick / O substeps are UNIT-mapped: a unit is a free atom, a rigid water or a star of
+//     pair constraints; its owner lane holds the unit in registers, updates it, applies analytic
+//     SETTLE / a Newton solve of the star (positions) and an exact 3x3 solve (velocities), and
+//     stages the new positions for the next force phase.  Consecutive unit-mapped substeps need no
+//     synchronisation; heat and shadow work are accumulated per lane and reduced once per leg.
+//   * per-force-group force caches with validity bits: a group is re-evaluated only after R.
+//   * O noise: Philox-4x32-10 keyed by (replica, leg, draw, atom).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "lsi_internal.h"
+#include "particles_shared.h"
+#include "rng.cuh"
+
+namespace pk {
+
+template <typename real> struct Vec;
+template <> struct Vec<float> { using r4 = float4; using r2 = float2; };
+template <> struct Vec<double> { using r4 = double4; using r2 = double2; };
+
+static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+static __device__ __forceinline__ double rsqrt_(double x) { return rsqrt(x); }
+// round to nearest integer by adding and removing 1.5 * 2^(mantissa bits): two full-rate adds
+static __device__ __forceinline__ float round_fma(float d, float inv) { return __fadd_rn(__fmaf_rn(d, inv, 12582912.0f), -12582912.0f); }
+static __device__ __forceinline__ double round_fma(double d, double inv) { return __dadd_rn(__fma_rn(d, inv, 6755399441055744.0), -6755399441055744.0); }
+
+// ---- shared-memory layout of one team (host and device agree through this function)
+struct Layout {
+    size_t x, v, xref, mass, invm, sigv, red, ctx, xq, ljp, qk, f, tf, total;
+};
+template <typename real>
+__host__ __device__ inline Layout layout(int N, int n_slots, int n_tf, bool generic, bool warp_team)
+{
+    Layout L;
+    size_t o = 0;
+    L.x = o; o += sizeof(double) * 3 * (size_t)N;
+    L.v = o; o += sizeof(double) * 3 * (size_t)N;
+    L.xref = o; if (generic) o += sizeof(double) * 3 * (size_t)N;
+    L.mass = o; o += sizeof(double) * (size_t)N;
+    L.invm = o; o += sizeof(double) * (size_t)N;
+    L.sigv = o; o += sizeof(double) * (size_t)N;
+    L.red = o; if (!warp_team) o += sizeof(double) * 32;
+    L.ctx = o; o += 320;  // TeamCtx<real> (static_assert in the kernel file)
+    o = (o + 31) & ~(size_t)31;
+    L.xq = o; o += 4 * sizeof(real) * (size_t)N;
+    L.ljp = o; o += 2 * sizeof(real) * (size_t)N;
+    L.qk = o; o += sizeof(real) * (size_t)N;
+    o = (o + 15) & ~(size_t)15;
+    L.f = o; o += sizeof(real) * 3 * (size_t)N * (size_t)n_slots;
+    L.tf = o; o += sizeof(real) * 3 * (size_t)n_tf;
+    L.total = (o + 31) & ~(size_t)31;
+    return L;
+}
+
+template <typename real>
+struct Smem {
+    double *x, *v, *xref, *mass, *invm, *sigv, *red;
+    typename Vec<real>::r4* xq;
+    typename Vec<real>::r2* ljp;
+    real *qk, *f, *tf;
+};
+
+template <typename real>
+__device__ __forceinline__ Smem<real> carve(unsigned char* base, const Layout& L)
+{
+    Smem<real> s;
+    s.x = reinterpret_cast<double*>(base + L.x);
+    s.v = reinterpret_cast<double*>(base + L.v);
+    s.xref = reinterpret_cast<double*>(base + L.xref);
+    s.mass = reinterpret_cast<double*>(base + L.mass);
+    s.invm = reinterpret_cast<double*>(base + L.invm);
+    s.sigv = reinterpret_cast<double*>(base + L.sigv);
+    s.red = reinterpret_cast<double*>(base + L.red);
+    s.xq = reinterpret_cast<typename Vec<real>::r4*>(base + L.xq);
+    s.ljp = reinterpret_cast<typename Vec<real>::r2*>(base + L.ljp);
+    s.qk = reinterpret_cast<real*>(base + L.qk);
+    s.f = reinterpret_cast<real*>(base + L.f);
+    s.tf = reinterpret_cast<real*>(base + L.tf);
+    return s;
+}
+
+template <bool WT>
+__device__ __forceinline__ void team_sync()
+{
+    if (WT) __syncwarp();
+    else __syncthreads();
+}
+
+// sum over the team, result in every thread (fixed order: deterministic)
+template <bool WT>
+__device__ __forceinline__ double team_sum(double val, double* red, int tid, int T)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    if (WT) return val;
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = val;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < (T >> 5); ++w) s += red[w];
+    return s;
+}
+
+struct Box {
+    double bx, by, bz, ibx, iby, ibz;
+};
+
+template <typename real, bool PERIODIC>
+__device__ __forceinline__ void min_image(const PKParams& P, real& dx, real& dy, real& dz)
+{
+    if (PERIODIC) {
+        dx = dx - (real)P.box[0] * round_fma(dx, (real)P.inv_box[0]);
+        dy = dy - (real)P.box[1] * round_fma(dy, (real)P.inv_box[1]);
+        dz = dz - (real)P.box[2] * round_fma(dz, (real)P.inv_box[2]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ forces
+// nonbonded full-shell loop for the APL atoms of this lane
+template <typename real, bool PERIODIC, int APL, bool ENERGY>
+__device__ __forceinline__ void pair_forces(const PKParams& P, const Smem<real>& s, const int (&atom)[APL],
+                                            real (&fx)[APL], real (&fy)[APL], real (&fz)[APL], real (&en)[APL])
+{
+    using r4 = typename Vec<real>::r4;
+    using r2 = typename Vec<real>::r2;
+    const int N = P.N, W = P.excl_words;
+    real xi[APL], yi[APL], zi[APL], qi[APL], hsi[APL], sei[APL];
+    bool lane_lj = false;
+#pragma unroll
+    for (int a = 0; a < APL; ++a) {
+        const int i = atom[a] >= 0 ? atom[a] : 0;
+        const r4 p = s.xq[i];
+        const r2 l = s.ljp[i];
+        xi[a] = p.x; yi[a] = p.y; zi[a] = p.z;
+        qi[a] = atom[a] >= 0 ? p.w : (real)0;
+        hsi[a] = l.x;
+        sei[a] = atom[a] >= 0 ? l.y : (real)0;
+        lane_lj = lane_lj || sei[a] != (real)0;
+    }
+    const bool warp_lj = __any_sync(0xffffffffu, lane_lj);
+    const real bx = (real)P.box[0], by = (real)P.box[1], bz = (real)P.box[2];
+    const real ibx = (real)P.inv_box[0], iby = (real)P.inv_box[1], ibz = (real)P.inv_box[2];
+    const real rc2 = (real)P.cutoff2, krf = (real)P.krf, krf2 = (real)(2.0 * P.krf), crf = (real)P.crf;
+
+    for (int jb = 0; jb < N; jb += 32) {
+        uint32_t mw[APL];
+#pragma unroll
+        for (int a = 0; a < APL; ++a) mw[a] = atom[a] >= 0 ? __ldg(P.excl + (size_t)atom[a] * W + (jb >> 5)) : 0xffffffffu;
+        const int jn = min(32, N - jb);
+#pragma unroll 4
+        for (int jj = 0; jj < jn; ++jj) {
+            const int j = jb + jj;
+            const r4 pj = s.xq[j];
+            r2 lj;
+            lj.x = (real)0; lj.y = (real)0;
+            if (warp_lj) lj = s.ljp[j];
+            const bool do_lj = lj.y != (real)0;  // warp-uniform: j is
+#pragma unroll
+            for (int a = 0; a < APL; ++a) {
+                real dx = pj.x - xi[a], dy = pj.y - yi[a], dz = pj.z - zi[a];
+                if (PERIODIC) {
+                    dx = dx - bx * round_fma(dx, ibx);
+                    dy = dy - by * round_fma(dy, iby);
+                    dz = dz - bz * round_fma(dz, ibz);
+                }
+                const real r2v = dx * dx + dy * dy + dz * dz;
+                bool ok = ((mw[a] >> jj) & 1u) == 0u;  // not excluded, not an exception, not self
+                if (PERIODIC) ok = ok && (r2v < rc2);
+                const real inv_r = rsqrt_(r2v), inv_r2 = inv_r * inv_r;
+                const real qq = qi[a] * pj.w;
+                real fr = PERIODIC ? qq * (inv_r * inv_r2 - krf2) : qq * inv_r * inv_r2;
+                real e = (real)0;
+                if (ENERGY) e = PERIODIC ? qq * (inv_r + krf * r2v - crf) : qq * inv_r;
+                if (do_lj) {
+                    const real sig = hsi[a] + lj.x;
+                    const real s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
+                    const real t = sei[a] * lj.y * s6;  // 4 eps s6
+                    fr += t * ((real)12 * s6 - (real)6) * inv_r2;
+                    if (ENERGY) e += t * (s6 - (real)1);
+                }
+                fr = ok ? fr : (real)0;
+                fx[a] -= fr * dx; fy[a] -= fr * dy; fz[a] -= fr * dz;
+                if (ENERGY) en[a] += ok ? e : (real)0;
+            }
+        }
+    }
+}
+
+// one lane per bonded term / exception: every role gradient once, into tf[3 * (slot + role) + c]
+template <typename real, bool PERIODIC, bool ENERGY>
+__device__ __forceinline__ real eval_terms(const PKParams& P, const Smem<real>& s, int lo, int hi, int tid, int T)
+{
+    using r4 = typename Vec<real>::r4;
+    const PKTerm<real>* terms = reinterpret_cast<const PKTerm<real>*>(P.terms);
+    real e_acc = (real)0;
+    for (int k = lo + tid; k < hi; k += T) {
+        const PKTerm<real> t = terms[k];
+        real* out = s.tf + 3 * (size_t)t.slot;
+        const r4 p0 = s.xq[t.a0], p1 = s.xq[t.a1];
+        if (t.kind == TERM_BOND || t.kind == TERM_EXCEPTION) {
+            real dx = p1.x - p0.x, dy = p1.y - p0.y, dz = p1.z - p0.z;  // from atom 0 to atom 1
+            min_image<real, PERIODIC>(P, dx, dy, dz);
+            const real r2v = dx * dx + dy * dy + dz * dz;
+            const real inv_r = rsqrt_(r2v);
+            real fr, e;
+            if (t.kind == TERM_BOND) {
+                const real dr = r2v * inv_r - t.p[0];
+                e = (real)0.5 * t.p[1] * dr * dr;
+                fr = t.p[1] * dr * inv_r;  // force on atom 0 = +fr d
+            } else {
+                const real inv_r2 = inv_r * inv_r;
+                const real s2 = t.p[1] * t.p[1] * inv_r2, s6 = s2 * s2 * s2;
+                e = t.p[2] * (s6 * s6 - s6) + t.p[0] * inv_r;
+                fr = -(t.p[2] * ((real)12 * s6 * s6 - (real)6 * s6) * inv_r2 + t.p[0] * inv_r * inv_r2);
+                if (PERIODIC && r2v >= (real)P.cutoff2) { fr = (real)0; e = (real)0; }
+            }
+            out[0] = fr * dx; out[1] = fr * dy; out[2] = fr * dz;
+            out[3] = -fr * dx; out[4] = -fr * dy; out[5] = -fr * dz;
+            if (ENERGY) e_acc += e;
+        } else if (t.kind == TERM_ANGLE) {
+            const r4 p2 = s.xq[t.a2];
+            real ax = p0.x - p1.x, ay = p0.y - p1.y, az = p0.z - p1.z;
+            real cx = p2.x - p1.x, cy = p2.y - p1.y, cz = p2.z - p1.z;
+            min_image<real, PERIODIC>(P, ax, ay, az);
+            min_image<real, PERIODIC>(P, cx, cy, cz);
+            const real ira = rsqrt_(ax * ax + ay * ay + az * az), irc = rsqrt_(cx * cx + cy * cy + cz * cz);
+            real ct = (ax * cx + ay * cy + az * cz) * ira * irc;
+            ct = fmin(fmax(ct, (real)-1), (real)1);
+            const real dth = acos(ct) - t.p[0];
+            const real st = sqrt(fmax((real)1 - ct * ct, (real)1e-24));
+            const real c = t.p[1] * dth / st;  // force = +c * d cos(theta)/d r
+            const real iac = ira * irc, ia2 = ira * ira, ic2 = irc * irc;
+            const real gax = cx * iac - ct * ax * ia2, gay = cy * iac - ct * ay * ia2, gaz = cz * iac - ct * az * ia2;
+            const real gcx = ax * iac - ct * cx * ic2, gcy = ay * iac - ct * cy * ic2, gcz = az * iac - ct * cz * ic2;
+            out[0] = c * gax; out[1] = c * gay; out[2] = c * gaz;
+            out[3] = -c * (gax + gcx); out[4] = -c * (gay + gcy); out[5] = -c * (gaz + gcz);
+            out[6] = c * gcx; out[7] = c * gcy; out[8] = c * gcz;
+            if (ENERGY) e_acc += (real)0.5 * t.p[1] * dth * dth;
+        } else {
+            const r4 p2 = s.xq[t.a2], p3 = s.xq[t.a3];
+            real b1x = p1.x - p0.x, b1y = p1.y - p0.y, b1z = p1.z - p0.z;
+            real b2x = p2.x - p1.x, b2y = p2.y - p1.y, b2z = p2.z - p1.z;
+            real b3x = p3.x - p2.x, b3y = p3.y - p2.y, b3z = p3.z - p2.z;
+            min_image<real, PERIODIC>(P, b1x, b1y, b1z);
+            min_image<real, PERIODIC>(P, b2x, b2y, b2z);
+            min_image<real, PERIODIC>(P, b3x, b3y, b3z);
+            const real n1x = b1y * b2z - b1z * b2y, n1y = b1z * b2x - b1x * b2z, n1z = b1x * b2y - b1y * b2x;
+            const real n2x = b2y * b3z - b2z * b3y, n2y = b2z * b3x - b2x * b3z, n2z = b2x * b3y - b2y * b3x;
+            const real b2sq = b2x * b2x + b2y * b2y + b2z * b2z;
+            const real ib2 = rsqrt_(b2sq), b2n = b2sq * ib2;
+            const real yy = b2n * (b1x * n2x + b1y * n2y + b1z * n2z);
+            const real xx = n1x * n2x + n1y * n2y + n1z * n2z;
+            const real n1sq = n1x * n1x + n1y * n1y + n1z * n1z, n2sq = n2x * n2x + n2y * n2y + n2z * n2z;
+            // cos(phi) = xx / (|n1||n2|), sin(phi) = yy / (|n1||n2|)  (phi = atan2(yy, xx), IUPAC sign)
+            const real inorm = rsqrt_(fmax(n1sq * n2sq, (real)1e-36));
+            const real c1 = xx * inorm, s1 = yy * inorm;
+            real cn = c1, sn = s1;
+            const int nper = (int)(t.p[0] + (real)0.5);
+            for (int q = 1; q < nper; ++q) {  // multiple-angle recurrence
+                const real c2 = cn * c1 - sn * s1;
+                sn = sn * c1 + cn * s1;
+                cn = c2;
+            }
+            if (nper == 0) { cn = (real)1; sn = (real)0; }
+            // E = k (1 + cos(n phi - phase)), dE/dphi = -k n sin(n phi - phase)
+            const real dE = -t.p[3] * (real)nper * (sn * t.p[1] - cn * t.p[2]);
+            if (ENERGY) e_acc += t.p[3] * ((real)1 + cn * t.p[1] + sn * t.p[2]);
+            const real k1 = -b2n / n1sq, k4 = b2n / n2sq;
+            const real g1x = k1 * n1x, g1y = k1 * n1y, g1z = k1 * n1z;
+            const real g4x = k4 * n2x, g4y = k4 * n2y, g4z = k4 * n2z;
+            const real ib2sq = ib2 * ib2;
+            const real u = (b1x * b2x + b1y * b2y + b1z * b2z) * ib2sq, w = (b3x * b2x + b3y * b2y + b3z * b2z) * ib2sq;
+            out[0] = -dE * g1x; out[1] = -dE * g1y; out[2] = -dE * g1z;
+            out[3] = -dE * (-g1x - u * g1x + w * g4x); out[4] = -dE * (-g1y - u * g1y + w * g4y);
+            out[5] = -dE * (-g1z - u * g1z + w * g4z);
+            out[6] = -dE * (-g4x + u * g1x - w * g4x); out[7] = -dE * (-g4y + u * g1y - w * g4y);
+            out[8] = -dE * (-g4z + u * g1z - w * g4z);
+            out[9] = -dE * g4x; out[10] = -dE * g4y; out[11] = -dE * g4z;
+        }
+    }
+    return e_acc;
+}
+
+// forces of force group g (-1 = all) into fout[3N] (team shared memory); ENERGY: returns the
+// potential energy (team sum, fp64).  Entry: positions staged in s.xq by the unit owners (the
+// leading team_sync orders those writes).  Exit: fout complete and visible to the team.
+template <typename real, bool PERIODIC, bool WT, int APL, bool ENERGY>
+__device__ double compute_forces(const PKParams& P, const Smem<real>& s, int g, real* __restrict__ fout, int tid, int T)
+{
+    const bool do_nb = g < 0 || g == P.g_nb;
+    const bool do_restr = (g < 0 || g == P.g_restr) && P.restraint_k != 0.0;
+    int set = -1;
+    if (g < 0) set = P.n_terms > 0 ? 0 : -1;
+    else
+        for (int q = 1; q < P.n_sets; ++q)
+            if (P.set_group[q] == g) set = q;
+    int atom[APL];
+    real fx[APL], fy[APL], fz[APL], en[APL];
+#pragma unroll
+    for (int a = 0; a < APL; ++a) {
+        const int slot = tid + a * T;
+        atom[a] = slot < P.N ? __ldg(P.perm + slot) : -1;
+        fx[a] = fy[a] = fz[a] = en[a] = (real)0;
+    }
+    team_sync<WT>();
+    if (do_nb) pair_forces<real, PERIODIC, APL, ENERGY>(P, s, atom, fx, fy, fz, en);
+    double e_thread = 0.0;
+    if (set >= 0) {
+        const real et = eval_terms<real, PERIODIC, ENERGY>(P, s, P.set_lo[set], P.set_hi[set], tid, T);
+        if (ENERGY) e_thread += (double)et;
+        team_sync<WT>();
+    }
+#pragma unroll
+    for (int a = 0; a < APL; ++a) {
+        const int i = atom[a];
+        if (i < 0) continue;
+        if (set >= 0) {
+            const int32_t* off = P.gather_off + (size_t)set * (P.N + 1) + i;
+            const int k0 = __ldg(off), k1 = __ldg(off + 1);
+            for (int k = k0; k < k1; ++k) {
+                const real* tfp = s.tf + 3 * (size_t)__ldg(P.gather_idx + k);
+                fx[a] += tfp[0]; fy[a] += tfp[1]; fz[a] += tfp[2];
+            }
+        }
+        real er = (real)0;
+        if (do_restr) {  // restraint acts on the true (unwrapped) coordinates
+            const real k = (real)P.restraint_k;
+            const real px = (real)s.x[3 * i], py = (real)s.x[3 * i + 1], pz = (real)s.x[3 * i + 2];
+            fx[a] -= k * px; fy[a] -= k * py; fz[a] -= k * pz;
+            if (ENERGY) er = (real)0.5 * k * (px * px + py * py + pz * pz);
+        }
+        fout[3 * i] = fx[a]; fout[3 * i + 1] = fy[a]; fout[3 * i + 2] = fz[a];
+        if (ENERGY) e_thread += (double)((real)0.5 * en[a] + er);  // every pair is visited from both ends
+    }
+    team_sync<WT>();
+    if (ENERGY) return team_sum<WT>(e_thread, s.red, tid, T);
+    return 0.0;
+}
+
+// ------------------------------------------------------------------------------------------ constraints (fp64)
+static __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// analytic SETTLE (Miyamoto & Kollman 1992): x0 = reference triangle (O, H1, H2), x1 = unconstrained
+// new positions, overwritten with the constrained ones
+static __device__ __forceinline__ void settle_positions(const double (&x0)[4][3], double (&x1)[4][3], double mO, double mH, double dOH,
+                                              double dHH)
+{
+    const double inv_mtot = 1.0 / (mO + 2.0 * mH);
+    double xb0[3], xc0[3], xcom[3], xa1[3], xb1[3], xc1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        xb0[c] = x0[1][c] - x0[0][c];
+        xc0[c] = x0[2][c] - x0[0][c];
+        xcom[c] = (mO * x1[0][c] + mH * x1[1][c] + mH * x1[2][c]) * inv_mtot;
+        xa1[c] = x1[0][c] - xcom[c];
+        xb1[c] = x1[1][c] - xcom[c];
+        xc1[c] = x1[2][c] - xcom[c];
+    }
+    double Z[3] = {xb0[1] * xc0[2] - xb0[2] * xc0[1], xb0[2] * xc0[0] - xb0[0] * xc0[2], xb0[0] * xc0[1] - xb0[1] * xc0[0]};
+    double X[3] = {xa1[1] * Z[2] - xa1[2] * Z[1], xa1[2] * Z[0] - xa1[0] * Z[2], xa1[0] * Z[1] - xa1[1] * Z[0]};
+    double Y[3] = {Z[1] * X[2] - Z[2] * X[1], Z[2] * X[0] - Z[0] * X[2], Z[0] * X[1] - Z[1] * X[0]};
+    const double nz = rsqrt(dot3(Z, Z)), nx = rsqrt(dot3(X, X)), ny = rsqrt(dot3(Y, Y));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { X[c] *= nx; Y[c] *= ny; Z[c] *= nz; }
+    const double xb0d = dot3(X, xb0), yb0d = dot3(Y, xb0), xc0d = dot3(X, xc0), yc0d = dot3(Y, xc0);
+    const double za1d = dot3(Z, xa1);
+    const double xb1d = dot3(X, xb1), yb1d = dot3(Y, xb1), zb1d = dot3(Z, xb1);
+    const double xc1d = dot3(X, xc1), yc1d = dot3(Y, xc1), zc1d = dot3(Z, xc1);
+    const double rc = 0.5 * dHH;
+    const double hgt = sqrt(dOH * dOH - rc * rc);
+    const double ra = hgt * 2.0 * mH * inv_mtot, rb = hgt - ra;
+    const double sinphi = za1d / ra, cosphi = sqrt(1.0 - sinphi * sinphi);
+    const double sinpsi = (zb1d - zc1d) / (2.0 * rc * cosphi), cospsi = sqrt(1.0 - sinpsi * sinpsi);
+    const double ya2d = ra * cosphi;
+    const double xb2d = -rc * cospsi;
+    const double yb2d = -rb * cosphi - rc * sinpsi * sinphi;
+    const double yc2d = -rb * cosphi + rc * sinpsi * sinphi;
+    const double alpha = xb2d * (xb0d - xc0d) + yb0d * yb2d + yc0d * yc2d;
+    const double beta = xb2d * (yc0d - yb0d) + xb0d * yb2d + xc0d * yc2d;
+    const double gamma = xb0d * yb1d - xb1d * yb0d + xc0d * yc1d - xc1d * yc0d;
+    const double al2be2 = alpha * alpha + beta * beta;
+    const double sintheta = (alpha * gamma - beta * sqrt(al2be2 - gamma * gamma)) / al2be2;
+    const double costheta = sqrt(1.0 - sintheta * sintheta);
+    const double xa3d = -ya2d * sintheta, ya3d = ya2d * costheta, za3d = za1d;
+    const double xb3d = xb2d * costheta - yb2d * sintheta, yb3d = xb2d * sintheta + yb2d * costheta, zb3d = zb1d;
+    const double xc3d = -xb2d * costheta - yc2d * sintheta, yc3d = -xb2d * sintheta + yc2d * costheta, zc3d = zc1d;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        x1[0][c] = xcom[c] + X[c] * xa3d + Y[c] * ya3d + Z[c] * za3d;
+        x1[1][c] = xcom[c] + X[c] * xb3d + Y[c] * yb3d + Z[c] * zb3d;
+        x1[2][c] = xcom[c] + X[c] * xc3d + Y[c] * yc3d + Z[c] * zc3d;
+    }
+}
+
+static __device__ __forceinline__ void solve3(double A00, double A01, double A02, double A10, double A11, double A12, double A20,
+                                       double A21, double A22, double r0, double r1, double r2, double& l0, double& l1,
+                                       double& l2)
+{
+    const double c00 = A11 * A22 - A12 * A21, c01 = A10 * A22 - A12 * A20, c02 = A10 * A21 - A11 * A20;
+    const double inv_det = 1.0 / (A00 * c00 - A01 * c01 + A02 * c02);
+    l0 = (r0 * c00 - A01 * (r1 * A22 - A12 * r2) + A02 * (r1 * A21 - A11 * r2)) * inv_det;
+    l1 = (A00 * (r1 * A22 - A12 * r2) - r0 * c01 + A02 * (A10 * r2 - r1 * A20)) * inv_det;
+    l2 = (A00 * (A11 * r2 - r1 * A21) - A01 * (A10 * r2 - r1 * A20) + r0 * c02) * inv_det;
+}
+
+// exact removal of the velocity components along the three edges of a rigid water
+static __device__ __forceinline__ void settle_velocities(const double (&x)[4][3], double (&v)[4][3], double mO, double mH)
+{
+    const double im[3] = {1.0 / mO, 1.0 / mH, 1.0 / mH};
+    double u[3][3], b[3];  // edges: k -> (k+1)%3
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int h = (k + 1) % 3;
+        double n2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            u[k][c] = x[h][c] - x[k][c];
+            n2 += u[k][c] * u[k][c];
+        }
+        const double inv = rsqrt(n2);
+        b[k] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            u[k][c] *= inv;
+            b[k] += (v[h][c] - v[k][c]) * u[k][c];
+        }
+    }
+    const double u01 = dot3(u[0], u[1]), u02 = dot3(u[0], u[2]), u12 = dot3(u[1], u[2]);
+    const double A00 = im[0] + im[1], A11 = im[1] + im[2], A22 = im[2] + im[0];
+    const double A01 = -im[1] * u01, A12 = -im[2] * u12, A02 = -im[0] * u02;
+    double lam[3];
+    solve3(A00, A01, A02, A01, A11, A12, A02, A12, A22, -b[0], -b[1], -b[2], lam[0], lam[1], lam[2]);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const int h = (l + 1) % 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            v[h][c] += lam[l] * u[l][c] * im[h];
+            v[l][c] -= lam[l] * u[l][c] * im[l];
+        }
+    }
+}
+
+// star of m <= 3 pair constraints around atom 0: Newton iteration on the multipliers of SHAKE
+// (displacements along the reference bond vectors s_k = x0[0] - x0[k+1]); converges quadratically
+static __device__ __forceinline__ void star_positions(const double (&x0)[4][3], double (&x1)[4][3], int m, const double (&d)[3],
+                                            const double (&im)[4], double tol)
+{
+    double sv[3][3], r[3][3], lam[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            sv[k][c] = k < m ? x0[0][c] - x0[k + 1][c] : 0.0;
+            r[k][c] = k < m ? x1[0][c] - x1[k + 1][c] : 0.0;
+        }
+    for (int it = 0; it < 30; ++it) {
+        // r'_k = r_k - im0 sum_l lam_l s_l - im_k lam_k s_k
+        double sum[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sum[c] = im[0] * (lam[0] * sv[0][c] + lam[1] * sv[1][c] + lam[2] * sv[2][c]);
+        double rp[3][3], sig[3];
+        bool done = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rp[k][c] = r[k][c] - sum[c] - im[k + 1] * lam[k] * sv[k][c];
+            const double d2 = d[k] * d[k];
+            sig[k] = k < m ? dot3(rp[k], rp[k]) - d2 : 0.0;
+            if (k < m && fabs(sig[k]) > 2.0 * tol * d2) done = false;
+        }
+        if (done && it > 0) break;
+        // J_kl = d sig_k / d lam_l = -2 r'_k . s_l (im0 + delta_kl im_k)
+        double J[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                if (k < m && l < m) J[k][l] = -2.0 * dot3(rp[k], sv[l]) * (im[0] + (k == l ? im[k + 1] : 0.0));
+                else J[k][l] = k == l ? 1.0 : 0.0;
+            }
+        double d0, d1, d2;
+        solve3(J[0][0], J[0][1], J[0][2], J[1][0], J[1][1], J[1][2], J[2][0], J[2][1], J[2][2], -sig[0], -sig[1], -sig[2], d0, d1, d2);
+        lam[0] += d0; lam[1] += d1; lam[2] += d2;
+        if (done) break;  // one polishing step past the tolerance
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        x1[0][c] -= im[0] * (lam[0] * sv[0][c] + lam[1] * sv[1][c] + lam[2] * sv[2][c]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k < m) x1[k + 1][c] += im[k + 1] * lam[k] * sv[k][c];
+    }
+}
+
+// star: exact removal of the relative velocity along each constrained bond (3x3 linear solve)
+static __device__ __forceinline__ void star_velocities(const double (&x)[4][3], double (&v)[4][3], int m, const double (&im)[4])
+{
+    double r[3][3], b[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        b[k] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            r[k][c] = k < m ? x[0][c] - x[k + 1][c] : 0.0;
+            b[k] += k < m ? r[k][c] * (v[0][c] - v[k + 1][c]) : 0.0;
+        }
+    }
+    double A[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            if (k < m && l < m) A[k][l] = dot3(r[k], r[l]) * (im[0] + (k == l ? im[k + 1] : 0.0));
+            else A[k][l] = k == l ? 1.0 : 0.0;
+        }
+    double mu[3];
+    solve3(A[0][0], A[0][1], A[0][2], A[1][0], A[1][1], A[1][2], A[2][0], A[2][1], A[2][2], b[0], b[1], b[2], mu[0], mu[1], mu[2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        v[0][c] -= im[0] * (mu[0] * r[0][c] + mu[1] * r[1][c] + mu[2] * r[2][c]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k < m) v[k + 1][c] += im[k + 1] * mu[k] * r[k][c];
+    }
+}
+
+// generic clusters (anything that is not a water or a small star): Gauss-Seidel SHAKE / RATTLE in
+// shared memory by the cluster's owner lane
+static __device__ __noinline__ void shake_cluster(const int32_t* pairs, const double* dist, double tol, const double* mass, const double* x0,
+                                           double* x1, int c0, int c1)
+{
+    for (int it = 0; it < 500; ++it) {
+        bool done = true;
+        for (int k = c0; k < c1; ++k) {
+            const int i = pairs[2 * k], j = pairs[2 * k + 1];
+            const double d2 = dist[k] * dist[k];
+            double r[3], sv[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                r[c] = x1[3 * i + c] - x1[3 * j + c];
+                sv[c] = x0[3 * i + c] - x0[3 * j + c];
+            }
+            const double diff = dot3(r, r) - d2;
+            if (fabs(diff) > 2.0 * tol * d2) done = false;
+            const double imi = 1.0 / mass[i], imj = 1.0 / mass[j];
+            const double gl = diff / (2.0 * dot3(r, sv) * (imi + imj));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                x1[3 * i + c] -= gl * sv[c] * imi;
+                x1[3 * j + c] += gl * sv[c] * imj;
+            }
+        }
+        if (done) break;
+    }
+}
+
+static __device__ __noinline__ void rattle_cluster(const int32_t* pairs, const double* dist, double tol, const double* mass, const double* x,
+                                            double* v, int c0, int c1)
+{
+    for (int it = 0; it < 500; ++it) {
+        bool done = true;
+        for (int k = c0; k < c1; ++k) {
+            const int i = pairs[2 * k], j = pairs[2 * k + 1];
+            const double d2 = dist[k] * dist[k];
+            double r[3], w[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                r[c] = x[3 * i + c] - x[3 * j + c];
+                w[c] = v[3 * i + c] - v[3 * j + c];
+            }
+            const double imi = 1.0 / mass[i], imj = 1.0 / mass[j];
+            const double gl = dot3(r, w) / (d2 * (imi + imj));
+            if (fabs(gl) > tol) done = false;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                v[3 * i + c] -= gl * r[c] * imi;
+                v[3 * j + c] += gl * r[c] * imj;
+            }
+        }
+        if (done) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ units
+// three normals for atom `unit`
+template <bool NOISE32>
+__device__ __forceinline__ void atom_normals(uint64_t seed, uint64_t rid, uint32_t draw, uint32_t tag, uint32_t unit,
+                                             double& n0, double& n1, double& n2)
+{
+    const lsi::Philox4 r = lsi::philox_block(seed, rid, draw, tag, unit);
+    if (NOISE32) {
+        float a, b, c, d;
+        lsi::box_muller(r.x, r.y, a, b);
+        lsi::box_muller(r.z, r.w, c, d);
+        n0 = (double)a; n1 = (double)b; n2 = (double)c;
+    } else {
+        double d;
+        lsi::box_muller(r.x, r.y, n0, n1);
+        lsi::box_muller(r.z, r.w, n2, d);
+    }
+}
+
+// Per-team context in shared memory: what the unit-mapped substeps need.  They are separate
+// (non-inlined, non-template) functions so that the fp64 constraint algebra gets its own register
+// allocation and is compiled once per `real`, not once per kernel instantiation.
+template <typename real>
+struct TeamCtx {
+    Smem<real> s;
+    const PKUnit* units;
+    const int32_t *gc_off, *gc_pairs, *gc_atom_off, *gc_atoms;
+    const double* gc_dist;
+    double box[3], inv_box[3], oh, hh, tol;
+    uint64_t seed;
+    int periodic;
+};
+
+template <typename real>
+__device__ __forceinline__ void fill_ctx(TeamCtx<real>* c, const PKParams& P, const Smem<real>& s)
+{
+    c->s = s;
+    c->units = P.units;
+    c->gc_off = P.gc_off; c->gc_pairs = P.gc_pairs; c->gc_atom_off = P.gc_atom_off; c->gc_atoms = P.gc_atoms;
+    c->gc_dist = P.gc_dist;
+    for (int k = 0; k < 3; ++k) { c->box[k] = P.box[k]; c->inv_box[k] = P.inv_box[k]; }
+    c->oh = P.oh; c->hh = P.hh; c->tol = P.tol;
+    c->seed = P.seed;
+    c->periodic = P.nb_method == LSI_NB_CUTOFF_PERIODIC;
+}
+
+template <typename real>
+struct UnitOps {
+    const TeamCtx<real>& C;
+    const Smem<real>& s;
+
+    __device__ __forceinline__ void load(const double* arr, const PKUnit& U, double (&a)[4][3]) const
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) a[k][c] = k < U.n ? arr[3 * U.a[k] + c] : 0.0;
+    }
+    __device__ __forceinline__ void store(double* arr, const PKUnit& U, const double (&a)[4][3]) const
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < U.n) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) arr[3 * U.a[k] + c] = a[k][c];
+            }
+    }
+    // positions for the force loop: force precision, wrapped into the box when periodic
+    __device__ __forceinline__ void stage_atom(int i, double px, double py, double pz) const
+    {
+        if (C.periodic) {
+            px -= C.box[0] * floor(px * C.inv_box[0]);
+            py -= C.box[1] * floor(py * C.inv_box[1]);
+            pz -= C.box[2] * floor(pz * C.inv_box[2]);
+        }
+        typename Vec<real>::r4 q;
+        q.x = (real)px; q.y = (real)py; q.z = (real)pz; q.w = s.qk[i];
+        s.xq[i] = q;
+    }
+    __device__ __forceinline__ void stage(const PKUnit& U, const double (&x)[4][3]) const
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < U.n) stage_atom(U.a[k], x[k][0], x[k][1], x[k][2]);
+    }
+    __device__ __forceinline__ void inv_masses(const PKUnit& U, double (&im)[4]) const
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) im[k] = k < U.n ? s.invm[U.a[k]] : 0.0;
+    }
+    __device__ __forceinline__ double kinetic(const PKUnit& U, const double (&v)[4][3]) const
+    {
+        double ke = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < U.n) ke += 0.5 * s.mass[U.a[k]] * (v[k][0] * v[k][0] + v[k][1] * v[k][1] + v[k][2] * v[k][2]);
+        return ke;
+    }
+    __device__ __forceinline__ void project_positions(const PKUnit& U, const double (&x0)[4][3], double (&x1)[4][3]) const
+    {
+        if (U.kind == UNIT_WATER) settle_positions(x0, x1, s.mass[U.a[0]], s.mass[U.a[1]], C.oh, C.hh);
+        else if (U.kind == UNIT_STAR) {
+            double im[4];
+            inv_masses(U, im);
+            const double d[3] = {U.d[0], U.d[1], U.d[2]};
+            star_positions(x0, x1, U.n - 1, d, im, C.tol);
+        }
+    }
+    __device__ __forceinline__ void project_velocities(const PKUnit& U, const double (&x)[4][3], double (&v)[4][3]) const
+    {
+        if (U.kind == UNIT_WATER) settle_velocities(x, v, s.mass[U.a[0]], s.mass[U.a[1]]);
+        else if (U.kind == UNIT_STAR) {
+            double im[4];
+            inv_masses(U, im);
+            star_velocities(x, v, U.n - 1, im);
+        }
+    }
+
+    // ---- generic clusters: atoms gc_atoms[a0..a1), constraints [c0..c1)
+    __device__ __forceinline__ double generic_kinetic(int a0, int a1) const
+    {
+        double ke = 0.0;
+        for (int q = a0; q < a1; ++q) {
+            const int i = C.gc_atoms[q];
+            ke += 0.5 * s.mass[i] * (s.v[3 * i] * s.v[3 * i] + s.v[3 * i + 1] * s.v[3 * i + 1] + s.v[3 * i + 2] * s.v[3 * i + 2]);
+        }
+        return ke;
+    }
+    __device__ __forceinline__ void generic_stage(int a0, int a1) const
+    {
+        for (int q = a0; q < a1; ++q) {
+            const int i = C.gc_atoms[q];
+            stage_atom(i, s.x[3 * i], s.x[3 * i + 1], s.x[3 * i + 2]);
+        }
+    }
+    __device__ __forceinline__ void generic_shake(int c) const
+    {
+        shake_cluster(C.gc_pairs, C.gc_dist, C.tol, s.mass, s.xref, s.x, C.gc_off[c], C.gc_off[c + 1]);
+    }
+    __device__ __forceinline__ void generic_rattle(int c) const
+    {
+        rattle_cluster(C.gc_pairs, C.gc_dist, C.tol, s.mass, s.x, s.v, C.gc_off[c], C.gc_off[c + 1]);
+    }
+};
+
+// constraints at the start of a leg: Context.applyConstraints / applyVelocityConstraints
+// (bookkeepers.py:206-208); stages the unit's positions; returns its kinetic energy afterwards
+template <typename real>
+__device__ __noinline__ double unit_init(const TeamCtx<real>* ctx, int u)
+{
+    const TeamCtx<real>& C = *ctx;
+    const Smem<real> s = C.s;
+    const UnitOps<real> ops{C, s};
+    const PKUnit U = C.units[u];
+    if (U.kind == UNIT_GENERIC) {
+        const int c = U.a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
+        for (int q = a0; q < a1; ++q) {
+            const int i = C.gc_atoms[q];
+            for (int k = 0; k < 3; ++k) s.xref[3 * i + k] = s.x[3 * i + k];
+        }
+        ops.generic_shake(c);
+        ops.generic_rattle(c);
+        ops.generic_stage(a0, a1);
+        return ops.generic_kinetic(a0, a1);
+    }
+    double x[4][3], v[4][3];
+    ops.load(s.x, U, x);
+    ops.load(s.v, U, v);
+    if (U.kind != UNIT_FREE) {
+        double x0[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x0[k][c] = x[k][c];
+        ops.project_positions(U, x0, x);
+        ops.project_velocities(U, x, v);
+        ops.store(s.x, U, x);
+        ops.store(s.v, U, v);
+    }
+    ops.stage(U, x);
+    return ops.kinetic(U, v);
+}
+
+// R: x <- x + h v; constrain positions; v <- v + (x - x1)/h; constrain velocities
+// (langevin.py:124-139); stages the new positions; returns the change of the unit's kinetic energy
+template <typename real>
+__device__ __noinline__ double unit_R(const TeamCtx<real>* ctx, int u, double h)
+{
+    const TeamCtx<real>& C = *ctx;
+    const Smem<real> s = C.s;
+    const UnitOps<real> ops{C, s};
+    const PKUnit U = C.units[u];
+    if (U.kind == UNIT_GENERIC) {
+        const int c = U.a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
+        const double ke0 = ops.generic_kinetic(a0, a1);
+        for (int q = a0; q < a1; ++q) {
+            const int i = C.gc_atoms[q];
+            for (int k = 0; k < 3; ++k) {
+                s.xref[3 * i + k] = s.x[3 * i + k];
+                s.x[3 * i + k] = s.x[3 * i + k] + h * s.v[3 * i + k];
+            }
+        }
+        ops.generic_shake(c);
+        for (int q = a0; q < a1; ++q) {
+            const int i = C.gc_atoms[q];
+            for (int k = 0; k < 3; ++k) {
+                const double x1 = s.xref[3 * i + k] + h * s.v[3 * i + k];
+                s.v[3 * i + k] = s.v[3 * i + k] + (s.x[3 * i + k] - x1) / h;
+            }
+        }
+        ops.generic_rattle(c);
+        ops.generic_stage(a0, a1);
+        return ops.generic_kinetic(a0, a1) - ke0;
+    }
+    double x[4][3], v[4][3];
+    ops.load(s.x, U, x);
+    ops.load(s.v, U, v);
+    if (U.kind == UNIT_FREE) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[0][c] = x[0][c] + h * v[0][c];
+        ops.store(s.x, U, x);
+        ops.stage(U, x);
+        return 0.0;
+    }
+    const double ke0 = ops.kinetic(U, v);
+    double x0[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            x0[k][c] = x[k][c];
+            x[k][c] = x[k][c] + h * v[k][c];
+        }
+    ops.project_positions(U, x0, x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double x1 = x0[k][c] + h * v[k][c];  // the unconstrained update
+            v[k][c] = v[k][c] + (x[k][c] - x1) / h;
+        }
+    ops.project_velocities(U, x, v);
+    ops.store(s.x, U, x);
+    ops.store(s.v, U, v);
+    ops.stage(U, x);
+    return ops.kinetic(U, v) - ke0;
+}
+
+// V: v <- v + h f / m; constrain velocities (langevin.py:141-163); returns the change of KE if asked
+template <typename real>
+__device__ __noinline__ double unit_V(const TeamCtx<real>* ctx, int u, double h, const real* __restrict__ f, int want_dke)
+{
+    const TeamCtx<real>& C = *ctx;
+    const Smem<real> s = C.s;
+    const UnitOps<real> ops{C, s};
+    const PKUnit U = C.units[u];
+    if (U.kind == UNIT_GENERIC) {
+        const int c = U.a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
+        const double ke0 = want_dke ? ops.generic_kinetic(a0, a1) : 0.0;
+        for (int q = a0; q < a1; ++q) {
+            const int i = C.gc_atoms[q];
+            const double hm = h * s.invm[i];
+            for (int k = 0; k < 3; ++k) s.v[3 * i + k] = s.v[3 * i + k] + hm * (double)f[3 * i + k];
+        }
+        ops.generic_rattle(c);
+        return want_dke ? ops.generic_kinetic(a0, a1) - ke0 : 0.0;
+    }
+    double v[4][3];
+    ops.load(s.v, U, v);
+    const double ke0 = want_dke ? ops.kinetic(U, v) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < U.n) {
+            const int i = U.a[k];
+            const double hm = h * s.invm[i];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[k][c] = v[k][c] + hm * (double)f[3 * i + c];
+        }
+    if (U.kind != UNIT_FREE) {
+        double x[4][3];
+        ops.load(s.x, U, x);
+        ops.project_velocities(U, x, v);
+    }
+    ops.store(s.v, U, v);
+    return want_dke ? ops.kinetic(U, v) - ke0 : 0.0;
+}
+
+// O: v <- a v + b sqrt(kT/m) xi; constrain velocities; returns the heat = change of KE (langevin.py:165-175)
+template <typename real>
+__device__ __noinline__ double unit_O(const TeamCtx<real>* ctx, int u, double a, double b, uint64_t rid, uint32_t draw)
+{
+    constexpr bool NOISE32 = sizeof(real) == 4;
+    const TeamCtx<real>& C = *ctx;
+    const Smem<real> s = C.s;
+    const UnitOps<real> ops{C, s};
+    const PKUnit U = C.units[u];
+    if (U.kind == UNIT_GENERIC) {
+        const int c = U.a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
+        const double ke0 = ops.generic_kinetic(a0, a1);
+        for (int q = a0; q < a1; ++q) {
+            const int i = C.gc_atoms[q];
+            double n0, n1, n2;
+            atom_normals<NOISE32>(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i, n0, n1, n2);
+            const double sg = b * s.sigv[i];
+            s.v[3 * i] = a * s.v[3 * i] + sg * n0;
+            s.v[3 * i + 1] = a * s.v[3 * i + 1] + sg * n1;
+            s.v[3 * i + 2] = a * s.v[3 * i + 2] + sg * n2;
+        }
+        ops.generic_rattle(c);
+        return ops.generic_kinetic(a0, a1) - ke0;
+    }
+    double v[4][3];
+    ops.load(s.v, U, v);
+    const double ke0 = ops.kinetic(U, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < U.n) {
+            const int i = U.a[k];
+            double n0, n1, n2;
+            atom_normals<NOISE32>(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i, n0, n1, n2);
+            const double sg = b * s.sigv[i];
+            v[k][0] = a * v[k][0] + sg * n0;
+            v[k][1] = a * v[k][1] + sg * n1;
+            v[k][2] = a * v[k][2] + sg * n2;
+        }
+    if (U.kind != UNIT_FREE) {
+        double x[4][3];
+        ops.load(s.x, U, x);
+        ops.project_velocities(U, x, v);
+    }
+    ops.store(s.v, U, v);
+    return ops.kinetic(U, v) - ke0;
+}
+
+template <typename real>
+__device__ __noinline__ double unit_kinetic(const TeamCtx<real>* ctx, int u)
+{
+    const TeamCtx<real>& C = *ctx;
+    const Smem<real> s = C.s;
+    const UnitOps<real> ops{C, s};
+    const PKUnit U = C.units[u];
+    if (U.kind == UNIT_GENERIC) return ops.generic_kinetic(C.gc_atom_off[U.a[0]], C.gc_atom_off[U.a[0] + 1]);
+    double v[4][3];
+    ops.load(s.v, U, v);
+    return ops.kinetic(U, v);
+}
+
+// tables -> team shared memory
+template <typename real>
+__device__ __forceinline__ void load_tables(const PKParams& P, const Smem<real>& s, int tid, int T)
+{
+    const typename Vec<real>::r4* nbp = reinterpret_cast<const typename Vec<real>::r4*>(P.nbp);
+    for (int i = tid; i < P.N; i += T) {
+        const double m = P.mass[i];
+        s.mass[i] = m;
+        s.invm[i] = 1.0 / m;
+        s.sigv[i] = sqrt(P.kT / m);
+        const typename Vec<real>::r4 p = nbp[i];
+        s.qk[i] = p.x;
+        typename Vec<real>::r2 l;
+        l.x = p.y; l.y = p.z;
+        s.ljp[i] = l;
+    }
+}
+
+#define PK_FOR_UNITS(u) for (int u = tid; u < P.n_units; u += T)
+
+template <typename real, bool PERIODIC, bool WT, int APL>
+__global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol_kernel(const __grid_constant__ PKParams P, int teams)
+{
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int N = P.N, D = 3 * N;
+    const int T = WT ? 32 : (int)blockDim.x;
+    const int tid = WT ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const int team = WT ? (int)(threadIdx.x >> 5) : 0;
+    const int64_t r = WT ? (int64_t)blockIdx.x * teams + team : (int64_t)blockIdx.x;
+    if (r >= P.n) return;  // whole team (warp-team mode never uses CTA barriers)
+    const bool DIAG = P.diag != 0;
+    const Layout L = layout<real>(N, P.n_slots, P.n_tf, P.n_generic > 0, WT);
+    unsigned char* team_base = smem_raw + (size_t)team * L.total;
+    const Smem<real> s = carve<real>(team_base, L);
+    TeamCtx<real>* ctx = reinterpret_cast<TeamCtx<real>*>(team_base + L.ctx);
+    if (tid == 0) fill_ctx<real>(ctx, P, s);
+    const uint64_t rid = P.replica0 + (uint64_t)r;
+    const int64_t TT = (int64_t)P.n_steps + 1;
+
+    // ---- start state
+    load_tables<real>(P, s, tid, T);
+    {
+        const double* xs = P.x0 ? P.x0 + r * D : P.x_cache + lsi::cache_index(P.seed, rid, P.n_cache) * D;
+        for (int k = tid; k < D; k += T) s.x[k] = xs[k];
+        if (P.v0) {
+            for (int k = tid; k < D; k += T) s.v[k] = P.v0[r * D + k];
+        } else {
+            for (int i = tid; i < N; i += T) {
+                double n0, n1, n2;
+                atom_normals<false>(P.seed, rid, 0u, LSI_TAG_V0, (uint32_t)i, n0, n1, n2);
+                const double sg = sqrt(P.kT / P.mass[i]);
+                s.v[3 * i] = sg * n0; s.v[3 * i + 1] = sg * n1; s.v[3 * i + 2] = sg * n2;
+            }
+        }
+    }
+    team_sync<WT>();
+
+    real* const scratch = s.f + (size_t)(P.n_slots - 1) * D;  // DIAG: an extra slot that is never a cache
+    double heat_run = 0.0;  // per-lane share of the heat accumulated so far (all legs)
+    for (int leg = 0; leg < P.n_legs; ++leg) {
+        if (leg > 0) {
+            if (P.flags & LSI_FLAG_ROUND_MIDPOINT_X_FP32)
+                for (int k = tid; k < D; k += T) s.x[k] = (double)(float)s.x[k];
+            if (P.marginal == LSI_MARGINAL_CONFIGURATION)
+                for (int i = tid; i < N; i += T) {
+                    double n0, n1, n2;
+                    atom_normals<false>(P.seed, rid, (uint32_t)(leg - 1), LSI_TAG_VMID, (uint32_t)i, n0, n1, n2);
+                    const double sg = s.sigv[i];
+                    s.v[3 * i] = sg * n0; s.v[3 * i + 1] = sg * n1; s.v[3 * i + 2] = sg * n2;
+                }
+            team_sync<WT>();
+        }
+        double ke0 = 0.0;
+        PK_FOR_UNITS(u) ke0 += unit_init<real>(ctx, u);
+        unsigned valid = 0u;  // bit per force-cache slot (team-uniform)
+        double pe_cur = compute_forces<real, PERIODIC, WT, APL, true>(P, s, -1, scratch, tid, T);
+        const double pe0 = pe_cur;
+        const double heat0 = heat_run;
+        double wd_ke = 0.0, wd_pe = 0.0;
+        double E0 = 0.0;
+        uint32_t q = 0;
+        if (DIAG) {
+            E0 = pe0 + team_sum<WT>(ke0, s.red, tid, T);
+            const int64_t base = ((int64_t)leg * TT) * P.n + r;
+            if (P.trace_x) for (int k = tid; k < D; k += T) P.trace_x[base * D + k] = s.x[k];
+            if (P.trace_v) for (int k = tid; k < D; k += T) P.trace_v[base * D + k] = s.v[k];
+            if (P.trace_w && tid == 0) P.trace_w[base] = 0.0;
+            team_sync<WT>();
+        }
+
+        for (int st = 0; st < P.n_steps; ++st) {
+            for (int op = 0; op < P.n_ops; ++op) {
+                const int kind = P.op_kind[op];
+                const double c0 = P.op_c0[op];
+                if (kind == LSI_OP_R) {
+                    double dke = 0.0;
+                    PK_FOR_UNITS(u) dke += unit_R<real>(ctx, u, c0);
+                    valid = 0u;
+                    if (DIAG) {
+                        wd_ke += dke;
+                        const double pe_new = compute_forces<real, PERIODIC, WT, APL, true>(P, s, -1, scratch, tid, T);
+                        wd_pe += pe_new - pe_cur;
+                        pe_cur = pe_new;
+                    }
+                } else if (kind == LSI_OP_V) {
+                    const int slot = P.op_slot[op];
+                    real* fs = s.f + (size_t)slot * D;
+                    if (!((valid >> slot) & 1u)) {
+                        compute_forces<real, PERIODIC, WT, APL, false>(P, s, P.slot_group[slot], fs, tid, T);
+                        valid |= 1u << slot;
+                    }
+                    double dke = 0.0;
+                    PK_FOR_UNITS(u) dke += unit_V<real>(ctx, u, c0, fs, DIAG ? 1 : 0);
+                    if (DIAG) wd_ke += dke;
+                } else {
+                    const double a = c0, b = P.op_c1[op];
+                    const uint32_t draw = ((uint32_t)leg << 26) | q;
+                    ++q;
+                    double dke = 0.0;
+                    PK_FOR_UNITS(u) dke += unit_O<real>(ctx, u, a, b, rid, draw);
+                    heat_run += dke;
+                }
+            }
+            if (DIAG) {
+                team_sync<WT>();
+                const int64_t idx = ((int64_t)leg * TT + st + 1) * P.n + r;
+                if (P.trace_x) for (int k = tid; k < D; k += T) P.trace_x[idx * D + k] = s.x[k];
+                if (P.trace_v) for (int k = tid; k < D; k += T) P.trace_v[idx * D + k] = s.v[k];
+                if (P.trace_w) {
+                    double ke = 0.0;
+                    PK_FOR_UNITS(u) ke += unit_kinetic<real>(ctx, u);
+                    // pe_cur is current: DIAG re-evaluates the energy after every R
+                    const double tot = team_sum<WT>(ke - (heat_run - heat0), s.red, tid, T);
+                    if (tid == 0) P.trace_w[idx] = ((pe_cur + tot) - E0) * P.inv_kT;
+                }
+                team_sync<WT>();  // trace reads of x, v finish before the owners move on
+            }
+        }
+        // ---- end of leg: W = ((E1 - E0) - (heat1 - heat0)) / kT
+        {
+            const double pe1 = DIAG ? pe_cur : compute_forces<real, PERIODIC, WT, APL, true>(P, s, -1, scratch, tid, T);
+            double ke1 = 0.0;
+            PK_FOR_UNITS(u) ke1 += unit_kinetic<real>(ctx, u);
+            const double dq = heat_run - heat0;
+            const double part = team_sum<WT>((ke1 - ke0) - dq, s.red, tid, T);
+            double heat_tot = 0.0, wd_tot = 0.0;
+            if (P.heat) heat_tot = team_sum<WT>(dq, s.red, tid, T);
+            if (DIAG && P.W_direct) wd_tot = team_sum<WT>(wd_ke, s.red, tid, T) + wd_pe;
+            if (tid == 0) {
+                P.W[(int64_t)leg * P.n + r] = ((pe1 - pe0) + part) * P.inv_kT;
+                if (P.heat) P.heat[(int64_t)leg * P.n + r] = heat_tot;
+                if (DIAG && P.W_direct) P.W_direct[(int64_t)leg * P.n + r] = wd_tot * P.inv_kT;
+            }
+        }
+        team_sync<WT>();
+    }
+    if (P.x_final) for (int k = tid; k < D; k += T) P.x_final[r * D + k] = s.x[k];
+    if (P.v_final) for (int k = tid; k < D; k += T) P.v_final[r * D + k] = s.v[k];
+}
+
+// potential energy and forces of force group q_group for n configurations
+template <typename real, bool PERIODIC, bool WT, int APL>
+__global__ void __launch_bounds__(WT ? 128 : 384) particles_energy_kernel(const __grid_constant__ PKParams P, int teams)
+{
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int N = P.N, D = 3 * N;
+    const int T = WT ? 32 : (int)blockDim.x;
+    const int tid = WT ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const int team = WT ? (int)(threadIdx.x >> 5) : 0;
+    const int64_t r = WT ? (int64_t)blockIdx.x * teams + team : (int64_t)blockIdx.x;
+    if (r >= P.n) return;
+    const Layout L = layout<real>(N, 1, P.n_tf, false, WT);
+    unsigned char* team_base = smem_raw + (size_t)team * L.total;
+    const Smem<real> s = carve<real>(team_base, L);
+    TeamCtx<real>* ctx = reinterpret_cast<TeamCtx<real>*>(team_base + L.ctx);
+    if (tid == 0) fill_ctx<real>(ctx, P, s);
+    load_tables<real>(P, s, tid, T);
+    for (int k = tid; k < D; k += T) s.x[k] = P.q_x[r * D + k];
+    team_sync<WT>();
+    {
+        const UnitOps<real> ops{*ctx, s};
+        for (int i = tid; i < N; i += T) ops.stage_atom(i, s.x[3 * i], s.x[3 * i + 1], s.x[3 * i + 2]);
+    }
+    const double e = compute_forces<real, PERIODIC, WT, APL, true>(P, s, P.q_group, s.f, tid, T);
+    if (P.q_energy && tid == 0) P.q_energy[r] = e;
+    if (P.q_forces) for (int k = tid; k < D; k += T) P.q_forces[r * D + k] = (double)s.f[k];
+}
+
+// ------------------------------------------------------------------------------------------ launch
+template <typename K>
+int set_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024) LSI_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return LSI_OK;
+}
+
+template <typename real, bool PERIODIC, bool WT, int APL>
+int launch_protocol3(const PKParams& P, const PKLaunch& L, cudaStream_t st)
+{
+    static_assert(sizeof(TeamCtx<real>) <= 320, "Layout reserves 320 bytes for TeamCtx");
+    const unsigned grid = (unsigned)(WT ? (L.n + L.teams - 1) / L.teams : L.n);
+    auto k = particles_protocol_kernel<real, PERIODIC, WT, APL>;
+    int rc;
+    if ((rc = set_smem(k, L.smem)) != LSI_OK) return rc;
+    k<<<grid, L.threads, L.smem, st>>>(P, L.teams);
+    LSI_CUDA_CHECK(cudaGetLastError());
+    return LSI_OK;
+}
+
+template <typename real, bool PERIODIC, bool WT, int APL>
+int launch_energy3(const PKParams& P, const PKLaunch& L, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)(WT ? (L.n + L.teams - 1) / L.teams : L.n);
+    auto k = particles_energy_kernel<real, PERIODIC, WT, APL>;
+    int rc;
+    if ((rc = set_smem(k, L.smem)) != LSI_OK) return rc;
+    k<<<grid, L.threads, L.smem, st>>>(P, L.teams);
+    LSI_CUDA_CHECK(cudaGetLastError());
+    return LSI_OK;
+}
+
+#define PK_DISPATCH(FN, real)                                                                     \
+    if (L.warp_team) {                                                                            \
+        if (L.apl == 1) return L.periodic ? FN<real, true, true, 1>(P, L, st) : FN<real, false, true, 1>(P, L, st); \
+        return L.periodic ? FN<real, true, true, 2>(P, L, st) : FN<real, false, true, 2>(P, L, st); \
+    }                                                                                             \
+    if (L.apl == 1) return L.periodic ? FN<real, true, false, 1>(P, L, st) : FN<real, false, false, 1>(P, L, st); \
+    return L.periodic ? FN<real, true, false, 2>(P, L, st) : FN<real, false, false, 2>(P, L, st);
+
+template <typename real>
+int launch_protocol(const PKParams& P, const PKLaunch& L, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    PK_DISPATCH(launch_protocol3, real)
+}
+
+template <typename real>
+int launch_energy(const PKParams& P, const PKLaunch& L, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    PK_DISPATCH(launch_energy3, real)
+}
+
+}  // namespace pk
