@@ -39,7 +39,13 @@ template <typename real> struct Vec;
 template <> struct Vec<float> { using r4 = float4; using r2 = float2; };
 template <> struct Vec<double> { using r4 = double4; using r2 = double2; };
 
-static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+// MUFU.RSQ without the denormal pre/post-scaling of rsqrtf (squared distances are never denormal; 2 ulp)
+static __device__ __forceinline__ float rsqrt_(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 static __device__ __forceinline__ double rsqrt_(double x) { return rsqrt(x); }
 // round to nearest integer by adding and removing 1.5 * 2^(mantissa bits): two full-rate adds
 static __device__ __forceinline__ float round_fma(float d, float inv) { return __fadd_rn(__fmaf_rn(d, inv, 12582912.0f), -12582912.0f); }
@@ -61,10 +67,10 @@ __host__ __device__ inline Layout layout(int N, int n_slots, int n_tf, bool gene
     L.invm = o; o += sizeof(double) * (size_t)N;
     L.sigv = o; o += sizeof(double) * (size_t)N;
     L.red = o; if (!warp_team) o += sizeof(double) * 32;
-    L.ctx = o; o += 320;  // TeamCtx<real> (static_assert in the kernel file)
+    L.ctx = o; o += 512;  // TeamCtx<real> (static_assert in the kernel file)
     o = (o + 31) & ~(size_t)31;
-    L.xq = o; o += 4 * sizeof(real) * (size_t)N;
-    L.ljp = o; o += 2 * sizeof(real) * (size_t)N;
+    L.xq = o; o += 8 * sizeof(real) * (size_t)N;  // per atom {x, y, z, q sqrt(K)}, {sigma/2, 2 sqrt(eps), -, -}
+    L.ljp = o;
     L.qk = o; o += sizeof(real) * (size_t)N;
     o = (o + 15) & ~(size_t)15;
     L.f = o; o += sizeof(real) * 3 * (size_t)N * (size_t)n_slots;
@@ -77,7 +83,6 @@ template <typename real>
 struct Smem {
     double *x, *v, *xref, *mass, *invm, *sigv, *red;
     typename Vec<real>::r4* xq;
-    typename Vec<real>::r2* ljp;
     real *qk, *f, *tf;
 };
 
@@ -93,7 +98,6 @@ __device__ __forceinline__ Smem<real> carve(unsigned char* base, const Layout& L
     s.sigv = reinterpret_cast<double*>(base + L.sigv);
     s.red = reinterpret_cast<double*>(base + L.red);
     s.xq = reinterpret_cast<typename Vec<real>::r4*>(base + L.xq);
-    s.ljp = reinterpret_cast<typename Vec<real>::r2*>(base + L.ljp);
     s.qk = reinterpret_cast<real*>(base + L.qk);
     s.f = reinterpret_cast<real*>(base + L.f);
     s.tf = reinterpret_cast<real*>(base + L.tf);
@@ -122,36 +126,79 @@ __device__ __forceinline__ double team_sum(double val, double* red, int tid, int
     return s;
 }
 
-struct Box {
-    double bx, by, bz, ibx, iby, ibz;
+// Per-team context in shared memory: everything the non-inlined phases (force evaluation, unit-mapped
+// substeps) need, with the force-loop constants already in force precision.  Keeping those phases out
+// of line keeps the kernel small enough for the instruction cache and gives the fp64 constraint
+// algebra its own register allocation.
+template <typename real>
+struct TeamCtx {
+    Smem<real> s;
+    // units
+    const PKUnit* units;
+    const int32_t *gc_off, *gc_pairs, *gc_atom_off, *gc_atoms;
+    const double* gc_dist;
+    double box[3], inv_box[3], oh, hh, tol;
+    uint64_t seed;
+    int periodic;
+    // forces
+    int N, excl_words, n_terms, n_sets, g_nb, g_restr;
+    int set_group[kMaxSets], set_lo[kMaxSets], set_hi[kMaxSets];
+    const uint32_t* excl;
+    const int32_t* perm;
+    const PKTerm<real>* terms;
+    const int32_t *gather_off, *gather_idx;
+    real boxr[3], inv_boxr[3], rc2, krf, krf2, crf, restraint_k;
 };
 
+template <typename real>
+__device__ __forceinline__ void fill_ctx(TeamCtx<real>* c, const PKParams& P, const Smem<real>& s)
+{
+    c->s = s;
+    c->units = P.units;
+    c->gc_off = P.gc_off; c->gc_pairs = P.gc_pairs; c->gc_atom_off = P.gc_atom_off; c->gc_atoms = P.gc_atoms;
+    c->gc_dist = P.gc_dist;
+    for (int k = 0; k < 3; ++k) {
+        c->box[k] = P.box[k]; c->inv_box[k] = P.inv_box[k];
+        c->boxr[k] = (real)P.box[k]; c->inv_boxr[k] = (real)P.inv_box[k];
+    }
+    c->oh = P.oh; c->hh = P.hh; c->tol = P.tol;
+    c->seed = P.seed;
+    c->periodic = P.nb_method == LSI_NB_CUTOFF_PERIODIC;
+    c->N = P.N; c->excl_words = P.excl_words; c->n_terms = P.n_terms; c->n_sets = P.n_sets;
+    c->g_nb = P.g_nb; c->g_restr = P.g_restr;
+    for (int k = 0; k < kMaxSets; ++k) { c->set_group[k] = P.set_group[k]; c->set_lo[k] = P.set_lo[k]; c->set_hi[k] = P.set_hi[k]; }
+    c->excl = P.excl; c->perm = P.perm;
+    c->terms = reinterpret_cast<const PKTerm<real>*>(P.terms);
+    c->gather_off = P.gather_off; c->gather_idx = P.gather_idx;
+    c->rc2 = (real)P.cutoff2; c->krf = (real)P.krf; c->krf2 = (real)(2.0 * P.krf); c->crf = (real)P.crf;
+    c->restraint_k = (real)P.restraint_k;
+}
+
 template <typename real, bool PERIODIC>
-__device__ __forceinline__ void min_image(const PKParams& P, real& dx, real& dy, real& dz)
+__device__ __forceinline__ void min_image(const TeamCtx<real>& C, real& dx, real& dy, real& dz)
 {
     if (PERIODIC) {
-        dx = dx - (real)P.box[0] * round_fma(dx, (real)P.inv_box[0]);
-        dy = dy - (real)P.box[1] * round_fma(dy, (real)P.inv_box[1]);
-        dz = dz - (real)P.box[2] * round_fma(dz, (real)P.inv_box[2]);
+        dx = dx - C.boxr[0] * round_fma(dx, C.inv_boxr[0]);
+        dy = dy - C.boxr[1] * round_fma(dy, C.inv_boxr[1]);
+        dz = dz - C.boxr[2] * round_fma(dz, C.inv_boxr[2]);
     }
 }
 
 // ------------------------------------------------------------------------------------------ forces
 // nonbonded full-shell loop for the APL atoms of this lane
 template <typename real, bool PERIODIC, int APL, bool ENERGY>
-__device__ __forceinline__ void pair_forces(const PKParams& P, const Smem<real>& s, const int (&atom)[APL],
-                                            real (&fx)[APL], real (&fy)[APL], real (&fz)[APL], real (&en)[APL])
+__device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typename Vec<real>::r4* __restrict__ xq,
+                                            const int (&atom)[APL], real (&fx)[APL], real (&fy)[APL], real (&fz)[APL],
+                                            real (&en)[APL])
 {
     using r4 = typename Vec<real>::r4;
-    using r2 = typename Vec<real>::r2;
-    const int N = P.N, W = P.excl_words;
+    const int N = C.N, W = C.excl_words;
     real xi[APL], yi[APL], zi[APL], qi[APL], hsi[APL], sei[APL];
     bool lane_lj = false;
 #pragma unroll
     for (int a = 0; a < APL; ++a) {
         const int i = atom[a] >= 0 ? atom[a] : 0;
-        const r4 p = s.xq[i];
-        const r2 l = s.ljp[i];
+        const r4 p = xq[2 * i], l = xq[2 * i + 1];
         xi[a] = p.x; yi[a] = p.y; zi[a] = p.z;
         qi[a] = atom[a] >= 0 ? p.w : (real)0;
         hsi[a] = l.x;
@@ -159,23 +206,25 @@ __device__ __forceinline__ void pair_forces(const PKParams& P, const Smem<real>&
         lane_lj = lane_lj || sei[a] != (real)0;
     }
     const bool warp_lj = __any_sync(0xffffffffu, lane_lj);
-    const real bx = (real)P.box[0], by = (real)P.box[1], bz = (real)P.box[2];
-    const real ibx = (real)P.inv_box[0], iby = (real)P.inv_box[1], ibz = (real)P.inv_box[2];
-    const real rc2 = (real)P.cutoff2, krf = (real)P.krf, krf2 = (real)(2.0 * P.krf), crf = (real)P.crf;
+    const real bx = C.boxr[0], by = C.boxr[1], bz = C.boxr[2];
+    const real ibx = C.inv_boxr[0], iby = C.inv_boxr[1], ibz = C.inv_boxr[2];
+    const real rc2 = C.rc2, krf = C.krf, krf2 = C.krf2, crf = C.crf;
 
     for (int jb = 0; jb < N; jb += 32) {
         uint32_t mw[APL];
 #pragma unroll
-        for (int a = 0; a < APL; ++a) mw[a] = atom[a] >= 0 ? __ldg(P.excl + (size_t)atom[a] * W + (jb >> 5)) : 0xffffffffu;
+        for (int a = 0; a < APL; ++a) mw[a] = atom[a] >= 0 ? __ldg(C.excl + (size_t)atom[a] * W + (jb >> 5)) : 0xffffffffu;
         const int jn = min(32, N - jb);
-#pragma unroll 4
+        const r4* __restrict__ xj = xq + 2 * jb;
+#pragma unroll 2
         for (int jj = 0; jj < jn; ++jj) {
-            const int j = jb + jj;
-            const r4 pj = s.xq[j];
-            r2 lj;
-            lj.x = (real)0; lj.y = (real)0;
-            if (warp_lj) lj = s.ljp[j];
-            const bool do_lj = lj.y != (real)0;  // warp-uniform: j is
+            const r4 pj = xj[2 * jj];
+            real ljx = (real)0, ljy = (real)0;
+            if (warp_lj) {
+                const r4 l = xj[2 * jj + 1];
+                ljx = l.x; ljy = l.y;
+            }
+            const bool do_lj = ljy != (real)0;  // warp-uniform: the partner is
 #pragma unroll
             for (int a = 0; a < APL; ++a) {
                 real dx = pj.x - xi[a], dy = pj.y - yi[a], dz = pj.z - zi[a];
@@ -193,9 +242,9 @@ __device__ __forceinline__ void pair_forces(const PKParams& P, const Smem<real>&
                 real e = (real)0;
                 if (ENERGY) e = PERIODIC ? qq * (inv_r + krf * r2v - crf) : qq * inv_r;
                 if (do_lj) {
-                    const real sig = hsi[a] + lj.x;
+                    const real sig = hsi[a] + ljx;
                     const real s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
-                    const real t = sei[a] * lj.y * s6;  // 4 eps s6
+                    const real t = sei[a] * ljy * s6;  // 4 eps s6
                     fr += t * ((real)12 * s6 - (real)6) * inv_r2;
                     if (ENERGY) e += t * (s6 - (real)1);
                 }
@@ -209,18 +258,18 @@ __device__ __forceinline__ void pair_forces(const PKParams& P, const Smem<real>&
 
 // one lane per bonded term / exception: every role gradient once, into tf[3 * (slot + role) + c]
 template <typename real, bool PERIODIC, bool ENERGY>
-__device__ __forceinline__ real eval_terms(const PKParams& P, const Smem<real>& s, int lo, int hi, int tid, int T)
+__device__ __forceinline__ real eval_terms(const TeamCtx<real>& C, const typename Vec<real>::r4* __restrict__ xq,
+                                           real* __restrict__ tf, int lo, int hi, int tid, int T)
 {
     using r4 = typename Vec<real>::r4;
-    const PKTerm<real>* terms = reinterpret_cast<const PKTerm<real>*>(P.terms);
     real e_acc = (real)0;
     for (int k = lo + tid; k < hi; k += T) {
-        const PKTerm<real> t = terms[k];
-        real* out = s.tf + 3 * (size_t)t.slot;
-        const r4 p0 = s.xq[t.a0], p1 = s.xq[t.a1];
+        const PKTerm<real> t = C.terms[k];
+        real* out = tf + 3 * (size_t)t.slot;
+        const r4 p0 = xq[2 * t.a0], p1 = xq[2 * t.a1];
         if (t.kind == TERM_BOND || t.kind == TERM_EXCEPTION) {
             real dx = p1.x - p0.x, dy = p1.y - p0.y, dz = p1.z - p0.z;  // from atom 0 to atom 1
-            min_image<real, PERIODIC>(P, dx, dy, dz);
+            min_image<real, PERIODIC>(C, dx, dy, dz);
             const real r2v = dx * dx + dy * dy + dz * dz;
             const real inv_r = rsqrt_(r2v);
             real fr, e;
@@ -233,17 +282,17 @@ __device__ __forceinline__ real eval_terms(const PKParams& P, const Smem<real>& 
                 const real s2 = t.p[1] * t.p[1] * inv_r2, s6 = s2 * s2 * s2;
                 e = t.p[2] * (s6 * s6 - s6) + t.p[0] * inv_r;
                 fr = -(t.p[2] * ((real)12 * s6 * s6 - (real)6 * s6) * inv_r2 + t.p[0] * inv_r * inv_r2);
-                if (PERIODIC && r2v >= (real)P.cutoff2) { fr = (real)0; e = (real)0; }
+                if (PERIODIC && r2v >= C.rc2) { fr = (real)0; e = (real)0; }
             }
             out[0] = fr * dx; out[1] = fr * dy; out[2] = fr * dz;
             out[3] = -fr * dx; out[4] = -fr * dy; out[5] = -fr * dz;
             if (ENERGY) e_acc += e;
         } else if (t.kind == TERM_ANGLE) {
-            const r4 p2 = s.xq[t.a2];
+            const r4 p2 = xq[2 * t.a2];
             real ax = p0.x - p1.x, ay = p0.y - p1.y, az = p0.z - p1.z;
             real cx = p2.x - p1.x, cy = p2.y - p1.y, cz = p2.z - p1.z;
-            min_image<real, PERIODIC>(P, ax, ay, az);
-            min_image<real, PERIODIC>(P, cx, cy, cz);
+            min_image<real, PERIODIC>(C, ax, ay, az);
+            min_image<real, PERIODIC>(C, cx, cy, cz);
             const real ira = rsqrt_(ax * ax + ay * ay + az * az), irc = rsqrt_(cx * cx + cy * cy + cz * cz);
             real ct = (ax * cx + ay * cy + az * cz) * ira * irc;
             ct = fmin(fmax(ct, (real)-1), (real)1);
@@ -258,13 +307,13 @@ __device__ __forceinline__ real eval_terms(const PKParams& P, const Smem<real>& 
             out[6] = c * gcx; out[7] = c * gcy; out[8] = c * gcz;
             if (ENERGY) e_acc += (real)0.5 * t.p[1] * dth * dth;
         } else {
-            const r4 p2 = s.xq[t.a2], p3 = s.xq[t.a3];
+            const r4 p2 = xq[2 * t.a2], p3 = xq[2 * t.a3];
             real b1x = p1.x - p0.x, b1y = p1.y - p0.y, b1z = p1.z - p0.z;
             real b2x = p2.x - p1.x, b2y = p2.y - p1.y, b2z = p2.z - p1.z;
             real b3x = p3.x - p2.x, b3y = p3.y - p2.y, b3z = p3.z - p2.z;
-            min_image<real, PERIODIC>(P, b1x, b1y, b1z);
-            min_image<real, PERIODIC>(P, b2x, b2y, b2z);
-            min_image<real, PERIODIC>(P, b3x, b3y, b3z);
+            min_image<real, PERIODIC>(C, b1x, b1y, b1z);
+            min_image<real, PERIODIC>(C, b2x, b2y, b2z);
+            min_image<real, PERIODIC>(C, b3x, b3y, b3z);
             const real n1x = b1y * b2z - b1z * b2y, n1y = b1z * b2x - b1x * b2z, n1z = b1x * b2y - b1y * b2x;
             const real n2x = b2y * b3z - b2z * b3y, n2y = b2z * b3x - b2x * b3z, n2z = b2x * b3y - b2y * b3x;
             const real b2sq = b2x * b2x + b2y * b2y + b2z * b2z;
@@ -306,28 +355,30 @@ __device__ __forceinline__ real eval_terms(const PKParams& P, const Smem<real>& 
 // potential energy (team sum, fp64).  Entry: positions staged in s.xq by the unit owners (the
 // leading team_sync orders those writes).  Exit: fout complete and visible to the team.
 template <typename real, bool PERIODIC, bool WT, int APL, bool ENERGY>
-__device__ double compute_forces(const PKParams& P, const Smem<real>& s, int g, real* __restrict__ fout, int tid, int T)
+__device__ __noinline__ double compute_forces(const TeamCtx<real>* ctx, int g, real* __restrict__ fout, int tid, int T)
 {
-    const bool do_nb = g < 0 || g == P.g_nb;
-    const bool do_restr = (g < 0 || g == P.g_restr) && P.restraint_k != 0.0;
+    const TeamCtx<real>& C = *ctx;
+    const Smem<real> s = C.s;
+    const bool do_nb = g < 0 || g == C.g_nb;
+    const bool do_restr = (g < 0 || g == C.g_restr) && C.restraint_k != (real)0;
     int set = -1;
-    if (g < 0) set = P.n_terms > 0 ? 0 : -1;
+    if (g < 0) set = C.n_terms > 0 ? 0 : -1;
     else
-        for (int q = 1; q < P.n_sets; ++q)
-            if (P.set_group[q] == g) set = q;
+        for (int q = 1; q < C.n_sets; ++q)
+            if (C.set_group[q] == g) set = q;
     int atom[APL];
     real fx[APL], fy[APL], fz[APL], en[APL];
 #pragma unroll
     for (int a = 0; a < APL; ++a) {
         const int slot = tid + a * T;
-        atom[a] = slot < P.N ? __ldg(P.perm + slot) : -1;
+        atom[a] = slot < C.N ? __ldg(C.perm + slot) : -1;
         fx[a] = fy[a] = fz[a] = en[a] = (real)0;
     }
     team_sync<WT>();
-    if (do_nb) pair_forces<real, PERIODIC, APL, ENERGY>(P, s, atom, fx, fy, fz, en);
+    if (do_nb) pair_forces<real, PERIODIC, APL, ENERGY>(C, s.xq, atom, fx, fy, fz, en);
     double e_thread = 0.0;
     if (set >= 0) {
-        const real et = eval_terms<real, PERIODIC, ENERGY>(P, s, P.set_lo[set], P.set_hi[set], tid, T);
+        const real et = eval_terms<real, PERIODIC, ENERGY>(C, s.xq, s.tf, C.set_lo[set], C.set_hi[set], tid, T);
         if (ENERGY) e_thread += (double)et;
         team_sync<WT>();
     }
@@ -336,16 +387,16 @@ __device__ double compute_forces(const PKParams& P, const Smem<real>& s, int g, 
         const int i = atom[a];
         if (i < 0) continue;
         if (set >= 0) {
-            const int32_t* off = P.gather_off + (size_t)set * (P.N + 1) + i;
+            const int32_t* off = C.gather_off + (size_t)set * (C.N + 1) + i;
             const int k0 = __ldg(off), k1 = __ldg(off + 1);
             for (int k = k0; k < k1; ++k) {
-                const real* tfp = s.tf + 3 * (size_t)__ldg(P.gather_idx + k);
+                const real* tfp = s.tf + 3 * (size_t)__ldg(C.gather_idx + k);
                 fx[a] += tfp[0]; fy[a] += tfp[1]; fz[a] += tfp[2];
             }
         }
         real er = (real)0;
         if (do_restr) {  // restraint acts on the true (unwrapped) coordinates
-            const real k = (real)P.restraint_k;
+            const real k = C.restraint_k;
             const real px = (real)s.x[3 * i], py = (real)s.x[3 * i + 1], pz = (real)s.x[3 * i + 2];
             fx[a] -= k * px; fy[a] -= k * py; fz[a] -= k * pz;
             if (ENERGY) er = (real)0.5 * k * (px * px + py * py + pz * pz);
@@ -363,7 +414,7 @@ static __device__ __forceinline__ double dot3(const double* a, const double* b) 
 
 // analytic SETTLE (Miyamoto & Kollman 1992): x0 = reference triangle (O, H1, H2), x1 = unconstrained
 // new positions, overwritten with the constrained ones
-static __device__ __forceinline__ void settle_positions(const double (&x0)[4][3], double (&x1)[4][3], double mO, double mH, double dOH,
+static __device__ __forceinline__ void settle_positions(const double (&x0)[3][3], double (&x1)[3][3], double mO, double mH, double dOH,
                                               double dHH)
 {
     const double inv_mtot = 1.0 / (mO + 2.0 * mH);
@@ -425,7 +476,7 @@ static __device__ __forceinline__ void solve3(double A00, double A01, double A02
 }
 
 // exact removal of the velocity components along the three edges of a rigid water
-static __device__ __forceinline__ void settle_velocities(const double (&x)[4][3], double (&v)[4][3], double mO, double mH)
+static __device__ __forceinline__ void settle_velocities(const double (&x)[3][3], double (&v)[3][3], double mO, double mH)
 {
     const double im[3] = {1.0 / mO, 1.0 / mH, 1.0 / mH};
     double u[3][3], b[3];  // edges: k -> (k+1)%3
@@ -604,49 +655,28 @@ static __device__ __noinline__ void rattle_cluster(const int32_t* pairs, const d
 }
 
 // ------------------------------------------------------------------------------------------ units
-// three normals for atom `unit`
-template <bool NOISE32>
-__device__ __forceinline__ void atom_normals(uint64_t seed, uint64_t rid, uint32_t draw, uint32_t tag, uint32_t unit,
-                                             double& n0, double& n1, double& n2)
+struct N3 { double x, y, z; };
+
+// three normals for atom `unit` (fp64 Box-Muller): start and midpoint velocities
+static __device__ __noinline__ N3 normals3_f64(uint64_t seed, uint64_t rid, uint32_t draw, uint32_t tag, uint32_t unit)
 {
     const lsi::Philox4 r = lsi::philox_block(seed, rid, draw, tag, unit);
-    if (NOISE32) {
-        float a, b, c, d;
-        lsi::box_muller(r.x, r.y, a, b);
-        lsi::box_muller(r.z, r.w, c, d);
-        n0 = (double)a; n1 = (double)b; n2 = (double)c;
-    } else {
-        double d;
-        lsi::box_muller(r.x, r.y, n0, n1);
-        lsi::box_muller(r.z, r.w, n2, d);
-    }
+    N3 n;
+    double d;
+    lsi::box_muller(r.x, r.y, n.x, n.y);
+    lsi::box_muller(r.z, r.w, n.z, d);
+    return n;
 }
-
-// Per-team context in shared memory: what the unit-mapped substeps need.  They are separate
-// (non-inlined, non-template) functions so that the fp64 constraint algebra gets its own register
-// allocation and is compiled once per `real`, not once per kernel instantiation.
-template <typename real>
-struct TeamCtx {
-    Smem<real> s;
-    const PKUnit* units;
-    const int32_t *gc_off, *gc_pairs, *gc_atom_off, *gc_atoms;
-    const double* gc_dist;
-    double box[3], inv_box[3], oh, hh, tol;
-    uint64_t seed;
-    int periodic;
-};
-
-template <typename real>
-__device__ __forceinline__ void fill_ctx(TeamCtx<real>* c, const PKParams& P, const Smem<real>& s)
+// fp32 Box-Muller ("mixed" O noise, as OpenMM's mixed mode draws single-precision gaussians)
+static __device__ __noinline__ N3 normals3_f32(uint64_t seed, uint64_t rid, uint32_t draw, uint32_t tag, uint32_t unit)
 {
-    c->s = s;
-    c->units = P.units;
-    c->gc_off = P.gc_off; c->gc_pairs = P.gc_pairs; c->gc_atom_off = P.gc_atom_off; c->gc_atoms = P.gc_atoms;
-    c->gc_dist = P.gc_dist;
-    for (int k = 0; k < 3; ++k) { c->box[k] = P.box[k]; c->inv_box[k] = P.inv_box[k]; }
-    c->oh = P.oh; c->hh = P.hh; c->tol = P.tol;
-    c->seed = P.seed;
-    c->periodic = P.nb_method == LSI_NB_CUTOFF_PERIODIC;
+    const lsi::Philox4 r = lsi::philox_block(seed, rid, draw, tag, unit);
+    float a, b, c, d;
+    lsi::box_muller(r.x, r.y, a, b);
+    lsi::box_muller(r.z, r.w, c, d);
+    N3 n;
+    n.x = (double)a; n.y = (double)b; n.z = (double)c;
+    return n;
 }
 
 template <typename real>
@@ -654,17 +684,19 @@ struct UnitOps {
     const TeamCtx<real>& C;
     const Smem<real>& s;
 
-    __device__ __forceinline__ void load(const double* arr, const PKUnit& U, double (&a)[4][3]) const
+    template <int NA>
+    __device__ __forceinline__ void load(const double* arr, const PKUnit& U, double (&a)[NA][3]) const
     {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < NA; ++k)
 #pragma unroll
             for (int c = 0; c < 3; ++c) a[k][c] = k < U.n ? arr[3 * U.a[k] + c] : 0.0;
     }
-    __device__ __forceinline__ void store(double* arr, const PKUnit& U, const double (&a)[4][3]) const
+    template <int NA>
+    __device__ __forceinline__ void store(double* arr, const PKUnit& U, const double (&a)[NA][3]) const
     {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < NA; ++k)
             if (k < U.n) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) arr[3 * U.a[k] + c] = a[k][c];
@@ -680,12 +712,13 @@ struct UnitOps {
         }
         typename Vec<real>::r4 q;
         q.x = (real)px; q.y = (real)py; q.z = (real)pz; q.w = s.qk[i];
-        s.xq[i] = q;
+        s.xq[2 * i] = q;
     }
-    __device__ __forceinline__ void stage(const PKUnit& U, const double (&x)[4][3]) const
+    template <int NA>
+    __device__ __forceinline__ void stage(const PKUnit& U, const double (&x)[NA][3]) const
     {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < NA; ++k)
             if (k < U.n) stage_atom(U.a[k], x[k][0], x[k][1], x[k][2]);
     }
     __device__ __forceinline__ void inv_masses(const PKUnit& U, double (&im)[4]) const
@@ -693,31 +726,28 @@ struct UnitOps {
 #pragma unroll
         for (int k = 0; k < 4; ++k) im[k] = k < U.n ? s.invm[U.a[k]] : 0.0;
     }
-    __device__ __forceinline__ double kinetic(const PKUnit& U, const double (&v)[4][3]) const
+    template <int NA>
+    __device__ __forceinline__ double kinetic(const PKUnit& U, const double (&v)[NA][3]) const
     {
         double ke = 0.0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < NA; ++k)
             if (k < U.n) ke += 0.5 * s.mass[U.a[k]] * (v[k][0] * v[k][0] + v[k][1] * v[k][1] + v[k][2] * v[k][2]);
         return ke;
     }
-    __device__ __forceinline__ void project_positions(const PKUnit& U, const double (&x0)[4][3], double (&x1)[4][3]) const
+    // O noise on the unit's atoms, in shared memory (a loop, not unrolled: Philox + Box-Muller is large)
+    __device__ __forceinline__ void noise(const PKUnit& U, int u, double a, double b, uint64_t rid, uint32_t draw) const
     {
-        if (U.kind == UNIT_WATER) settle_positions(x0, x1, s.mass[U.a[0]], s.mass[U.a[1]], C.oh, C.hh);
-        else if (U.kind == UNIT_STAR) {
-            double im[4];
-            inv_masses(U, im);
-            const double d[3] = {U.d[0], U.d[1], U.d[2]};
-            star_positions(x0, x1, U.n - 1, d, im, C.tol);
-        }
-    }
-    __device__ __forceinline__ void project_velocities(const PKUnit& U, const double (&x)[4][3], double (&v)[4][3]) const
-    {
-        if (U.kind == UNIT_WATER) settle_velocities(x, v, s.mass[U.a[0]], s.mass[U.a[1]]);
-        else if (U.kind == UNIT_STAR) {
-            double im[4];
-            inv_masses(U, im);
-            star_velocities(x, v, U.n - 1, im);
+        constexpr bool NOISE32 = sizeof(real) == 4;
+#pragma unroll 1
+        for (int k = 0; k < U.n; ++k) {
+            const int i = C.units[u].a[k];
+            const N3 n = NOISE32 ? normals3_f32(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i)
+                                 : normals3_f64(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i);
+            const double sg = b * s.sigv[i];
+            s.v[3 * i] = a * s.v[3 * i] + sg * n.x;
+            s.v[3 * i + 1] = a * s.v[3 * i + 1] + sg * n.y;
+            s.v[3 * i + 2] = a * s.v[3 * i + 2] + sg * n.z;
         }
     }
 
@@ -748,64 +778,181 @@ struct UnitOps {
     }
 };
 
-// constraints at the start of a leg: Context.applyConstraints / applyVelocityConstraints
-// (bookkeepers.py:206-208); stages the unit's positions; returns its kinetic energy afterwards
+// ---- rigid water (SETTLE).  R: x <- x + h v; constrain positions; v <- v + (x - x1)/h; constrain
+// velocities (langevin.py:124-139).  h = 0: Context.applyConstraints / applyVelocityConstraints at the
+// start of a leg (bookkeepers.py:206-208).  Stages the new positions.  Returns KE after (h = 0) or its change.
 template <typename real>
-__device__ __noinline__ double unit_init(const TeamCtx<real>* ctx, int u)
+__device__ __noinline__ double water_R(const TeamCtx<real>* ctx, int u, double h)
 {
     const TeamCtx<real>& C = *ctx;
     const Smem<real> s = C.s;
     const UnitOps<real> ops{C, s};
     const PKUnit U = C.units[u];
-    if (U.kind == UNIT_GENERIC) {
-        const int c = U.a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
-        for (int q = a0; q < a1; ++q) {
-            const int i = C.gc_atoms[q];
-            for (int k = 0; k < 3; ++k) s.xref[3 * i + k] = s.x[3 * i + k];
-        }
-        ops.generic_shake(c);
-        ops.generic_rattle(c);
-        ops.generic_stage(a0, a1);
-        return ops.generic_kinetic(a0, a1);
+    const double mO = s.mass[U.a[0]], mH = s.mass[U.a[1]];
+    double x[3][3];
+    double ke0 = 0.0;
+    {
+        double x0[3][3], v[3][3];
+        ops.load(s.x, U, x0);
+        ops.load(s.v, U, v);
+        if (h != 0.0) ke0 = ops.kinetic(U, v);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x[k][c] = x0[k][c] + h * v[k][c];
+        settle_positions(x0, x, mO, mH, C.oh, C.hh);
     }
-    double x[4][3], v[4][3];
-    ops.load(s.x, U, x);
+    double v[3][3];
     ops.load(s.v, U, v);
-    if (U.kind != UNIT_FREE) {
-        double x0[4][3];
+    if (h != 0.0) {
+        double x0[3][3];
+        ops.load(s.x, U, x0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double x1 = x0[k][c] + h * v[k][c];  // the unconstrained update
+                v[k][c] = v[k][c] + (x[k][c] - x1) / h;
+            }
+    }
+    ops.store(s.x, U, x);
+    ops.stage(U, x);
+    settle_velocities(x, v, mO, mH);
+    ops.store(s.v, U, v);
+    return ops.kinetic(U, v) - ke0;
+}
+
+// velocity part of V and O for a rigid water: kick (f != nullptr) or noise, then project; returns change of KE
+template <typename real>
+__device__ __noinline__ double water_VO(const TeamCtx<real>* ctx, int u, double h, const real* __restrict__ f, double a, double b,
+                                        uint64_t rid, uint32_t draw, int want_dke)
+{
+    const TeamCtx<real>& C = *ctx;
+    const Smem<real> s = C.s;
+    const UnitOps<real> ops{C, s};
+    const PKUnit U = C.units[u];
+    double v[3][3];
+    double ke0 = 0.0;
+    if (f) {
+        ops.load(s.v, U, v);
+        if (want_dke) ke0 = ops.kinetic(U, v);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int i = U.a[k];
+            const double hm = h * s.invm[i];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[k][c] = v[k][c] + hm * (double)f[3 * i + c];
+        }
+    } else {
+        ops.load(s.v, U, v);
+        ke0 = ops.kinetic(U, v);
+        ops.noise(U, u, a, b, rid, draw);
+        ops.load(s.v, U, v);
+    }
+    double x[3][3];
+    ops.load(s.x, U, x);
+    settle_velocities(x, v, s.mass[U.a[0]], s.mass[U.a[1]]);
+    ops.store(s.v, U, v);
+    return want_dke ? ops.kinetic(U, v) - ke0 : 0.0;
+}
+
+// ---- star of pair constraints (H-bonds): same contracts as the water functions
+template <typename real>
+__device__ __noinline__ double star_R(const TeamCtx<real>* ctx, int u, double h)
+{
+    const TeamCtx<real>& C = *ctx;
+    const Smem<real> s = C.s;
+    const UnitOps<real> ops{C, s};
+    const PKUnit U = C.units[u];
+    double im[4];
+    ops.inv_masses(U, im);
+    const double d[3] = {U.d[0], U.d[1], U.d[2]};
+    double x[4][3];
+    double ke0 = 0.0;
+    {
+        double x0[4][3], v[4][3];
+        ops.load(s.x, U, x0);
+        ops.load(s.v, U, v);
+        if (h != 0.0) ke0 = ops.kinetic(U, v);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) x0[k][c] = x[k][c];
-        ops.project_positions(U, x0, x);
-        ops.project_velocities(U, x, v);
-        ops.store(s.x, U, x);
-        ops.store(s.v, U, v);
+            for (int c = 0; c < 3; ++c) x[k][c] = x0[k][c] + h * v[k][c];
+        star_positions(x0, x, U.n - 1, d, im, C.tol);
     }
+    double v[4][3];
+    ops.load(s.v, U, v);
+    if (h != 0.0) {
+        double x0[4][3];
+        ops.load(s.x, U, x0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double x1 = x0[k][c] + h * v[k][c];
+                v[k][c] = v[k][c] + (x[k][c] - x1) / h;
+            }
+    }
+    ops.store(s.x, U, x);
     ops.stage(U, x);
-    return ops.kinetic(U, v);
+    star_velocities(x, v, U.n - 1, im);
+    ops.store(s.v, U, v);
+    return ops.kinetic(U, v) - ke0;
 }
 
-// R: x <- x + h v; constrain positions; v <- v + (x - x1)/h; constrain velocities
-// (langevin.py:124-139); stages the new positions; returns the change of the unit's kinetic energy
 template <typename real>
-__device__ __noinline__ double unit_R(const TeamCtx<real>* ctx, int u, double h)
+__device__ __noinline__ double star_VO(const TeamCtx<real>* ctx, int u, double h, const real* __restrict__ f, double a, double b,
+                                       uint64_t rid, uint32_t draw, int want_dke)
 {
     const TeamCtx<real>& C = *ctx;
     const Smem<real> s = C.s;
     const UnitOps<real> ops{C, s};
     const PKUnit U = C.units[u];
-    if (U.kind == UNIT_GENERIC) {
-        const int c = U.a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
-        const double ke0 = ops.generic_kinetic(a0, a1);
-        for (int q = a0; q < a1; ++q) {
-            const int i = C.gc_atoms[q];
-            for (int k = 0; k < 3; ++k) {
-                s.xref[3 * i + k] = s.x[3 * i + k];
-                s.x[3 * i + k] = s.x[3 * i + k] + h * s.v[3 * i + k];
+    double im[4];
+    ops.inv_masses(U, im);
+    double v[4][3];
+    double ke0 = 0.0;
+    ops.load(s.v, U, v);
+    if (f) {
+        if (want_dke) ke0 = ops.kinetic(U, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < U.n) {
+                const int i = U.a[k];
+                const double hm = h * im[k];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[k][c] = v[k][c] + hm * (double)f[3 * i + c];
             }
+    } else {
+        ke0 = ops.kinetic(U, v);
+        ops.noise(U, u, a, b, rid, draw);
+        ops.load(s.v, U, v);
+    }
+    double x[4][3];
+    ops.load(s.x, U, x);
+    star_velocities(x, v, U.n - 1, im);
+    ops.store(s.v, U, v);
+    return want_dke ? ops.kinetic(U, v) - ke0 : 0.0;
+}
+
+// ---- generic clusters (Gauss-Seidel SHAKE / RATTLE in shared memory by the owner lane)
+template <typename real>
+__device__ __noinline__ double generic_R(const TeamCtx<real>* ctx, int u, double h)
+{
+    const TeamCtx<real>& C = *ctx;
+    const Smem<real> s = C.s;
+    const UnitOps<real> ops{C, s};
+    const int c = C.units[u].a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
+    const double ke0 = h != 0.0 ? ops.generic_kinetic(a0, a1) : 0.0;
+    for (int q = a0; q < a1; ++q) {
+        const int i = C.gc_atoms[q];
+        for (int k = 0; k < 3; ++k) {
+            s.xref[3 * i + k] = s.x[3 * i + k];
+            s.x[3 * i + k] = s.x[3 * i + k] + h * s.v[3 * i + k];
         }
-        ops.generic_shake(c);
+    }
+    ops.generic_shake(c);
+    if (h != 0.0)
         for (int q = a0; q < a1; ++q) {
             const int i = C.gc_atoms[q];
             for (int k = 0; k < 3; ++k) {
@@ -813,141 +960,113 @@ __device__ __noinline__ double unit_R(const TeamCtx<real>* ctx, int u, double h)
                 s.v[3 * i + k] = s.v[3 * i + k] + (s.x[3 * i + k] - x1) / h;
             }
         }
-        ops.generic_rattle(c);
-        ops.generic_stage(a0, a1);
-        return ops.generic_kinetic(a0, a1) - ke0;
-    }
-    double x[4][3], v[4][3];
-    ops.load(s.x, U, x);
-    ops.load(s.v, U, v);
-    if (U.kind == UNIT_FREE) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) x[0][c] = x[0][c] + h * v[0][c];
-        ops.store(s.x, U, x);
-        ops.stage(U, x);
-        return 0.0;
-    }
-    const double ke0 = ops.kinetic(U, v);
-    double x0[4][3];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            x0[k][c] = x[k][c];
-            x[k][c] = x[k][c] + h * v[k][c];
-        }
-    ops.project_positions(U, x0, x);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const double x1 = x0[k][c] + h * v[k][c];  // the unconstrained update
-            v[k][c] = v[k][c] + (x[k][c] - x1) / h;
-        }
-    ops.project_velocities(U, x, v);
-    ops.store(s.x, U, x);
-    ops.store(s.v, U, v);
-    ops.stage(U, x);
-    return ops.kinetic(U, v) - ke0;
+    ops.generic_rattle(c);
+    ops.generic_stage(a0, a1);
+    return ops.generic_kinetic(a0, a1) - ke0;
 }
 
-// V: v <- v + h f / m; constrain velocities (langevin.py:141-163); returns the change of KE if asked
 template <typename real>
-__device__ __noinline__ double unit_V(const TeamCtx<real>* ctx, int u, double h, const real* __restrict__ f, int want_dke)
-{
-    const TeamCtx<real>& C = *ctx;
-    const Smem<real> s = C.s;
-    const UnitOps<real> ops{C, s};
-    const PKUnit U = C.units[u];
-    if (U.kind == UNIT_GENERIC) {
-        const int c = U.a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
-        const double ke0 = want_dke ? ops.generic_kinetic(a0, a1) : 0.0;
-        for (int q = a0; q < a1; ++q) {
-            const int i = C.gc_atoms[q];
-            const double hm = h * s.invm[i];
-            for (int k = 0; k < 3; ++k) s.v[3 * i + k] = s.v[3 * i + k] + hm * (double)f[3 * i + k];
-        }
-        ops.generic_rattle(c);
-        return want_dke ? ops.generic_kinetic(a0, a1) - ke0 : 0.0;
-    }
-    double v[4][3];
-    ops.load(s.v, U, v);
-    const double ke0 = want_dke ? ops.kinetic(U, v) : 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (k < U.n) {
-            const int i = U.a[k];
-            const double hm = h * s.invm[i];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) v[k][c] = v[k][c] + hm * (double)f[3 * i + c];
-        }
-    if (U.kind != UNIT_FREE) {
-        double x[4][3];
-        ops.load(s.x, U, x);
-        ops.project_velocities(U, x, v);
-    }
-    ops.store(s.v, U, v);
-    return want_dke ? ops.kinetic(U, v) - ke0 : 0.0;
-}
-
-// O: v <- a v + b sqrt(kT/m) xi; constrain velocities; returns the heat = change of KE (langevin.py:165-175)
-template <typename real>
-__device__ __noinline__ double unit_O(const TeamCtx<real>* ctx, int u, double a, double b, uint64_t rid, uint32_t draw)
+__device__ __noinline__ double generic_VO(const TeamCtx<real>* ctx, int u, double h, const real* __restrict__ f, double a, double b,
+                                          uint64_t rid, uint32_t draw, int want_dke)
 {
     constexpr bool NOISE32 = sizeof(real) == 4;
     const TeamCtx<real>& C = *ctx;
     const Smem<real> s = C.s;
     const UnitOps<real> ops{C, s};
-    const PKUnit U = C.units[u];
-    if (U.kind == UNIT_GENERIC) {
-        const int c = U.a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
-        const double ke0 = ops.generic_kinetic(a0, a1);
-        for (int q = a0; q < a1; ++q) {
-            const int i = C.gc_atoms[q];
-            double n0, n1, n2;
-            atom_normals<NOISE32>(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i, n0, n1, n2);
+    const int c = C.units[u].a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
+    const double ke0 = want_dke ? ops.generic_kinetic(a0, a1) : 0.0;
+    for (int q = a0; q < a1; ++q) {
+        const int i = C.gc_atoms[q];
+        if (f) {
+            const double hm = h * s.invm[i];
+            for (int k = 0; k < 3; ++k) s.v[3 * i + k] = s.v[3 * i + k] + hm * (double)f[3 * i + k];
+        } else {
+            const N3 n = NOISE32 ? normals3_f32(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i)
+                                 : normals3_f64(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i);
             const double sg = b * s.sigv[i];
-            s.v[3 * i] = a * s.v[3 * i] + sg * n0;
-            s.v[3 * i + 1] = a * s.v[3 * i + 1] + sg * n1;
-            s.v[3 * i + 2] = a * s.v[3 * i + 2] + sg * n2;
+            s.v[3 * i] = a * s.v[3 * i] + sg * n.x;
+            s.v[3 * i + 1] = a * s.v[3 * i + 1] + sg * n.y;
+            s.v[3 * i + 2] = a * s.v[3 * i + 2] + sg * n.z;
         }
-        ops.generic_rattle(c);
-        return ops.generic_kinetic(a0, a1) - ke0;
     }
-    double v[4][3];
-    ops.load(s.v, U, v);
-    const double ke0 = ops.kinetic(U, v);
+    ops.generic_rattle(c);
+    return want_dke ? ops.generic_kinetic(a0, a1) - ke0 : 0.0;
+}
+
+// ---- free atom
+template <typename real>
+__device__ __noinline__ double free_O(const TeamCtx<real>* ctx, int i, double a, double b, uint64_t rid, uint32_t draw)
+{
+    constexpr bool NOISE32 = sizeof(real) == 4;
+    const TeamCtx<real>& C = *ctx;
+    const Smem<real> s = C.s;
+    const N3 n = NOISE32 ? normals3_f32(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i) : normals3_f64(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i);
+    const double sg = b * s.sigv[i];
+    const double v0 = s.v[3 * i], v1 = s.v[3 * i + 1], v2 = s.v[3 * i + 2];
+    const double w0 = a * v0 + sg * n.x, w1 = a * v1 + sg * n.y, w2 = a * v2 + sg * n.z;
+    s.v[3 * i] = w0; s.v[3 * i + 1] = w1; s.v[3 * i + 2] = w2;
+    return 0.5 * s.mass[i] * (w0 * w0 + w1 * w1 + w2 * w2) - 0.5 * s.mass[i] * (v0 * v0 + v1 * v1 + v2 * v2);
+}
+
+// ---- dispatch by unit kind (units are sorted by kind, so warps rarely diverge here)
+template <typename real>
+__device__ __forceinline__ double unit_R(const TeamCtx<real>* ctx, int u, double h)
+{
+    const int kind = ctx->units[u].kind;
+    if (kind == UNIT_WATER) return water_R<real>(ctx, u, h);
+    if (kind == UNIT_STAR) return star_R<real>(ctx, u, h);
+    if (kind == UNIT_GENERIC) return generic_R<real>(ctx, u, h);
+    const Smem<real>& s = ctx->s;
+    const UnitOps<real> ops{*ctx, s};
+    const int i = ctx->units[u].a[0];
+    const double px = s.x[3 * i] + h * s.v[3 * i], py = s.x[3 * i + 1] + h * s.v[3 * i + 1], pz = s.x[3 * i + 2] + h * s.v[3 * i + 2];
+    s.x[3 * i] = px; s.x[3 * i + 1] = py; s.x[3 * i + 2] = pz;
+    ops.stage_atom(i, px, py, pz);
+    if (h != 0.0) return 0.0;
+    return 0.5 * s.mass[i] * (s.v[3 * i] * s.v[3 * i] + s.v[3 * i + 1] * s.v[3 * i + 1] + s.v[3 * i + 2] * s.v[3 * i + 2]);
+}
+
+template <typename real>
+__device__ __forceinline__ double unit_V(const TeamCtx<real>* ctx, int u, double h, const real* __restrict__ f, int want_dke)
+{
+    const int kind = ctx->units[u].kind;
+    if (kind == UNIT_WATER) return water_VO<real>(ctx, u, h, f, 0.0, 0.0, 0ull, 0u, want_dke);
+    if (kind == UNIT_STAR) return star_VO<real>(ctx, u, h, f, 0.0, 0.0, 0ull, 0u, want_dke);
+    if (kind == UNIT_GENERIC) return generic_VO<real>(ctx, u, h, f, 0.0, 0.0, 0ull, 0u, want_dke);
+    const Smem<real>& s = ctx->s;
+    const int i = ctx->units[u].a[0];
+    const double hm = h * s.invm[i];
+    const double v0 = s.v[3 * i], v1 = s.v[3 * i + 1], v2 = s.v[3 * i + 2];
+    const double w0 = v0 + hm * (double)f[3 * i], w1 = v1 + hm * (double)f[3 * i + 1], w2 = v2 + hm * (double)f[3 * i + 2];
+    s.v[3 * i] = w0; s.v[3 * i + 1] = w1; s.v[3 * i + 2] = w2;
+    return want_dke ? 0.5 * s.mass[i] * ((w0 * w0 + w1 * w1 + w2 * w2) - (v0 * v0 + v1 * v1 + v2 * v2)) : 0.0;
+}
+
+template <typename real>
+__device__ __forceinline__ double unit_O(const TeamCtx<real>* ctx, int u, double a, double b, uint64_t rid, uint32_t draw)
+{
+    const int kind = ctx->units[u].kind;
+    if (kind == UNIT_WATER) return water_VO<real>(ctx, u, 0.0, nullptr, a, b, rid, draw, 1);
+    if (kind == UNIT_STAR) return star_VO<real>(ctx, u, 0.0, nullptr, a, b, rid, draw, 1);
+    if (kind == UNIT_GENERIC) return generic_VO<real>(ctx, u, 0.0, nullptr, a, b, rid, draw, 1);
+    return free_O<real>(ctx, ctx->units[u].a[0], a, b, rid, draw);
+}
+
+template <typename real>
+__device__ __forceinline__ double unit_kinetic(const TeamCtx<real>* ctx, int u)
+{
+    const Smem<real>& s = ctx->s;
+    const PKUnit U = ctx->units[u];
+    const UnitOps<real> ops{*ctx, s};
+    if (U.kind == UNIT_GENERIC) return ops.generic_kinetic(ctx->gc_atom_off[U.a[0]], ctx->gc_atom_off[U.a[0] + 1]);
+    double ke = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if (k < U.n) {
             const int i = U.a[k];
-            double n0, n1, n2;
-            atom_normals<NOISE32>(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i, n0, n1, n2);
-            const double sg = b * s.sigv[i];
-            v[k][0] = a * v[k][0] + sg * n0;
-            v[k][1] = a * v[k][1] + sg * n1;
-            v[k][2] = a * v[k][2] + sg * n2;
+            ke += 0.5 * s.mass[i] * (s.v[3 * i] * s.v[3 * i] + s.v[3 * i + 1] * s.v[3 * i + 1] + s.v[3 * i + 2] * s.v[3 * i + 2]);
         }
-    if (U.kind != UNIT_FREE) {
-        double x[4][3];
-        ops.load(s.x, U, x);
-        ops.project_velocities(U, x, v);
-    }
-    ops.store(s.v, U, v);
-    return ops.kinetic(U, v) - ke0;
-}
-
-template <typename real>
-__device__ __noinline__ double unit_kinetic(const TeamCtx<real>* ctx, int u)
-{
-    const TeamCtx<real>& C = *ctx;
-    const Smem<real> s = C.s;
-    const UnitOps<real> ops{C, s};
-    const PKUnit U = C.units[u];
-    if (U.kind == UNIT_GENERIC) return ops.generic_kinetic(C.gc_atom_off[U.a[0]], C.gc_atom_off[U.a[0] + 1]);
-    double v[4][3];
-    ops.load(s.v, U, v);
-    return ops.kinetic(U, v);
+    return ke;
 }
 
 // tables -> team shared memory
@@ -962,9 +1081,22 @@ __device__ __forceinline__ void load_tables(const PKParams& P, const Smem<real>&
         s.sigv[i] = sqrt(P.kT / m);
         const typename Vec<real>::r4 p = nbp[i];
         s.qk[i] = p.x;
-        typename Vec<real>::r2 l;
-        l.x = p.y; l.y = p.z;
-        s.ljp[i] = l;
+        typename Vec<real>::r4 l;
+        l.x = p.y; l.y = p.z; l.z = (real)0; l.w = (real)0;
+        s.xq[2 * i + 1] = l;
+    }
+}
+
+// Maxwell-Boltzmann velocities for every atom (start of the protocol, midpoint of the "configuration" marginal)
+template <typename real>
+__device__ __noinline__ void draw_velocities(const TeamCtx<real>* ctx, uint64_t rid, uint32_t draw, uint32_t tag, const double* mass,
+                                             double kT, int tid, int T)
+{
+    const Smem<real>& s = ctx->s;
+    for (int i = tid; i < ctx->N; i += T) {
+        const N3 n = normals3_f64(ctx->seed, rid, draw, tag, (uint32_t)i);
+        const double sg = sqrt(kT / mass[i]);
+        s.v[3 * i] = sg * n.x; s.v[3 * i + 1] = sg * n.y; s.v[3 * i + 2] = sg * n.z;
     }
 }
 
@@ -994,18 +1126,14 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
     {
         const double* xs = P.x0 ? P.x0 + r * D : P.x_cache + lsi::cache_index(P.seed, rid, P.n_cache) * D;
         for (int k = tid; k < D; k += T) s.x[k] = xs[k];
-        if (P.v0) {
+        if (P.v0)
             for (int k = tid; k < D; k += T) s.v[k] = P.v0[r * D + k];
-        } else {
-            for (int i = tid; i < N; i += T) {
-                double n0, n1, n2;
-                atom_normals<false>(P.seed, rid, 0u, LSI_TAG_V0, (uint32_t)i, n0, n1, n2);
-                const double sg = sqrt(P.kT / P.mass[i]);
-                s.v[3 * i] = sg * n0; s.v[3 * i + 1] = sg * n1; s.v[3 * i + 2] = sg * n2;
-            }
-        }
     }
     team_sync<WT>();
+    if (!P.v0) {
+        draw_velocities<real>(ctx, rid, 0u, LSI_TAG_V0, P.mass, P.kT, tid, T);
+        team_sync<WT>();
+    }
 
     real* const scratch = s.f + (size_t)(P.n_slots - 1) * D;  // DIAG: an extra slot that is never a cache
     double heat_run = 0.0;  // per-lane share of the heat accumulated so far (all legs)
@@ -1014,18 +1142,13 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
             if (P.flags & LSI_FLAG_ROUND_MIDPOINT_X_FP32)
                 for (int k = tid; k < D; k += T) s.x[k] = (double)(float)s.x[k];
             if (P.marginal == LSI_MARGINAL_CONFIGURATION)
-                for (int i = tid; i < N; i += T) {
-                    double n0, n1, n2;
-                    atom_normals<false>(P.seed, rid, (uint32_t)(leg - 1), LSI_TAG_VMID, (uint32_t)i, n0, n1, n2);
-                    const double sg = s.sigv[i];
-                    s.v[3 * i] = sg * n0; s.v[3 * i + 1] = sg * n1; s.v[3 * i + 2] = sg * n2;
-                }
+                draw_velocities<real>(ctx, rid, (uint32_t)(leg - 1), LSI_TAG_VMID, P.mass, P.kT, tid, T);
             team_sync<WT>();
         }
         double ke0 = 0.0;
-        PK_FOR_UNITS(u) ke0 += unit_init<real>(ctx, u);
+        PK_FOR_UNITS(u) ke0 += unit_R<real>(ctx, u, 0.0);  // h = 0: project onto the constraints, stage
         unsigned valid = 0u;  // bit per force-cache slot (team-uniform)
-        double pe_cur = compute_forces<real, PERIODIC, WT, APL, true>(P, s, -1, scratch, tid, T);
+        double pe_cur = compute_forces<real, PERIODIC, WT, APL, true>(ctx, -1, scratch, tid, T);
         const double pe0 = pe_cur;
         const double heat0 = heat_run;
         double wd_ke = 0.0, wd_pe = 0.0;
@@ -1050,7 +1173,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
                     valid = 0u;
                     if (DIAG) {
                         wd_ke += dke;
-                        const double pe_new = compute_forces<real, PERIODIC, WT, APL, true>(P, s, -1, scratch, tid, T);
+                        const double pe_new = compute_forces<real, PERIODIC, WT, APL, true>(ctx, -1, scratch, tid, T);
                         wd_pe += pe_new - pe_cur;
                         pe_cur = pe_new;
                     }
@@ -1058,7 +1181,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
                     const int slot = P.op_slot[op];
                     real* fs = s.f + (size_t)slot * D;
                     if (!((valid >> slot) & 1u)) {
-                        compute_forces<real, PERIODIC, WT, APL, false>(P, s, P.slot_group[slot], fs, tid, T);
+                        compute_forces<real, PERIODIC, WT, APL, false>(ctx, P.slot_group[slot], fs, tid, T);
                         valid |= 1u << slot;
                     }
                     double dke = 0.0;
@@ -1090,7 +1213,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
         }
         // ---- end of leg: W = ((E1 - E0) - (heat1 - heat0)) / kT
         {
-            const double pe1 = DIAG ? pe_cur : compute_forces<real, PERIODIC, WT, APL, true>(P, s, -1, scratch, tid, T);
+            const double pe1 = DIAG ? pe_cur : compute_forces<real, PERIODIC, WT, APL, true>(ctx, -1, scratch, tid, T);
             double ke1 = 0.0;
             PK_FOR_UNITS(u) ke1 += unit_kinetic<real>(ctx, u);
             const double dq = heat_run - heat0;
@@ -1133,7 +1256,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384) particles_energy_kernel(const 
         const UnitOps<real> ops{*ctx, s};
         for (int i = tid; i < N; i += T) ops.stage_atom(i, s.x[3 * i], s.x[3 * i + 1], s.x[3 * i + 2]);
     }
-    const double e = compute_forces<real, PERIODIC, WT, APL, true>(P, s, P.q_group, s.f, tid, T);
+    const double e = compute_forces<real, PERIODIC, WT, APL, true>(ctx, P.q_group, s.f, tid, T);
     if (P.q_energy && tid == 0) P.q_energy[r] = e;
     if (P.q_forces) for (int k = tid; k < D; k += T) P.q_forces[r * D + k] = (double)s.f[k];
 }
@@ -1149,7 +1272,7 @@ int set_smem(K kernel, size_t bytes)
 template <typename real, bool PERIODIC, bool WT, int APL>
 int launch_protocol3(const PKParams& P, const PKLaunch& L, cudaStream_t st)
 {
-    static_assert(sizeof(TeamCtx<real>) <= 320, "Layout reserves 320 bytes for TeamCtx");
+    static_assert(sizeof(TeamCtx<real>) <= 512, "Layout reserves 512 bytes for TeamCtx");
     const unsigned grid = (unsigned)(WT ? (L.n + L.teams - 1) / L.teams : L.n);
     auto k = particles_protocol_kernel<real, PERIODIC, WT, APL>;
     int rc;
