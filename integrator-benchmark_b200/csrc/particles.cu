@@ -27,6 +27,7 @@ struct DevTables {
     void* nbp_f = nullptr;
     void* nbp_d = nullptr;
     uint32_t* excl = nullptr;
+    uint32_t* excl_lj = nullptr;
     int32_t* perm = nullptr;
     PKUnit* units = nullptr;
     int32_t *gc_off = nullptr, *gc_pairs = nullptr, *gc_atom_off = nullptr, *gc_atoms = nullptr;
@@ -46,8 +47,10 @@ struct lsi_particles {
     double restraint_k = 0;
     int g_nb = 0, g_bond = 0, g_angle = 0, g_tors = 0, g_restr = 0;
     double oh = 0, hh = 0, tol = 1e-8;
+    double settle_c[8] = {0}, settle_m[9] = {0};
     int excl_words = 1;
-    std::vector<uint32_t> excl;
+    std::vector<uint32_t> excl, excl_lj;
+    int n_lj = 0, lj_words = 1;
     std::vector<int32_t> perm;
     std::vector<HostTerm> terms;  // sorted by force group
     int n_tf = 0;
@@ -110,6 +113,7 @@ int get_tables(lsi_particles* p, DevTables** out)
     LSI_CUDA_CHECK(upload(&dd, nd));
     t.nbp_f = df; t.nbp_d = dd;
     LSI_CUDA_CHECK(upload(&t.excl, p->excl));
+    LSI_CUDA_CHECK(upload(&t.excl_lj, p->excl_lj));
     LSI_CUDA_CHECK(upload(&t.perm, p->perm));
     LSI_CUDA_CHECK(upload(&t.units, p->units));
     LSI_CUDA_CHECK(upload(&t.gc_off, p->gc_off));
@@ -152,9 +156,12 @@ void fill_system_params(const lsi_particles* p, const DevTables* t, bool mixed, 
     P.restraint_k = p->restraint_k;
     P.g_nb = p->g_nb; P.g_restr = p->g_restr;
     P.oh = p->oh; P.hh = p->hh; P.tol = p->tol;
+    for (int k = 0; k < 8; ++k) P.settle_c[k] = p->settle_c[k];
+    for (int k = 0; k < 9; ++k) P.settle_m[k] = p->settle_m[k];
     P.mass = t->mass;
     P.nbp = mixed ? t->nbp_f : t->nbp_d;
     P.excl = t->excl;
+    P.excl_lj = t->excl_lj; P.n_lj = p->n_lj; P.lj_words = p->lj_words;
     P.perm = t->perm; P.n_perm = p->n_atoms;
     P.units = t->units;
     P.gc_off = t->gc_off; P.gc_pairs = t->gc_pairs; P.gc_dist = t->gc_dist;
@@ -208,7 +215,7 @@ void lsi_particles_free(lsi_particles* p)
     if (!p) return;
     for (auto& kv : p->dev) {
         DevTables& t = kv.second;
-        cudaFree(t.mass); cudaFree(t.nbp_f); cudaFree(t.nbp_d); cudaFree(t.excl); cudaFree(t.perm); cudaFree(t.units);
+        cudaFree(t.mass); cudaFree(t.nbp_f); cudaFree(t.nbp_d); cudaFree(t.excl); cudaFree(t.excl_lj); cudaFree(t.perm); cudaFree(t.units);
         cudaFree(t.gc_off); cudaFree(t.gc_pairs); cudaFree(t.gc_atom_off); cudaFree(t.gc_atoms); cudaFree(t.gc_dist);
         cudaFree(t.terms_f); cudaFree(t.terms_d); cudaFree(t.gather_off); cudaFree(t.gather_idx);
     }
@@ -332,6 +339,17 @@ LSI_EXPORT int lsi_system_create_particles(const lsi_particles_desc* d, lsi_syst
     if (p->terms.empty()) p->terms.push_back(HostTerm{});  // keeps the device pointers valid
     if (p->terms.size() == 1 && terms.empty()) p->set_hi[0] = 0;
 
+    // exclusion bits over the LJ-active atoms (the partners of the separate Lennard-Jones loop)
+    for (int i = 0; i < N; ++i) p->n_lj += p->epsilon[i] != 0.0;
+    p->lj_words = std::max(1, (p->n_lj + 31) / 32);
+    p->excl_lj.assign((size_t)N * p->lj_words, 0u);
+    for (int i = 0; i < N; ++i)
+        for (int k = 0; k < p->n_lj; ++k) {
+            const int j = p->perm[k];
+            if ((p->excl[(size_t)i * p->excl_words + (j >> 5)] >> (j & 31)) & 1u)
+                p->excl_lj[(size_t)i * p->lj_words + (k >> 5)] |= 1u << (k & 31);
+        }
+
     // ---- units of the owner-mapped substeps: waters, constraint stars, generic clusters, free atoms
     std::vector<int> owner(N, -1);
     for (int k = 0; k < d->n_settle; ++k) {
@@ -350,6 +368,32 @@ LSI_EXPORT int lsi_system_create_particles(const lsi_particles_desc* d, lsi_syst
     }
     if (d->n_settle > 0 && !(p->oh > 0 && p->hh > 0 && p->hh < 2 * p->oh))
         return lsi_set_error(LSI_ERR_ARG, "settle distances must satisfy 0 < hh < 2 oh");
+    if (d->n_settle > 0) {
+        // constants of the rigid geometry; every water must share them (one set per system)
+        const double mO = p->mass[p->units[0].a[0]], mH = p->mass[p->units[0].a[1]];
+        for (const PKUnit& u : p->units)
+            if (p->mass[u.a[0]] != mO || p->mass[u.a[1]] != mH)
+                return lsi_set_error(LSI_ERR_UNSUPPORTED, "all SETTLE waters must have the same masses");
+        const double M = mO + 2.0 * mH, rc = 0.5 * p->hh, hgt = std::sqrt(p->oh * p->oh - rc * rc);
+        const double ra = hgt * 2.0 * mH / M, rb = hgt - ra;
+        const double sc[8] = {mO / M, mH / M, ra, rb, rc, 1.0 / ra, 1.0 / (2.0 * rc), 0.0};
+        for (int k = 0; k < 8; ++k) p->settle_c[k] = sc[k];
+        // C lambda = -b for edges 0: O->H1, 1: H1->H2, 2: H2->O (e0 + e1 + e2 = 0 fixes the dot products)
+        const double im[3] = {1.0 / mO, 1.0 / mH, 1.0 / mH};
+        const double d2[3] = {p->oh * p->oh, p->hh * p->hh, p->oh * p->oh};
+        const double e01 = 0.5 * (d2[2] - d2[0] - d2[1]), e02 = 0.5 * (d2[1] - d2[0] - d2[2]), e12 = 0.5 * (d2[0] - d2[1] - d2[2]);
+        const double C[3][3] = {{d2[0] * (im[1] + im[0]), -im[1] * e01, -im[0] * e02},
+                                {-im[1] * e01, d2[1] * (im[2] + im[1]), -im[2] * e12},
+                                {-im[0] * e02, -im[2] * e12, d2[2] * (im[0] + im[2])}};
+        const double det = C[0][0] * (C[1][1] * C[2][2] - C[1][2] * C[2][1]) - C[0][1] * (C[1][0] * C[2][2] - C[1][2] * C[2][0]) +
+                           C[0][2] * (C[1][0] * C[2][1] - C[1][1] * C[2][0]);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                // inverse of a symmetric matrix: cofactor(j, i) / det
+                p->settle_m[3 * i + j] = -(C[j1][i1] * C[j2][i2] - C[j1][i2] * C[j2][i1]) / det;
+            }
+    }
     {
         // connected components of the pair-constraint graph (union-find), constraints kept in input order
         std::vector<int> parent(N);

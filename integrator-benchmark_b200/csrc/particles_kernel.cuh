@@ -53,31 +53,36 @@ static __device__ __forceinline__ double round_fma(double d, double inv) { retur
 
 // ---- shared-memory layout of one team (host and device agree through this function)
 struct Layout {
-    size_t x, v, xref, mass, invm, sigv, red, ctx, xq, ljp, qk, f, tf, total;
+    uint32_t x, v, xref, mass, invm, sigv, red, ctx, xq, qk, f, tf, total;
 };
 template <typename real>
 __host__ __device__ inline Layout layout(int N, int n_slots, int n_tf, bool generic, bool warp_team)
 {
     Layout L;
-    size_t o = 0;
-    L.x = o; o += sizeof(double) * 3 * (size_t)N;
-    L.v = o; o += sizeof(double) * 3 * (size_t)N;
-    L.xref = o; if (generic) o += sizeof(double) * 3 * (size_t)N;
-    L.mass = o; o += sizeof(double) * (size_t)N;
-    L.invm = o; o += sizeof(double) * (size_t)N;
-    L.sigv = o; o += sizeof(double) * (size_t)N;
-    L.red = o; if (!warp_team) o += sizeof(double) * 32;
-    L.ctx = o; o += 512;  // TeamCtx<real> (static_assert in the kernel file)
-    o = (o + 31) & ~(size_t)31;
-    L.xq = o; o += 8 * sizeof(real) * (size_t)N;  // per atom {x, y, z, q sqrt(K)}, {sigma/2, 2 sqrt(eps), -, -}
-    L.ljp = o;
-    L.qk = o; o += sizeof(real) * (size_t)N;
-    o = (o + 15) & ~(size_t)15;
-    L.f = o; o += sizeof(real) * 3 * (size_t)N * (size_t)n_slots;
-    L.tf = o; o += sizeof(real) * 3 * (size_t)n_tf;
-    L.total = (o + 31) & ~(size_t)31;
+    uint32_t o = 0;
+    L.x = o; o += (uint32_t)sizeof(double) * 3 * N;
+    L.v = o; o += (uint32_t)sizeof(double) * 3 * N;
+    L.xref = o; if (generic) o += (uint32_t)sizeof(double) * 3 * N;
+    L.mass = o; o += (uint32_t)sizeof(double) * N;
+    L.invm = o; o += (uint32_t)sizeof(double) * N;
+    L.sigv = o; o += (uint32_t)sizeof(double) * N;
+    L.red = o; if (!warp_team) o += (uint32_t)sizeof(double) * 32;
+    L.ctx = o; o += 768;  // TeamCtx<real> (static_assert in the kernel file)
+    o = (o + 31u) & ~31u;
+    L.xq = o; o += 8 * (uint32_t)sizeof(real) * N;  // per atom {x, y, z, q sqrt(K)}, {sigma/2, 2 sqrt(eps), -, -}
+    L.qk = o; o += (uint32_t)sizeof(real) * N;
+    o = (o + 15u) & ~15u;
+    L.f = o; o += (uint32_t)sizeof(real) * 3 * N * n_slots;
+    L.tf = o; o += (uint32_t)sizeof(real) * 3 * n_tf;
+    L.total = (o + 31u) & ~31u;
     return L;
 }
+
+// the dynamic shared memory of every kernel in this file; pointers derived from it keep the shared
+// address space inside the non-inlined phase functions (LDS / STS instead of generic loads)
+extern __shared__ __align__(32) unsigned char pk_smem[];
+template <class T>
+__device__ __forceinline__ T* sm(uint32_t off) { return reinterpret_cast<T*>(pk_smem + off); }
 
 template <typename real>
 struct Smem {
@@ -132,18 +137,20 @@ __device__ __forceinline__ double team_sum(double val, double* red, int tid, int
 // algebra its own register allocation.
 template <typename real>
 struct TeamCtx {
-    Smem<real> s;
+    Layout L;
+    uint32_t team_off;
     // units
     const PKUnit* units;
     const int32_t *gc_off, *gc_pairs, *gc_atom_off, *gc_atoms;
     const double* gc_dist;
-    double box[3], inv_box[3], oh, hh, tol;
+    double box[3], inv_box[3], tol;
+    double settle_c[8], settle_m[9];
     uint64_t seed;
     int periodic;
     // forces
-    int N, excl_words, n_terms, n_sets, g_nb, g_restr;
+    int N, excl_words, n_terms, n_sets, g_nb, g_restr, n_lj, lj_words;
     int set_group[kMaxSets], set_lo[kMaxSets], set_hi[kMaxSets];
-    const uint32_t* excl;
+    const uint32_t *excl, *excl_lj;
     const int32_t* perm;
     const PKTerm<real>* terms;
     const int32_t *gather_off, *gather_idx;
@@ -151,9 +158,10 @@ struct TeamCtx {
 };
 
 template <typename real>
-__device__ __forceinline__ void fill_ctx(TeamCtx<real>* c, const PKParams& P, const Smem<real>& s)
+__device__ __forceinline__ void fill_ctx(TeamCtx<real>* c, const PKParams& P, const Layout& L, uint32_t team_off)
 {
-    c->s = s;
+    c->L = L;
+    c->team_off = team_off;
     c->units = P.units;
     c->gc_off = P.gc_off; c->gc_pairs = P.gc_pairs; c->gc_atom_off = P.gc_atom_off; c->gc_atoms = P.gc_atoms;
     c->gc_dist = P.gc_dist;
@@ -161,13 +169,16 @@ __device__ __forceinline__ void fill_ctx(TeamCtx<real>* c, const PKParams& P, co
         c->box[k] = P.box[k]; c->inv_box[k] = P.inv_box[k];
         c->boxr[k] = (real)P.box[k]; c->inv_boxr[k] = (real)P.inv_box[k];
     }
-    c->oh = P.oh; c->hh = P.hh; c->tol = P.tol;
+    c->tol = P.tol;
+    for (int k = 0; k < 8; ++k) c->settle_c[k] = P.settle_c[k];
+    for (int k = 0; k < 9; ++k) c->settle_m[k] = P.settle_m[k];
     c->seed = P.seed;
     c->periodic = P.nb_method == LSI_NB_CUTOFF_PERIODIC;
     c->N = P.N; c->excl_words = P.excl_words; c->n_terms = P.n_terms; c->n_sets = P.n_sets;
     c->g_nb = P.g_nb; c->g_restr = P.g_restr;
     for (int k = 0; k < kMaxSets; ++k) { c->set_group[k] = P.set_group[k]; c->set_lo[k] = P.set_lo[k]; c->set_hi[k] = P.set_hi[k]; }
-    c->excl = P.excl; c->perm = P.perm;
+    c->excl = P.excl; c->excl_lj = P.excl_lj; c->perm = P.perm;
+    c->n_lj = P.n_lj; c->lj_words = P.lj_words;
     c->terms = reinterpret_cast<const PKTerm<real>*>(P.terms);
     c->gather_off = P.gather_off; c->gather_idx = P.gather_idx;
     c->rc2 = (real)P.cutoff2; c->krf = (real)P.krf; c->krf2 = (real)(2.0 * P.krf); c->crf = (real)P.crf;
@@ -185,8 +196,12 @@ __device__ __forceinline__ void min_image(const TeamCtx<real>& C, real& dx, real
 }
 
 // ------------------------------------------------------------------------------------------ forces
-// nonbonded full-shell loop for the APL atoms of this lane
-template <typename real, bool PERIODIC, int APL, bool ENERGY>
+// Nonbonded full-shell loops for the APL atoms of this lane.
+//   COMBINED (every atom carries Lennard-Jones parameters, e.g. alanine dipeptide): one loop, Coulomb + LJ.
+//   otherwise (TIP3P: only the oxygens): a Coulomb loop over all partners with the lane's own charge
+//   factored out of the loop, then an LJ loop over the LJ-active atoms only (perm[0 .. n_lj)), which
+//   warps without LJ-active atoms skip.
+template <typename real, bool PERIODIC, int APL, bool ENERGY, bool COMBINED>
 __device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typename Vec<real>::r4* __restrict__ xq,
                                             const int (&atom)[APL], real (&fx)[APL], real (&fy)[APL], real (&fz)[APL],
                                             real (&en)[APL])
@@ -194,7 +209,6 @@ __device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typena
     using r4 = typename Vec<real>::r4;
     const int N = C.N, W = C.excl_words;
     real xi[APL], yi[APL], zi[APL], qi[APL], hsi[APL], sei[APL];
-    bool lane_lj = false;
 #pragma unroll
     for (int a = 0; a < APL; ++a) {
         const int i = atom[a] >= 0 ? atom[a] : 0;
@@ -203,28 +217,29 @@ __device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typena
         qi[a] = atom[a] >= 0 ? p.w : (real)0;
         hsi[a] = l.x;
         sei[a] = atom[a] >= 0 ? l.y : (real)0;
-        lane_lj = lane_lj || sei[a] != (real)0;
     }
-    const bool warp_lj = __any_sync(0xffffffffu, lane_lj);
     const real bx = C.boxr[0], by = C.boxr[1], bz = C.boxr[2];
     const real ibx = C.inv_boxr[0], iby = C.inv_boxr[1], ibz = C.inv_boxr[2];
     const real rc2 = C.rc2, krf = C.krf, krf2 = C.krf2, crf = C.crf;
 
+    // ---- all partners: Coulomb (+ LJ when COMBINED)
+    real gx[APL], gy[APL], gz[APL], ge[APL];  // Coulomb sums without the lane's own charge
+#pragma unroll
+    for (int a = 0; a < APL; ++a) gx[a] = gy[a] = gz[a] = ge[a] = (real)0;
     for (int jb = 0; jb < N; jb += 32) {
         uint32_t mw[APL];
 #pragma unroll
         for (int a = 0; a < APL; ++a) mw[a] = atom[a] >= 0 ? __ldg(C.excl + (size_t)atom[a] * W + (jb >> 5)) : 0xffffffffu;
         const int jn = min(32, N - jb);
         const r4* __restrict__ xj = xq + 2 * jb;
-#pragma unroll 2
+#pragma unroll 4
         for (int jj = 0; jj < jn; ++jj) {
             const r4 pj = xj[2 * jj];
             real ljx = (real)0, ljy = (real)0;
-            if (warp_lj) {
+            if (COMBINED) {
                 const r4 l = xj[2 * jj + 1];
                 ljx = l.x; ljy = l.y;
             }
-            const bool do_lj = ljy != (real)0;  // warp-uniform: the partner is
 #pragma unroll
             for (int a = 0; a < APL; ++a) {
                 real dx = pj.x - xi[a], dy = pj.y - yi[a], dz = pj.z - zi[a];
@@ -237,20 +252,67 @@ __device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typena
                 bool ok = ((mw[a] >> jj) & 1u) == 0u;  // not excluded, not an exception, not self
                 if (PERIODIC) ok = ok && (r2v < rc2);
                 const real inv_r = rsqrt_(r2v), inv_r2 = inv_r * inv_r;
-                const real qq = qi[a] * pj.w;
-                real fr = PERIODIC ? qq * (inv_r * inv_r2 - krf2) : qq * inv_r * inv_r2;
-                real e = (real)0;
-                if (ENERGY) e = PERIODIC ? qq * (inv_r + krf * r2v - crf) : qq * inv_r;
-                if (do_lj) {
+                if (COMBINED) {
+                    const real qq = qi[a] * pj.w;
+                    real fr = PERIODIC ? qq * (inv_r * inv_r2 - krf2) : qq * inv_r * inv_r2;
                     const real sig = hsi[a] + ljx;
                     const real s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
                     const real t = sei[a] * ljy * s6;  // 4 eps s6
                     fr += t * ((real)12 * s6 - (real)6) * inv_r2;
-                    if (ENERGY) e += t * (s6 - (real)1);
+                    fr = ok ? fr : (real)0;
+                    fx[a] -= fr * dx; fy[a] -= fr * dy; fz[a] -= fr * dz;
+                    if (ENERGY) {
+                        const real e = (PERIODIC ? qq * (inv_r + krf * r2v - crf) : qq * inv_r) + t * (s6 - (real)1);
+                        en[a] += ok ? e : (real)0;
+                    }
+                } else {
+                    real fr = PERIODIC ? pj.w * (inv_r * inv_r2 - krf2) : pj.w * inv_r * inv_r2;
+                    fr = ok ? fr : (real)0;
+                    gx[a] -= fr * dx; gy[a] -= fr * dy; gz[a] -= fr * dz;
+                    if (ENERGY) {
+                        const real e = PERIODIC ? pj.w * (inv_r + krf * r2v - crf) : pj.w * inv_r;
+                        ge[a] += ok ? e : (real)0;
+                    }
                 }
+            }
+        }
+    }
+    if (COMBINED) return;
+#pragma unroll
+    for (int a = 0; a < APL; ++a) {
+        fx[a] += qi[a] * gx[a]; fy[a] += qi[a] * gy[a]; fz[a] += qi[a] * gz[a];
+        if (ENERGY) en[a] += qi[a] * ge[a];
+    }
+
+    // ---- LJ-active partners only
+    const int n_lj = C.n_lj, Wl = C.lj_words;
+#pragma unroll
+    for (int a = 0; a < APL; ++a) {
+        if (!__any_sync(0xffffffffu, sei[a] != (real)0)) continue;  // warp-uniform
+        for (int kb = 0; kb < n_lj; kb += 32) {
+            const uint32_t mw = atom[a] >= 0 ? __ldg(C.excl_lj + (size_t)atom[a] * Wl + (kb >> 5)) : 0xffffffffu;
+            const int kn = min(32, n_lj - kb);
+#pragma unroll 2
+            for (int kk = 0; kk < kn; ++kk) {
+                const int j = __ldg(C.perm + kb + kk);
+                const r4 pj = xq[2 * j], l = xq[2 * j + 1];
+                real dx = pj.x - xi[a], dy = pj.y - yi[a], dz = pj.z - zi[a];
+                if (PERIODIC) {
+                    dx = dx - bx * round_fma(dx, ibx);
+                    dy = dy - by * round_fma(dy, iby);
+                    dz = dz - bz * round_fma(dz, ibz);
+                }
+                const real r2v = dx * dx + dy * dy + dz * dz;
+                bool ok = ((mw >> kk) & 1u) == 0u;
+                if (PERIODIC) ok = ok && (r2v < rc2);
+                const real inv_r = rsqrt_(r2v), inv_r2 = inv_r * inv_r;
+                const real sig = hsi[a] + l.x;
+                const real s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
+                const real t = sei[a] * l.y * s6;  // 4 eps s6
+                real fr = t * ((real)12 * s6 - (real)6) * inv_r2;
                 fr = ok ? fr : (real)0;
                 fx[a] -= fr * dx; fy[a] -= fr * dy; fz[a] -= fr * dz;
-                if (ENERGY) en[a] += ok ? e : (real)0;
+                if (ENERGY) en[a] += ok ? t * (s6 - (real)1) : (real)0;
             }
         }
     }
@@ -355,10 +417,11 @@ __device__ __forceinline__ real eval_terms(const TeamCtx<real>& C, const typenam
 // potential energy (team sum, fp64).  Entry: positions staged in s.xq by the unit owners (the
 // leading team_sync orders those writes).  Exit: fout complete and visible to the team.
 template <typename real, bool PERIODIC, bool WT, int APL, bool ENERGY>
-__device__ __noinline__ double compute_forces(const TeamCtx<real>* ctx, int g, real* __restrict__ fout, int tid, int T)
+__device__ __noinline__ double compute_forces(uint32_t ctx_off, int g, int out_slot, int tid, int T)
 {
-    const TeamCtx<real>& C = *ctx;
-    const Smem<real> s = C.s;
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
+    real* __restrict__ fout = s.f + (size_t)out_slot * 3 * C.N;
     const bool do_nb = g < 0 || g == C.g_nb;
     const bool do_restr = (g < 0 || g == C.g_restr) && C.restraint_k != (real)0;
     int set = -1;
@@ -375,7 +438,10 @@ __device__ __noinline__ double compute_forces(const TeamCtx<real>* ctx, int g, r
         fx[a] = fy[a] = fz[a] = en[a] = (real)0;
     }
     team_sync<WT>();
-    if (do_nb) pair_forces<real, PERIODIC, APL, ENERGY>(C, s.xq, atom, fx, fy, fz, en);
+    if (do_nb) {
+        if (C.n_lj == C.N) pair_forces<real, PERIODIC, APL, ENERGY, true>(C, s.xq, atom, fx, fy, fz, en);
+        else pair_forces<real, PERIODIC, APL, ENERGY, false>(C, s.xq, atom, fx, fy, fz, en);
+    }
     double e_thread = 0.0;
     if (set >= 0) {
         const real et = eval_terms<real, PERIODIC, ENERGY>(C, s.xq, s.tf, C.set_lo[set], C.set_hi[set], tid, T);
@@ -410,20 +476,48 @@ __device__ __noinline__ double compute_forces(const TeamCtx<real>* ctx, int g, r
 }
 
 // ------------------------------------------------------------------------------------------ constraints (fp64)
+// fp64 reciprocal square root / square root / reciprocal without the special-case slow paths of the
+// CUDA math library: hardware seed (2^-22.9 relative) + two Newton steps; ~1 ulp for normal inputs
+static __device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double e = fma(-x * y, y, 1.0);
+        y = fma(0.5 * y, e, y);
+    }
+    return y;
+}
+static __device__ __forceinline__ double fast_sqrt(double x)
+{
+    const double y = fast_rsqrt(x);
+    const double r = x * y;
+    return fma(fma(-r, r, x), 0.5 * y, r);
+}
+static __device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) y = fma(fma(-x, y, 1.0), y, y);
+    return y;
+}
+
 static __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
 // analytic SETTLE (Miyamoto & Kollman 1992): x0 = reference triangle (O, H1, H2), x1 = unconstrained
-// new positions, overwritten with the constrained ones
-static __device__ __forceinline__ void settle_positions(const double (&x0)[3][3], double (&x1)[3][3], double mO, double mH, double dOH,
-                                              double dHH)
+// new positions, overwritten with the constrained ones.  K = constants of the rigid geometry
+// (PKParams::settle_c): {mO / M, mH / M, ra, rb, rc, 1 / ra, 1 / (2 rc)}
+static __device__ __forceinline__ void settle_positions(const double (&x0)[3][3], double (&x1)[3][3], const double* __restrict__ K)
 {
-    const double inv_mtot = 1.0 / (mO + 2.0 * mH);
+    const double wO = K[0], wH = K[1], ra = K[2], rb = K[3], rc = K[4], inv_ra = K[5], inv_2rc = K[6];
     double xb0[3], xc0[3], xcom[3], xa1[3], xb1[3], xc1[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         xb0[c] = x0[1][c] - x0[0][c];
         xc0[c] = x0[2][c] - x0[0][c];
-        xcom[c] = (mO * x1[0][c] + mH * x1[1][c] + mH * x1[2][c]) * inv_mtot;
+        xcom[c] = wO * x1[0][c] + wH * x1[1][c] + wH * x1[2][c];
         xa1[c] = x1[0][c] - xcom[c];
         xb1[c] = x1[1][c] - xcom[c];
         xc1[c] = x1[2][c] - xcom[c];
@@ -431,18 +525,17 @@ static __device__ __forceinline__ void settle_positions(const double (&x0)[3][3]
     double Z[3] = {xb0[1] * xc0[2] - xb0[2] * xc0[1], xb0[2] * xc0[0] - xb0[0] * xc0[2], xb0[0] * xc0[1] - xb0[1] * xc0[0]};
     double X[3] = {xa1[1] * Z[2] - xa1[2] * Z[1], xa1[2] * Z[0] - xa1[0] * Z[2], xa1[0] * Z[1] - xa1[1] * Z[0]};
     double Y[3] = {Z[1] * X[2] - Z[2] * X[1], Z[2] * X[0] - Z[0] * X[2], Z[0] * X[1] - Z[1] * X[0]};
-    const double nz = rsqrt(dot3(Z, Z)), nx = rsqrt(dot3(X, X)), ny = rsqrt(dot3(Y, Y));
+    const double nz = fast_rsqrt(dot3(Z, Z)), nx = fast_rsqrt(dot3(X, X)), ny = fast_rsqrt(dot3(Y, Y));
 #pragma unroll
     for (int c = 0; c < 3; ++c) { X[c] *= nx; Y[c] *= ny; Z[c] *= nz; }
     const double xb0d = dot3(X, xb0), yb0d = dot3(Y, xb0), xc0d = dot3(X, xc0), yc0d = dot3(Y, xc0);
     const double za1d = dot3(Z, xa1);
     const double xb1d = dot3(X, xb1), yb1d = dot3(Y, xb1), zb1d = dot3(Z, xb1);
     const double xc1d = dot3(X, xc1), yc1d = dot3(Y, xc1), zc1d = dot3(Z, xc1);
-    const double rc = 0.5 * dHH;
-    const double hgt = sqrt(dOH * dOH - rc * rc);
-    const double ra = hgt * 2.0 * mH * inv_mtot, rb = hgt - ra;
-    const double sinphi = za1d / ra, cosphi = sqrt(1.0 - sinphi * sinphi);
-    const double sinpsi = (zb1d - zc1d) / (2.0 * rc * cosphi), cospsi = sqrt(1.0 - sinpsi * sinpsi);
+    const double sinphi = za1d * inv_ra;
+    const double c2 = fma(-sinphi, sinphi, 1.0);
+    const double icos = fast_rsqrt(c2), cosphi = c2 * icos;
+    const double sinpsi = (zb1d - zc1d) * inv_2rc * icos, cospsi = fast_sqrt(fma(-sinpsi, sinpsi, 1.0));
     const double ya2d = ra * cosphi;
     const double xb2d = -rc * cospsi;
     const double yb2d = -rb * cosphi - rc * sinpsi * sinphi;
@@ -451,8 +544,8 @@ static __device__ __forceinline__ void settle_positions(const double (&x0)[3][3]
     const double beta = xb2d * (yc0d - yb0d) + xb0d * yb2d + xc0d * yc2d;
     const double gamma = xb0d * yb1d - xb1d * yb0d + xc0d * yc1d - xc1d * yc0d;
     const double al2be2 = alpha * alpha + beta * beta;
-    const double sintheta = (alpha * gamma - beta * sqrt(al2be2 - gamma * gamma)) / al2be2;
-    const double costheta = sqrt(1.0 - sintheta * sintheta);
+    const double sintheta = (alpha * gamma - beta * fast_sqrt(al2be2 - gamma * gamma)) * fast_rcp(al2be2);
+    const double costheta = fast_sqrt(fma(-sintheta, sintheta, 1.0));
     const double xa3d = -ya2d * sintheta, ya3d = ya2d * costheta, za3d = za1d;
     const double xb3d = xb2d * costheta - yb2d * sintheta, yb3d = xb2d * sintheta + yb2d * costheta, zb3d = zb1d;
     const double xc3d = -xb2d * costheta - yc2d * sintheta, yc3d = -xb2d * sintheta + yc2d * costheta, zc3d = zc1d;
@@ -469,46 +562,41 @@ static __device__ __forceinline__ void solve3(double A00, double A01, double A02
                                        double& l2)
 {
     const double c00 = A11 * A22 - A12 * A21, c01 = A10 * A22 - A12 * A20, c02 = A10 * A21 - A11 * A20;
-    const double inv_det = 1.0 / (A00 * c00 - A01 * c01 + A02 * c02);
+    const double inv_det = fast_rcp(A00 * c00 - A01 * c01 + A02 * c02);
     l0 = (r0 * c00 - A01 * (r1 * A22 - A12 * r2) + A02 * (r1 * A21 - A11 * r2)) * inv_det;
     l1 = (A00 * (r1 * A22 - A12 * r2) - r0 * c01 + A02 * (A10 * r2 - r1 * A20)) * inv_det;
     l2 = (A00 * (A11 * r2 - r1 * A21) - A01 * (A10 * r2 - r1 * A20) + r0 * c02) * inv_det;
 }
 
-// exact removal of the velocity components along the three edges of a rigid water
-static __device__ __forceinline__ void settle_velocities(const double (&x)[3][3], double (&v)[3][3], double mO, double mH)
+// exact removal of the velocity components along the three edges of a rigid water.  Edges k -> (k+1)%3
+// with e_k = x_h - x_t; impulses lambda = M b, b_k = e_k . (v_h - v_t).  For a rigid triangle the
+// edge dot products are constants, so M = -C^-1 is precomputed on the host (PKParams::settle_m):
+//   C_kk = d_k^2 (1/m_h + 1/m_t),  C_01 = -(e0.e1)/m_1,  C_12 = -(e1.e2)/m_2,  C_02 = -(e0.e2)/m_0
+static __device__ __forceinline__ void settle_velocities(const double (&x)[3][3], double (&v)[3][3], const double* __restrict__ M,
+                                                         double imO, double imH)
 {
-    const double im[3] = {1.0 / mO, 1.0 / mH, 1.0 / mH};
-    double u[3][3], b[3];  // edges: k -> (k+1)%3
+    const double im[3] = {imO, imH, imH};
+    double e[3][3], b[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int h = (k + 1) % 3;
-        double n2 = 0.0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            u[k][c] = x[h][c] - x[k][c];
-            n2 += u[k][c] * u[k][c];
-        }
-        const double inv = rsqrt(n2);
         b[k] = 0.0;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            u[k][c] *= inv;
-            b[k] += (v[h][c] - v[k][c]) * u[k][c];
+            e[k][c] = x[h][c] - x[k][c];
+            b[k] += (v[h][c] - v[k][c]) * e[k][c];
         }
     }
-    const double u01 = dot3(u[0], u[1]), u02 = dot3(u[0], u[2]), u12 = dot3(u[1], u[2]);
-    const double A00 = im[0] + im[1], A11 = im[1] + im[2], A22 = im[2] + im[0];
-    const double A01 = -im[1] * u01, A12 = -im[2] * u12, A02 = -im[0] * u02;
     double lam[3];
-    solve3(A00, A01, A02, A01, A11, A12, A02, A12, A22, -b[0], -b[1], -b[2], lam[0], lam[1], lam[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) lam[k] = M[3 * k] * b[0] + M[3 * k + 1] * b[1] + M[3 * k + 2] * b[2];
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
         const int h = (l + 1) % 3;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            v[h][c] += lam[l] * u[l][c] * im[h];
-            v[l][c] -= lam[l] * u[l][c] * im[l];
+            v[h][c] += lam[l] * e[l][c] * im[h];
+            v[l][c] -= lam[l] * e[l][c] * im[l];
         }
     }
 }
@@ -782,13 +870,12 @@ struct UnitOps {
 // velocities (langevin.py:124-139).  h = 0: Context.applyConstraints / applyVelocityConstraints at the
 // start of a leg (bookkeepers.py:206-208).  Stages the new positions.  Returns KE after (h = 0) or its change.
 template <typename real>
-__device__ __noinline__ double water_R(const TeamCtx<real>* ctx, int u, double h)
+__device__ __noinline__ double water_R(uint32_t ctx_off, int u, double h)
 {
-    const TeamCtx<real>& C = *ctx;
-    const Smem<real> s = C.s;
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
     const UnitOps<real> ops{C, s};
     const PKUnit U = C.units[u];
-    const double mO = s.mass[U.a[0]], mH = s.mass[U.a[1]];
     double x[3][3];
     double ke0 = 0.0;
     {
@@ -800,11 +887,12 @@ __device__ __noinline__ double water_R(const TeamCtx<real>* ctx, int u, double h
         for (int k = 0; k < 3; ++k)
 #pragma unroll
             for (int c = 0; c < 3; ++c) x[k][c] = x0[k][c] + h * v[k][c];
-        settle_positions(x0, x, mO, mH, C.oh, C.hh);
+        settle_positions(x0, x, C.settle_c);
     }
     double v[3][3];
     ops.load(s.v, U, v);
     if (h != 0.0) {
+        const double inv_h = fast_rcp(h);
         double x0[3][3];
         ops.load(s.x, U, x0);
 #pragma unroll
@@ -812,25 +900,26 @@ __device__ __noinline__ double water_R(const TeamCtx<real>* ctx, int u, double h
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const double x1 = x0[k][c] + h * v[k][c];  // the unconstrained update
-                v[k][c] = v[k][c] + (x[k][c] - x1) / h;
+                v[k][c] = v[k][c] + (x[k][c] - x1) * inv_h;
             }
     }
     ops.store(s.x, U, x);
     ops.stage(U, x);
-    settle_velocities(x, v, mO, mH);
+    settle_velocities(x, v, C.settle_m, s.invm[U.a[0]], s.invm[U.a[1]]);
     ops.store(s.v, U, v);
     return ops.kinetic(U, v) - ke0;
 }
 
 // velocity part of V and O for a rigid water: kick (f != nullptr) or noise, then project; returns change of KE
 template <typename real>
-__device__ __noinline__ double water_VO(const TeamCtx<real>* ctx, int u, double h, const real* __restrict__ f, double a, double b,
+__device__ __noinline__ double water_VO(uint32_t ctx_off, int u, double h, int f_slot, double a, double b,
                                         uint64_t rid, uint32_t draw, int want_dke)
 {
-    const TeamCtx<real>& C = *ctx;
-    const Smem<real> s = C.s;
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
     const UnitOps<real> ops{C, s};
     const PKUnit U = C.units[u];
+    const real* __restrict__ f = f_slot >= 0 ? s.f + (size_t)f_slot * 3 * C.N : nullptr;
     double v[3][3];
     double ke0 = 0.0;
     if (f) {
@@ -851,17 +940,17 @@ __device__ __noinline__ double water_VO(const TeamCtx<real>* ctx, int u, double 
     }
     double x[3][3];
     ops.load(s.x, U, x);
-    settle_velocities(x, v, s.mass[U.a[0]], s.mass[U.a[1]]);
+    settle_velocities(x, v, C.settle_m, s.invm[U.a[0]], s.invm[U.a[1]]);
     ops.store(s.v, U, v);
     return want_dke ? ops.kinetic(U, v) - ke0 : 0.0;
 }
 
 // ---- star of pair constraints (H-bonds): same contracts as the water functions
 template <typename real>
-__device__ __noinline__ double star_R(const TeamCtx<real>* ctx, int u, double h)
+__device__ __noinline__ double star_R(uint32_t ctx_off, int u, double h)
 {
-    const TeamCtx<real>& C = *ctx;
-    const Smem<real> s = C.s;
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
     const UnitOps<real> ops{C, s};
     const PKUnit U = C.units[u];
     double im[4];
@@ -883,6 +972,7 @@ __device__ __noinline__ double star_R(const TeamCtx<real>* ctx, int u, double h)
     double v[4][3];
     ops.load(s.v, U, v);
     if (h != 0.0) {
+        const double inv_h = fast_rcp(h);
         double x0[4][3];
         ops.load(s.x, U, x0);
 #pragma unroll
@@ -890,7 +980,7 @@ __device__ __noinline__ double star_R(const TeamCtx<real>* ctx, int u, double h)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const double x1 = x0[k][c] + h * v[k][c];
-                v[k][c] = v[k][c] + (x[k][c] - x1) / h;
+                v[k][c] = v[k][c] + (x[k][c] - x1) * inv_h;
             }
     }
     ops.store(s.x, U, x);
@@ -901,15 +991,16 @@ __device__ __noinline__ double star_R(const TeamCtx<real>* ctx, int u, double h)
 }
 
 template <typename real>
-__device__ __noinline__ double star_VO(const TeamCtx<real>* ctx, int u, double h, const real* __restrict__ f, double a, double b,
+__device__ __noinline__ double star_VO(uint32_t ctx_off, int u, double h, int f_slot, double a, double b,
                                        uint64_t rid, uint32_t draw, int want_dke)
 {
-    const TeamCtx<real>& C = *ctx;
-    const Smem<real> s = C.s;
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
     const UnitOps<real> ops{C, s};
     const PKUnit U = C.units[u];
     double im[4];
     ops.inv_masses(U, im);
+    const real* __restrict__ f = f_slot >= 0 ? s.f + (size_t)f_slot * 3 * C.N : nullptr;
     double v[4][3];
     double ke0 = 0.0;
     ops.load(s.v, U, v);
@@ -937,10 +1028,10 @@ __device__ __noinline__ double star_VO(const TeamCtx<real>* ctx, int u, double h
 
 // ---- generic clusters (Gauss-Seidel SHAKE / RATTLE in shared memory by the owner lane)
 template <typename real>
-__device__ __noinline__ double generic_R(const TeamCtx<real>* ctx, int u, double h)
+__device__ __noinline__ double generic_R(uint32_t ctx_off, int u, double h)
 {
-    const TeamCtx<real>& C = *ctx;
-    const Smem<real> s = C.s;
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
     const UnitOps<real> ops{C, s};
     const int c = C.units[u].a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
     const double ke0 = h != 0.0 ? ops.generic_kinetic(a0, a1) : 0.0;
@@ -966,14 +1057,15 @@ __device__ __noinline__ double generic_R(const TeamCtx<real>* ctx, int u, double
 }
 
 template <typename real>
-__device__ __noinline__ double generic_VO(const TeamCtx<real>* ctx, int u, double h, const real* __restrict__ f, double a, double b,
+__device__ __noinline__ double generic_VO(uint32_t ctx_off, int u, double h, int f_slot, double a, double b,
                                           uint64_t rid, uint32_t draw, int want_dke)
 {
     constexpr bool NOISE32 = sizeof(real) == 4;
-    const TeamCtx<real>& C = *ctx;
-    const Smem<real> s = C.s;
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
     const UnitOps<real> ops{C, s};
     const int c = C.units[u].a[0], a0 = C.gc_atom_off[c], a1 = C.gc_atom_off[c + 1];
+    const real* __restrict__ f = f_slot >= 0 ? s.f + (size_t)f_slot * 3 * C.N : nullptr;
     const double ke0 = want_dke ? ops.generic_kinetic(a0, a1) : 0.0;
     for (int q = a0; q < a1; ++q) {
         const int i = C.gc_atoms[q];
@@ -995,11 +1087,11 @@ __device__ __noinline__ double generic_VO(const TeamCtx<real>* ctx, int u, doubl
 
 // ---- free atom
 template <typename real>
-__device__ __noinline__ double free_O(const TeamCtx<real>* ctx, int i, double a, double b, uint64_t rid, uint32_t draw)
+__device__ __noinline__ double free_O(uint32_t ctx_off, int i, double a, double b, uint64_t rid, uint32_t draw)
 {
     constexpr bool NOISE32 = sizeof(real) == 4;
-    const TeamCtx<real>& C = *ctx;
-    const Smem<real> s = C.s;
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
     const N3 n = NOISE32 ? normals3_f32(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i) : normals3_f64(C.seed, rid, draw, LSI_TAG_O, (uint32_t)i);
     const double sg = b * s.sigv[i];
     const double v0 = s.v[3 * i], v1 = s.v[3 * i + 1], v2 = s.v[3 * i + 2];
@@ -1010,15 +1102,16 @@ __device__ __noinline__ double free_O(const TeamCtx<real>* ctx, int i, double a,
 
 // ---- dispatch by unit kind (units are sorted by kind, so warps rarely diverge here)
 template <typename real>
-__device__ __forceinline__ double unit_R(const TeamCtx<real>* ctx, int u, double h)
+__device__ __forceinline__ double unit_R(uint32_t ctx_off, int u, double h)
 {
-    const int kind = ctx->units[u].kind;
-    if (kind == UNIT_WATER) return water_R<real>(ctx, u, h);
-    if (kind == UNIT_STAR) return star_R<real>(ctx, u, h);
-    if (kind == UNIT_GENERIC) return generic_R<real>(ctx, u, h);
-    const Smem<real>& s = ctx->s;
-    const UnitOps<real> ops{*ctx, s};
-    const int i = ctx->units[u].a[0];
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const int kind = C.units[u].kind;
+    if (kind == UNIT_WATER) return water_R<real>(ctx_off, u, h);
+    if (kind == UNIT_STAR) return star_R<real>(ctx_off, u, h);
+    if (kind == UNIT_GENERIC) return generic_R<real>(ctx_off, u, h);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
+    const UnitOps<real> ops{C, s};
+    const int i = C.units[u].a[0];
     const double px = s.x[3 * i] + h * s.v[3 * i], py = s.x[3 * i + 1] + h * s.v[3 * i + 1], pz = s.x[3 * i + 2] + h * s.v[3 * i + 2];
     s.x[3 * i] = px; s.x[3 * i + 1] = py; s.x[3 * i + 2] = pz;
     ops.stage_atom(i, px, py, pz);
@@ -1027,14 +1120,16 @@ __device__ __forceinline__ double unit_R(const TeamCtx<real>* ctx, int u, double
 }
 
 template <typename real>
-__device__ __forceinline__ double unit_V(const TeamCtx<real>* ctx, int u, double h, const real* __restrict__ f, int want_dke)
+__device__ __forceinline__ double unit_V(uint32_t ctx_off, int u, double h, int f_slot, int want_dke)
 {
-    const int kind = ctx->units[u].kind;
-    if (kind == UNIT_WATER) return water_VO<real>(ctx, u, h, f, 0.0, 0.0, 0ull, 0u, want_dke);
-    if (kind == UNIT_STAR) return star_VO<real>(ctx, u, h, f, 0.0, 0.0, 0ull, 0u, want_dke);
-    if (kind == UNIT_GENERIC) return generic_VO<real>(ctx, u, h, f, 0.0, 0.0, 0ull, 0u, want_dke);
-    const Smem<real>& s = ctx->s;
-    const int i = ctx->units[u].a[0];
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const int kind = C.units[u].kind;
+    if (kind == UNIT_WATER) return water_VO<real>(ctx_off, u, h, f_slot, 0.0, 0.0, 0ull, 0u, want_dke);
+    if (kind == UNIT_STAR) return star_VO<real>(ctx_off, u, h, f_slot, 0.0, 0.0, 0ull, 0u, want_dke);
+    if (kind == UNIT_GENERIC) return generic_VO<real>(ctx_off, u, h, f_slot, 0.0, 0.0, 0ull, 0u, want_dke);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
+    const real* __restrict__ f = s.f + (size_t)f_slot * 3 * C.N;
+    const int i = C.units[u].a[0];
     const double hm = h * s.invm[i];
     const double v0 = s.v[3 * i], v1 = s.v[3 * i + 1], v2 = s.v[3 * i + 2];
     const double w0 = v0 + hm * (double)f[3 * i], w1 = v1 + hm * (double)f[3 * i + 1], w2 = v2 + hm * (double)f[3 * i + 2];
@@ -1043,22 +1138,24 @@ __device__ __forceinline__ double unit_V(const TeamCtx<real>* ctx, int u, double
 }
 
 template <typename real>
-__device__ __forceinline__ double unit_O(const TeamCtx<real>* ctx, int u, double a, double b, uint64_t rid, uint32_t draw)
+__device__ __forceinline__ double unit_O(uint32_t ctx_off, int u, double a, double b, uint64_t rid, uint32_t draw)
 {
-    const int kind = ctx->units[u].kind;
-    if (kind == UNIT_WATER) return water_VO<real>(ctx, u, 0.0, nullptr, a, b, rid, draw, 1);
-    if (kind == UNIT_STAR) return star_VO<real>(ctx, u, 0.0, nullptr, a, b, rid, draw, 1);
-    if (kind == UNIT_GENERIC) return generic_VO<real>(ctx, u, 0.0, nullptr, a, b, rid, draw, 1);
-    return free_O<real>(ctx, ctx->units[u].a[0], a, b, rid, draw);
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const int kind = C.units[u].kind;
+    if (kind == UNIT_WATER) return water_VO<real>(ctx_off, u, 0.0, -1, a, b, rid, draw, 1);
+    if (kind == UNIT_STAR) return star_VO<real>(ctx_off, u, 0.0, -1, a, b, rid, draw, 1);
+    if (kind == UNIT_GENERIC) return generic_VO<real>(ctx_off, u, 0.0, -1, a, b, rid, draw, 1);
+    return free_O<real>(ctx_off, C.units[u].a[0], a, b, rid, draw);
 }
 
 template <typename real>
-__device__ __forceinline__ double unit_kinetic(const TeamCtx<real>* ctx, int u)
+__device__ __forceinline__ double unit_kinetic(uint32_t ctx_off, int u)
 {
-    const Smem<real>& s = ctx->s;
-    const PKUnit U = ctx->units[u];
-    const UnitOps<real> ops{*ctx, s};
-    if (U.kind == UNIT_GENERIC) return ops.generic_kinetic(ctx->gc_atom_off[U.a[0]], ctx->gc_atom_off[U.a[0] + 1]);
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
+    const PKUnit U = C.units[u];
+    const UnitOps<real> ops{C, s};
+    if (U.kind == UNIT_GENERIC) return ops.generic_kinetic(C.gc_atom_off[U.a[0]], C.gc_atom_off[U.a[0] + 1]);
     double ke = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -1089,12 +1186,13 @@ __device__ __forceinline__ void load_tables(const PKParams& P, const Smem<real>&
 
 // Maxwell-Boltzmann velocities for every atom (start of the protocol, midpoint of the "configuration" marginal)
 template <typename real>
-__device__ __noinline__ void draw_velocities(const TeamCtx<real>* ctx, uint64_t rid, uint32_t draw, uint32_t tag, const double* mass,
+__device__ __noinline__ void draw_velocities(uint32_t ctx_off, uint64_t rid, uint32_t draw, uint32_t tag, const double* mass,
                                              double kT, int tid, int T)
 {
-    const Smem<real>& s = ctx->s;
-    for (int i = tid; i < ctx->N; i += T) {
-        const N3 n = normals3_f64(ctx->seed, rid, draw, tag, (uint32_t)i);
+    const TeamCtx<real>& C = *sm<TeamCtx<real>>(ctx_off);
+    const Smem<real> s = carve<real>(pk_smem + C.team_off, C.L);
+    for (int i = tid; i < C.N; i += T) {
+        const N3 n = normals3_f64(C.seed, rid, draw, tag, (uint32_t)i);
         const double sg = sqrt(kT / mass[i]);
         s.v[3 * i] = sg * n.x; s.v[3 * i + 1] = sg * n.y; s.v[3 * i + 2] = sg * n.z;
     }
@@ -1105,7 +1203,6 @@ __device__ __noinline__ void draw_velocities(const TeamCtx<real>* ctx, uint64_t 
 template <typename real, bool PERIODIC, bool WT, int APL>
 __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol_kernel(const __grid_constant__ PKParams P, int teams)
 {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
     const int N = P.N, D = 3 * N;
     const int T = WT ? 32 : (int)blockDim.x;
     const int tid = WT ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
@@ -1114,10 +1211,10 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
     if (r >= P.n) return;  // whole team (warp-team mode never uses CTA barriers)
     const bool DIAG = P.diag != 0;
     const Layout L = layout<real>(N, P.n_slots, P.n_tf, P.n_generic > 0, WT);
-    unsigned char* team_base = smem_raw + (size_t)team * L.total;
-    const Smem<real> s = carve<real>(team_base, L);
-    TeamCtx<real>* ctx = reinterpret_cast<TeamCtx<real>*>(team_base + L.ctx);
-    if (tid == 0) fill_ctx<real>(ctx, P, s);
+    const uint32_t team_off = (uint32_t)team * L.total;
+    const Smem<real> s = carve<real>(pk_smem + team_off, L);
+    const uint32_t ctx = team_off + L.ctx;  // offset of this team's TeamCtx in shared memory
+    if (tid == 0) fill_ctx<real>(sm<TeamCtx<real>>(ctx), P, L, team_off);
     const uint64_t rid = P.replica0 + (uint64_t)r;
     const int64_t TT = (int64_t)P.n_steps + 1;
 
@@ -1135,7 +1232,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
         team_sync<WT>();
     }
 
-    real* const scratch = s.f + (size_t)(P.n_slots - 1) * D;  // DIAG: an extra slot that is never a cache
+    const int scratch = P.n_slots - 1;  // DIAG: an extra slot that is never a cache
     double heat_run = 0.0;  // per-lane share of the heat accumulated so far (all legs)
     for (int leg = 0; leg < P.n_legs; ++leg) {
         if (leg > 0) {
@@ -1179,13 +1276,12 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
                     }
                 } else if (kind == LSI_OP_V) {
                     const int slot = P.op_slot[op];
-                    real* fs = s.f + (size_t)slot * D;
                     if (!((valid >> slot) & 1u)) {
-                        compute_forces<real, PERIODIC, WT, APL, false>(ctx, P.slot_group[slot], fs, tid, T);
+                        compute_forces<real, PERIODIC, WT, APL, false>(ctx, P.slot_group[slot], slot, tid, T);
                         valid |= 1u << slot;
                     }
                     double dke = 0.0;
-                    PK_FOR_UNITS(u) dke += unit_V<real>(ctx, u, c0, fs, DIAG ? 1 : 0);
+                    PK_FOR_UNITS(u) dke += unit_V<real>(ctx, u, c0, slot, DIAG ? 1 : 0);
                     if (DIAG) wd_ke += dke;
                 } else {
                     const double a = c0, b = P.op_c1[op];
@@ -1237,7 +1333,6 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
 template <typename real, bool PERIODIC, bool WT, int APL>
 __global__ void __launch_bounds__(WT ? 128 : 384) particles_energy_kernel(const __grid_constant__ PKParams P, int teams)
 {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
     const int N = P.N, D = 3 * N;
     const int T = WT ? 32 : (int)blockDim.x;
     const int tid = WT ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
@@ -1245,18 +1340,18 @@ __global__ void __launch_bounds__(WT ? 128 : 384) particles_energy_kernel(const 
     const int64_t r = WT ? (int64_t)blockIdx.x * teams + team : (int64_t)blockIdx.x;
     if (r >= P.n) return;
     const Layout L = layout<real>(N, 1, P.n_tf, false, WT);
-    unsigned char* team_base = smem_raw + (size_t)team * L.total;
-    const Smem<real> s = carve<real>(team_base, L);
-    TeamCtx<real>* ctx = reinterpret_cast<TeamCtx<real>*>(team_base + L.ctx);
-    if (tid == 0) fill_ctx<real>(ctx, P, s);
+    const uint32_t team_off = (uint32_t)team * L.total;
+    const Smem<real> s = carve<real>(pk_smem + team_off, L);
+    const uint32_t ctx = team_off + L.ctx;  // offset of this team's TeamCtx in shared memory
+    if (tid == 0) fill_ctx<real>(sm<TeamCtx<real>>(ctx), P, L, team_off);
     load_tables<real>(P, s, tid, T);
     for (int k = tid; k < D; k += T) s.x[k] = P.q_x[r * D + k];
     team_sync<WT>();
     {
-        const UnitOps<real> ops{*ctx, s};
+        const UnitOps<real> ops{*sm<TeamCtx<real>>(ctx), s};
         for (int i = tid; i < N; i += T) ops.stage_atom(i, s.x[3 * i], s.x[3 * i + 1], s.x[3 * i + 2]);
     }
-    const double e = compute_forces<real, PERIODIC, WT, APL, true>(ctx, P.q_group, s.f, tid, T);
+    const double e = compute_forces<real, PERIODIC, WT, APL, true>(ctx, P.q_group, 0, tid, T);
     if (P.q_energy && tid == 0) P.q_energy[r] = e;
     if (P.q_forces) for (int k = tid; k < D; k += T) P.q_forces[r * D + k] = (double)s.f[k];
 }
@@ -1272,7 +1367,7 @@ int set_smem(K kernel, size_t bytes)
 template <typename real, bool PERIODIC, bool WT, int APL>
 int launch_protocol3(const PKParams& P, const PKLaunch& L, cudaStream_t st)
 {
-    static_assert(sizeof(TeamCtx<real>) <= 512, "Layout reserves 512 bytes for TeamCtx");
+    static_assert(sizeof(TeamCtx<real>) <= 768, "Layout reserves 768 bytes for TeamCtx");
     const unsigned grid = (unsigned)(WT ? (L.n + L.teams - 1) / L.teams : L.n);
     auto k = particles_protocol_kernel<real, PERIODIC, WT, APL>;
     int rc;

@@ -37,9 +37,13 @@ struct PKParams {
     double cutoff2, krf, crf, restraint_k;
     int g_nb, g_restr;
     double oh, hh, tol;
+    double settle_c[8];       // SETTLE positions: mO/M, mH/M, ra, rb, rc, 1/ra, 1/(2 rc)
+    double settle_m[9];       // SETTLE velocities: impulses = M b (row-major)
     const double* mass;       // [N]
     const void* nbp;          // real4 [N]: q sqrt(K), sigma/2, 2 sqrt(eps), 0
     const uint32_t* excl;     // [N][excl_words] (self, exclusions, exceptions)
+    const uint32_t* excl_lj;  // [N][lj_words]: the same bits over the LJ-active atoms perm[0 .. n_lj)
+    int n_lj, lj_words;
     const int32_t* perm;      // [n_perm] force-loop slot -> atom (LJ-active atoms first), -1 = empty
     int n_perm;
     const PKUnit* units;      // [n_units], constrained units first
