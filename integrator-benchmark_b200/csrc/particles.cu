@@ -27,8 +27,7 @@ struct DevTables {
     void* nbp_f = nullptr;
     void* nbp_d = nullptr;
     uint32_t* excl = nullptr;
-    uint32_t* excl_lj = nullptr;
-    int32_t* perm = nullptr;
+    int32_t *perm = nullptr, *iperm = nullptr;
     PKUnit* units = nullptr;
     int32_t *gc_off = nullptr, *gc_pairs = nullptr, *gc_atom_off = nullptr, *gc_atoms = nullptr;
     double* gc_dist = nullptr;
@@ -49,9 +48,9 @@ struct lsi_particles {
     double oh = 0, hh = 0, tol = 1e-8;
     double settle_c[8] = {0}, settle_m[9] = {0};
     int excl_words = 1;
-    std::vector<uint32_t> excl, excl_lj;
-    int n_lj = 0, lj_words = 1;
-    std::vector<int32_t> perm;
+    std::vector<uint32_t> excl, excl_slots;
+    int n_lj = 0;
+    std::vector<int32_t> perm, iperm;
     std::vector<HostTerm> terms;  // sorted by force group
     int n_tf = 0;
     int n_sets = 1;
@@ -78,13 +77,14 @@ cudaError_t upload(T** dst, const std::vector<T>& src)
 }
 
 template <typename real>
-std::vector<PKTerm<real>> pack_terms(const std::vector<HostTerm>& terms)
+std::vector<PKTerm<real>> pack_terms(const std::vector<HostTerm>& terms, const std::vector<int32_t>& iperm)
 {
     std::vector<PKTerm<real>> out(terms.size());
     for (size_t k = 0; k < terms.size(); ++k) {
         const HostTerm& t = terms[k];
         PKTerm<real>& o = out[k];
-        o.kind = t.kind; o.a0 = t.a[0]; o.a1 = t.a[1]; o.a2 = t.a[2]; o.a3 = t.a[3]; o.slot = t.slot;
+        o.kind = t.kind; o.slot = t.slot;
+        o.a0 = iperm[t.a[0]]; o.a1 = iperm[t.a[1]]; o.a2 = iperm[t.a[2]]; o.a3 = iperm[t.a[3]];  // position slots
         for (int q = 0; q < 4; ++q) o.p[q] = (real)t.p[q];
     }
     return out;
@@ -112,8 +112,8 @@ int get_tables(lsi_particles* p, DevTables** out)
     LSI_CUDA_CHECK(upload(&df, nf));
     LSI_CUDA_CHECK(upload(&dd, nd));
     t.nbp_f = df; t.nbp_d = dd;
-    LSI_CUDA_CHECK(upload(&t.excl, p->excl));
-    LSI_CUDA_CHECK(upload(&t.excl_lj, p->excl_lj));
+    LSI_CUDA_CHECK(upload(&t.excl, p->excl_slots));
+    LSI_CUDA_CHECK(upload(&t.iperm, p->iperm));
     LSI_CUDA_CHECK(upload(&t.perm, p->perm));
     LSI_CUDA_CHECK(upload(&t.units, p->units));
     LSI_CUDA_CHECK(upload(&t.gc_off, p->gc_off));
@@ -122,8 +122,8 @@ int get_tables(lsi_particles* p, DevTables** out)
     LSI_CUDA_CHECK(upload(&t.gc_atoms, p->gc_atoms));
     LSI_CUDA_CHECK(upload(&t.gc_dist, p->gc_dist));
     {
-        std::vector<PKTerm<float>> tf = pack_terms<float>(p->terms);
-        std::vector<PKTerm<double>> td = pack_terms<double>(p->terms);
+        std::vector<PKTerm<float>> tf = pack_terms<float>(p->terms, p->iperm);
+        std::vector<PKTerm<double>> td = pack_terms<double>(p->terms, p->iperm);
         PKTerm<float>* pf = nullptr;
         PKTerm<double>* pd = nullptr;
         LSI_CUDA_CHECK(upload(&pf, tf));
@@ -161,7 +161,7 @@ void fill_system_params(const lsi_particles* p, const DevTables* t, bool mixed, 
     P.mass = t->mass;
     P.nbp = mixed ? t->nbp_f : t->nbp_d;
     P.excl = t->excl;
-    P.excl_lj = t->excl_lj; P.n_lj = p->n_lj; P.lj_words = p->lj_words;
+    P.n_lj = p->n_lj; P.iperm = t->iperm;
     P.perm = t->perm; P.n_perm = p->n_atoms;
     P.units = t->units;
     P.gc_off = t->gc_off; P.gc_pairs = t->gc_pairs; P.gc_dist = t->gc_dist;
@@ -215,7 +215,7 @@ void lsi_particles_free(lsi_particles* p)
     if (!p) return;
     for (auto& kv : p->dev) {
         DevTables& t = kv.second;
-        cudaFree(t.mass); cudaFree(t.nbp_f); cudaFree(t.nbp_d); cudaFree(t.excl); cudaFree(t.excl_lj); cudaFree(t.perm); cudaFree(t.units);
+        cudaFree(t.mass); cudaFree(t.nbp_f); cudaFree(t.nbp_d); cudaFree(t.excl); cudaFree(t.perm); cudaFree(t.iperm); cudaFree(t.units);
         cudaFree(t.gc_off); cudaFree(t.gc_pairs); cudaFree(t.gc_atom_off); cudaFree(t.gc_atoms); cudaFree(t.gc_dist);
         cudaFree(t.terms_f); cudaFree(t.terms_d); cudaFree(t.gather_off); cudaFree(t.gather_idx);
     }
@@ -339,16 +339,17 @@ LSI_EXPORT int lsi_system_create_particles(const lsi_particles_desc* d, lsi_syst
     if (p->terms.empty()) p->terms.push_back(HostTerm{});  // keeps the device pointers valid
     if (p->terms.size() == 1 && terms.empty()) p->set_hi[0] = 0;
 
-    // exclusion bits over the LJ-active atoms (the partners of the separate Lennard-Jones loop)
+    // slot space: positions are staged with the LJ-active atoms first; exclusion bits follow
+    p->iperm.assign(N, 0);
+    for (int k = 0; k < N; ++k) p->iperm[p->perm[k]] = k;
     for (int i = 0; i < N; ++i) p->n_lj += p->epsilon[i] != 0.0;
-    p->lj_words = std::max(1, (p->n_lj + 31) / 32);
-    p->excl_lj.assign((size_t)N * p->lj_words, 0u);
+    p->excl_slots.assign((size_t)N * p->excl_words, 0u);
     for (int i = 0; i < N; ++i)
-        for (int k = 0; k < p->n_lj; ++k) {
-            const int j = p->perm[k];
-            if ((p->excl[(size_t)i * p->excl_words + (j >> 5)] >> (j & 31)) & 1u)
-                p->excl_lj[(size_t)i * p->lj_words + (k >> 5)] |= 1u << (k & 31);
-        }
+        for (int j = 0; j < N; ++j)
+            if ((p->excl[(size_t)i * p->excl_words + (j >> 5)] >> (j & 31)) & 1u) {
+                const int ki = p->iperm[i], kj = p->iperm[j];
+                p->excl_slots[(size_t)ki * p->excl_words + (kj >> 5)] |= 1u << (kj & 31);
+            }
 
     // ---- units of the owner-mapped substeps: waters, constraint stars, generic clusters, free atoms
     std::vector<int> owner(N, -1);

@@ -148,10 +148,10 @@ struct TeamCtx {
     uint64_t seed;
     int periodic;
     // forces
-    int N, excl_words, n_terms, n_sets, g_nb, g_restr, n_lj, lj_words;
+    int N, excl_words, n_terms, n_sets, g_nb, g_restr, n_lj;
     int set_group[kMaxSets], set_lo[kMaxSets], set_hi[kMaxSets];
-    const uint32_t *excl, *excl_lj;
-    const int32_t* perm;
+    const uint32_t* excl;
+    const int32_t *perm, *iperm;
     const PKTerm<real>* terms;
     const int32_t *gather_off, *gather_idx;
     real boxr[3], inv_boxr[3], rc2, krf, krf2, crf, restraint_k;
@@ -177,8 +177,8 @@ __device__ __forceinline__ void fill_ctx(TeamCtx<real>* c, const PKParams& P, co
     c->N = P.N; c->excl_words = P.excl_words; c->n_terms = P.n_terms; c->n_sets = P.n_sets;
     c->g_nb = P.g_nb; c->g_restr = P.g_restr;
     for (int k = 0; k < kMaxSets; ++k) { c->set_group[k] = P.set_group[k]; c->set_lo[k] = P.set_lo[k]; c->set_hi[k] = P.set_hi[k]; }
-    c->excl = P.excl; c->excl_lj = P.excl_lj; c->perm = P.perm;
-    c->n_lj = P.n_lj; c->lj_words = P.lj_words;
+    c->excl = P.excl; c->perm = P.perm; c->iperm = P.iperm;
+    c->n_lj = P.n_lj;
     c->terms = reinterpret_cast<const PKTerm<real>*>(P.terms);
     c->gather_off = P.gather_off; c->gather_idx = P.gather_idx;
     c->rc2 = (real)P.cutoff2; c->krf = (real)P.krf; c->krf2 = (real)(2.0 * P.krf); c->crf = (real)P.crf;
@@ -196,125 +196,121 @@ __device__ __forceinline__ void min_image(const TeamCtx<real>& C, real& dx, real
 }
 
 // ------------------------------------------------------------------------------------------ forces
-// Nonbonded full-shell loops for the APL atoms of this lane.
-//   COMBINED (every atom carries Lennard-Jones parameters, e.g. alanine dipeptide): one loop, Coulomb + LJ.
-//   otherwise (TIP3P: only the oxygens): a Coulomb loop over all partners with the lane's own charge
-//   factored out of the loop, then an LJ loop over the LJ-active atoms only (perm[0 .. n_lj)), which
-//   warps without LJ-active atoms skip.
-template <typename real, bool PERIODIC, int APL, bool ENERGY, bool COMBINED>
-__device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typename Vec<real>::r4* __restrict__ xq,
+// Nonbonded full-shell loop for the APL atoms of this lane.  Positions are staged in SLOT order:
+// slot k holds atom perm[k], Lennard-Jones-active atoms first.  Partners k < n_lj get the Coulomb + LJ
+// body (only in warps that own LJ-active atoms -- a warp-uniform choice), the rest (TIP3P hydrogens)
+// the Coulomb-only body, whose sums leave the lane's own charge out of the loop.
+template <typename real, bool PERIODIC, bool ENERGY>
+struct PairBody {
+    real bx, by, bz, ibx, iby, ibz, rc2, krf, krf2, crf;
+    // geometry shared by both bodies
+    __device__ __forceinline__ bool geom(const typename Vec<real>::r4& pj, real xi, real yi, real zi, uint32_t mw, int jj,
+                                         real& dx, real& dy, real& dz, real& r2v, real& inv_r, real& inv_r2) const
+    {
+        dx = pj.x - xi; dy = pj.y - yi; dz = pj.z - zi;
+        if (PERIODIC) {
+            dx = dx - bx * round_fma(dx, ibx);
+            dy = dy - by * round_fma(dy, iby);
+            dz = dz - bz * round_fma(dz, ibz);
+        }
+        r2v = dx * dx + dy * dy + dz * dz;
+        bool ok = ((mw >> jj) & 1u) == 0u;  // not excluded, not an exception, not self
+        if (PERIODIC) ok = ok && (r2v < rc2);
+        inv_r = rsqrt_(r2v);
+        inv_r2 = inv_r * inv_r;
+        return ok;
+    }
+};
+
+template <typename real, bool PERIODIC, int APL, bool ENERGY>
+__device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typename Vec<real>::r4* __restrict__ xq, int slot0, int T,
                                             const int (&atom)[APL], real (&fx)[APL], real (&fy)[APL], real (&fz)[APL],
-                                            real (&en)[APL])
+                                            double (&en)[APL])
 {
     using r4 = typename Vec<real>::r4;
-    const int N = C.N, W = C.excl_words;
+    const int N = C.N, W = C.excl_words, n_lj = C.n_lj;
     real xi[APL], yi[APL], zi[APL], qi[APL], hsi[APL], sei[APL];
+    bool wlj[APL];
 #pragma unroll
     for (int a = 0; a < APL; ++a) {
-        const int i = atom[a] >= 0 ? atom[a] : 0;
-        const r4 p = xq[2 * i], l = xq[2 * i + 1];
+        const int k = atom[a] >= 0 ? slot0 + a * T : 0;
+        const r4 p = xq[2 * k], l = xq[2 * k + 1];
         xi[a] = p.x; yi[a] = p.y; zi[a] = p.z;
         qi[a] = atom[a] >= 0 ? p.w : (real)0;
         hsi[a] = l.x;
         sei[a] = atom[a] >= 0 ? l.y : (real)0;
+        wlj[a] = __any_sync(0xffffffffu, sei[a] != (real)0);  // warp-uniform
     }
-    const real bx = C.boxr[0], by = C.boxr[1], bz = C.boxr[2];
-    const real ibx = C.inv_boxr[0], iby = C.inv_boxr[1], ibz = C.inv_boxr[2];
-    const real rc2 = C.rc2, krf = C.krf, krf2 = C.krf2, crf = C.crf;
-
-    // ---- all partners: Coulomb (+ LJ when COMBINED)
-    real gx[APL], gy[APL], gz[APL], ge[APL];  // Coulomb sums without the lane's own charge
+    PairBody<real, PERIODIC, ENERGY> B;
+    B.bx = C.boxr[0]; B.by = C.boxr[1]; B.bz = C.boxr[2];
+    B.ibx = C.inv_boxr[0]; B.iby = C.inv_boxr[1]; B.ibz = C.inv_boxr[2];
+    B.rc2 = C.rc2; B.krf = C.krf; B.krf2 = C.krf2; B.crf = C.crf;
+    real gx[APL], gy[APL], gz[APL];  // Coulomb sums without the lane's own charge
+    double ge[APL];              // energies: fp32 pair terms summed in fp64 (as OpenMM's mixed mode)
 #pragma unroll
-    for (int a = 0; a < APL; ++a) gx[a] = gy[a] = gz[a] = ge[a] = (real)0;
+    for (int a = 0; a < APL; ++a) { gx[a] = gy[a] = gz[a] = (real)0; ge[a] = 0.0; }
+
     for (int jb = 0; jb < N; jb += 32) {
         uint32_t mw[APL];
 #pragma unroll
-        for (int a = 0; a < APL; ++a) mw[a] = atom[a] >= 0 ? __ldg(C.excl + (size_t)atom[a] * W + (jb >> 5)) : 0xffffffffu;
+        for (int a = 0; a < APL; ++a)
+            mw[a] = atom[a] >= 0 ? __ldg(C.excl + (size_t)(slot0 + a * T) * W + (jb >> 5)) : 0xffffffffu;
         const int jn = min(32, N - jb);
+        const int jl = max(0, min(jn, n_lj - jb));  // partners [0, jl) of this block are LJ-active
         const r4* __restrict__ xj = xq + 2 * jb;
-#pragma unroll 4
-        for (int jj = 0; jj < jn; ++jj) {
-            const r4 pj = xj[2 * jj];
-            real ljx = (real)0, ljy = (real)0;
-            if (COMBINED) {
-                const r4 l = xj[2 * jj + 1];
-                ljx = l.x; ljy = l.y;
-            }
+        int jj = 0;
+#pragma unroll 2
+        for (; jj < jl; ++jj) {
+            const r4 pj = xj[2 * jj], lj = xj[2 * jj + 1];
 #pragma unroll
             for (int a = 0; a < APL; ++a) {
-                real dx = pj.x - xi[a], dy = pj.y - yi[a], dz = pj.z - zi[a];
-                if (PERIODIC) {
-                    dx = dx - bx * round_fma(dx, ibx);
-                    dy = dy - by * round_fma(dy, iby);
-                    dz = dz - bz * round_fma(dz, ibz);
-                }
-                const real r2v = dx * dx + dy * dy + dz * dz;
-                bool ok = ((mw[a] >> jj) & 1u) == 0u;  // not excluded, not an exception, not self
-                if (PERIODIC) ok = ok && (r2v < rc2);
-                const real inv_r = rsqrt_(r2v), inv_r2 = inv_r * inv_r;
-                if (COMBINED) {
+                real dx, dy, dz, r2v, inv_r, inv_r2;
+                const bool ok = B.geom(pj, xi[a], yi[a], zi[a], mw[a], jj, dx, dy, dz, r2v, inv_r, inv_r2);
+                if (wlj[a]) {
                     const real qq = qi[a] * pj.w;
-                    real fr = PERIODIC ? qq * (inv_r * inv_r2 - krf2) : qq * inv_r * inv_r2;
-                    const real sig = hsi[a] + ljx;
+                    real fr = PERIODIC ? qq * (inv_r * inv_r2 - B.krf2) : qq * inv_r * inv_r2;
+                    const real sig = hsi[a] + lj.x;
                     const real s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
-                    const real t = sei[a] * ljy * s6;  // 4 eps s6
+                    const real t = sei[a] * lj.y * s6;  // 4 eps s6
                     fr += t * ((real)12 * s6 - (real)6) * inv_r2;
                     fr = ok ? fr : (real)0;
                     fx[a] -= fr * dx; fy[a] -= fr * dy; fz[a] -= fr * dz;
                     if (ENERGY) {
-                        const real e = (PERIODIC ? qq * (inv_r + krf * r2v - crf) : qq * inv_r) + t * (s6 - (real)1);
-                        en[a] += ok ? e : (real)0;
+                        const real e = (PERIODIC ? qq * (inv_r + B.krf * r2v - B.crf) : qq * inv_r) + t * (s6 - (real)1);
+                        en[a] += ok ? (double)e : 0.0;
                     }
                 } else {
-                    real fr = PERIODIC ? pj.w * (inv_r * inv_r2 - krf2) : pj.w * inv_r * inv_r2;
+                    real fr = PERIODIC ? pj.w * (inv_r * inv_r2 - B.krf2) : pj.w * inv_r * inv_r2;
                     fr = ok ? fr : (real)0;
                     gx[a] -= fr * dx; gy[a] -= fr * dy; gz[a] -= fr * dz;
                     if (ENERGY) {
-                        const real e = PERIODIC ? pj.w * (inv_r + krf * r2v - crf) : pj.w * inv_r;
-                        ge[a] += ok ? e : (real)0;
+                        const real e = PERIODIC ? pj.w * (inv_r + B.krf * r2v - B.crf) : pj.w * inv_r;
+                        ge[a] += ok ? (double)e : 0.0;
                     }
                 }
             }
         }
+#pragma unroll 4
+        for (; jj < jn; ++jj) {
+            const r4 pj = xj[2 * jj];
+#pragma unroll
+            for (int a = 0; a < APL; ++a) {
+                real dx, dy, dz, r2v, inv_r, inv_r2;
+                const bool ok = B.geom(pj, xi[a], yi[a], zi[a], mw[a], jj, dx, dy, dz, r2v, inv_r, inv_r2);
+                real fr = PERIODIC ? pj.w * (inv_r * inv_r2 - B.krf2) : pj.w * inv_r * inv_r2;
+                fr = ok ? fr : (real)0;
+                gx[a] -= fr * dx; gy[a] -= fr * dy; gz[a] -= fr * dz;
+                if (ENERGY) {
+                    const real e = PERIODIC ? pj.w * (inv_r + B.krf * r2v - B.crf) : pj.w * inv_r;
+                    ge[a] += ok ? (double)e : 0.0;
+                }
+            }
+        }
     }
-    if (COMBINED) return;
 #pragma unroll
     for (int a = 0; a < APL; ++a) {
         fx[a] += qi[a] * gx[a]; fy[a] += qi[a] * gy[a]; fz[a] += qi[a] * gz[a];
-        if (ENERGY) en[a] += qi[a] * ge[a];
-    }
-
-    // ---- LJ-active partners only
-    const int n_lj = C.n_lj, Wl = C.lj_words;
-#pragma unroll
-    for (int a = 0; a < APL; ++a) {
-        if (!__any_sync(0xffffffffu, sei[a] != (real)0)) continue;  // warp-uniform
-        for (int kb = 0; kb < n_lj; kb += 32) {
-            const uint32_t mw = atom[a] >= 0 ? __ldg(C.excl_lj + (size_t)atom[a] * Wl + (kb >> 5)) : 0xffffffffu;
-            const int kn = min(32, n_lj - kb);
-#pragma unroll 2
-            for (int kk = 0; kk < kn; ++kk) {
-                const int j = __ldg(C.perm + kb + kk);
-                const r4 pj = xq[2 * j], l = xq[2 * j + 1];
-                real dx = pj.x - xi[a], dy = pj.y - yi[a], dz = pj.z - zi[a];
-                if (PERIODIC) {
-                    dx = dx - bx * round_fma(dx, ibx);
-                    dy = dy - by * round_fma(dy, iby);
-                    dz = dz - bz * round_fma(dz, ibz);
-                }
-                const real r2v = dx * dx + dy * dy + dz * dz;
-                bool ok = ((mw >> kk) & 1u) == 0u;
-                if (PERIODIC) ok = ok && (r2v < rc2);
-                const real inv_r = rsqrt_(r2v), inv_r2 = inv_r * inv_r;
-                const real sig = hsi[a] + l.x;
-                const real s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
-                const real t = sei[a] * l.y * s6;  // 4 eps s6
-                real fr = t * ((real)12 * s6 - (real)6) * inv_r2;
-                fr = ok ? fr : (real)0;
-                fx[a] -= fr * dx; fy[a] -= fr * dy; fz[a] -= fr * dz;
-                if (ENERGY) en[a] += ok ? t * (s6 - (real)1) : (real)0;
-            }
-        }
+        if (ENERGY) en[a] += (double)qi[a] * ge[a];
     }
 }
 
@@ -430,18 +426,17 @@ __device__ __noinline__ double compute_forces(uint32_t ctx_off, int g, int out_s
         for (int q = 1; q < C.n_sets; ++q)
             if (C.set_group[q] == g) set = q;
     int atom[APL];
-    real fx[APL], fy[APL], fz[APL], en[APL];
+    real fx[APL], fy[APL], fz[APL];
+    double en[APL];
 #pragma unroll
     for (int a = 0; a < APL; ++a) {
         const int slot = tid + a * T;
         atom[a] = slot < C.N ? __ldg(C.perm + slot) : -1;
-        fx[a] = fy[a] = fz[a] = en[a] = (real)0;
+        fx[a] = fy[a] = fz[a] = (real)0;
+        en[a] = 0.0;
     }
     team_sync<WT>();
-    if (do_nb) {
-        if (C.n_lj == C.N) pair_forces<real, PERIODIC, APL, ENERGY, true>(C, s.xq, atom, fx, fy, fz, en);
-        else pair_forces<real, PERIODIC, APL, ENERGY, false>(C, s.xq, atom, fx, fy, fz, en);
-    }
+    if (do_nb) pair_forces<real, PERIODIC, APL, ENERGY>(C, s.xq, tid, T, atom, fx, fy, fz, en);
     double e_thread = 0.0;
     if (set >= 0) {
         const real et = eval_terms<real, PERIODIC, ENERGY>(C, s.xq, s.tf, C.set_lo[set], C.set_hi[set], tid, T);
@@ -468,7 +463,7 @@ __device__ __noinline__ double compute_forces(uint32_t ctx_off, int g, int out_s
             if (ENERGY) er = (real)0.5 * k * (px * px + py * py + pz * pz);
         }
         fout[3 * i] = fx[a]; fout[3 * i + 1] = fy[a]; fout[3 * i + 2] = fz[a];
-        if (ENERGY) e_thread += (double)((real)0.5 * en[a] + er);  // every pair is visited from both ends
+        if (ENERGY) e_thread += 0.5 * en[a] + (double)er;  // every pair is visited from both ends
     }
     team_sync<WT>();
     if (ENERGY) return team_sum<WT>(e_thread, s.red, tid, T);
@@ -800,7 +795,7 @@ struct UnitOps {
         }
         typename Vec<real>::r4 q;
         q.x = (real)px; q.y = (real)py; q.z = (real)pz; q.w = s.qk[i];
-        s.xq[2 * i] = q;
+        s.xq[2 * __ldg(C.iperm + i)] = q;  // slot order: LJ-active atoms first
     }
     template <int NA>
     __device__ __forceinline__ void stage(const PKUnit& U, const double (&x)[NA][3]) const
@@ -1180,7 +1175,7 @@ __device__ __forceinline__ void load_tables(const PKParams& P, const Smem<real>&
         s.qk[i] = p.x;
         typename Vec<real>::r4 l;
         l.x = p.y; l.y = p.z; l.z = (real)0; l.w = (real)0;
-        s.xq[2 * i + 1] = l;
+        s.xq[2 * __ldg(P.iperm + i) + 1] = l;
     }
 }
 

@@ -18,7 +18,7 @@ constexpr int kMaxSlots = 4;   // force caches (distinct V tokens of a splitting
 //   exception: p = {K qq, sigma, 4 eps}
 template <typename real>
 struct PKTerm {
-    int32_t kind, a0, a1, a2, a3, slot;
+    int32_t kind, a0, a1, a2, a3, slot;  // a0..a3: position SLOTS of the atoms
     real p[4];
 };
 
@@ -41,10 +41,10 @@ struct PKParams {
     double settle_m[9];       // SETTLE velocities: impulses = M b (row-major)
     const double* mass;       // [N]
     const void* nbp;          // real4 [N]: q sqrt(K), sigma/2, 2 sqrt(eps), 0
-    const uint32_t* excl;     // [N][excl_words] (self, exclusions, exceptions)
-    const uint32_t* excl_lj;  // [N][lj_words]: the same bits over the LJ-active atoms perm[0 .. n_lj)
-    int n_lj, lj_words;
-    const int32_t* perm;      // [n_perm] force-loop slot -> atom (LJ-active atoms first), -1 = empty
+    const uint32_t* excl;     // [N][excl_words] in SLOT space (self, exclusions, exceptions)
+    int n_lj;                 // slots [0, n_lj) hold the Lennard-Jones-active atoms
+    const int32_t* iperm;     // [N] atom -> slot
+    const int32_t* perm;      // [N] slot -> atom (LJ-active atoms first)
     int n_perm;
     const PKUnit* units;      // [n_units], constrained units first
     const int32_t* gc_off;    // generic clusters: constraints [gc_off[c], gc_off[c+1])
