@@ -112,6 +112,7 @@ class ClockSampler:
 def cpu_port_throughput(n_replicas, protocol_length, repeats=1):
     """CPU oracle port (OpenMP over replicas, all host cores) on the same workload."""
     from oracle import oracle
+    oracle.set_threads()
     cache = oracle.sample_equilibrium_scalar(SYSTEM, 20000, 100, seed=1)
     steps = protocol_length - 1
     t0 = time.perf_counter()
@@ -196,6 +197,7 @@ def particle_system(name):
 def particles_cpu_port(name, cache, n_replicas, steps_per_leg, dt, splittings, seed=1):
     """CPU oracle port (fp64, OpenMP over replicas, all host cores) on a bounded sample of the workload."""
     from oracle import oracle
+    oracle.set_threads()
     desc, _ = particle_system(name)
     t0 = time.perf_counter()
     total = 0

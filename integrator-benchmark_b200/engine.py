@@ -307,6 +307,50 @@ def reduce_moments(W_F, W_R):
     return m
 
 
+def _ragged(Ws):
+    """rows of work samples (list of arrays, 2-D array, or (flat, offsets)) -> (flat CUDA tensor, int64 offsets tensor)"""
+    t = torch()
+    if isinstance(Ws, tuple) and len(Ws) == 2:
+        flat, offs = Ws
+        return _to_cuda64(flat), t.as_tensor(np.asarray(offs, dtype=np.int64)).cuda() if not t.is_tensor(offs) else offs.cuda()
+    if t.is_tensor(Ws) and Ws.dim() == 2:
+        n, m = Ws.shape
+        return _to_cuda64(Ws.reshape(-1)), t.arange(0, (n + 1) * m, m, dtype=t.int64, device="cuda")
+    rows = [np.asarray(r, dtype=np.float64).reshape(-1) for r in Ws]
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    flat = np.concatenate(rows) if rows else np.zeros(0)
+    return _to_cuda64(flat), t.as_tensor(offs).cuda()
+
+
+def reduce_logmeanexp(Ws):
+    """per row: log(mean(exp(-w))) and std(exp(-w)) / (mean(exp(-w)) sqrt(n)) (lsi_reduce_logmeanexp;
+    reference: compare_near_eq_and_exact.py:62-97).  Returns two CUDA tensors of length n_rows."""
+    require_cuda()
+    t = torch()
+    flat, offs = _ragged(Ws)
+    n_rows = offs.numel() - 1
+    est = t.empty(n_rows, dtype=t.float64, device=flat.device)
+    sd = t.empty(n_rows, dtype=t.float64, device=flat.device)
+    if n_rows > 0:
+        with t.cuda.device(flat.device):
+            check(lib.lsi_reduce_logmeanexp(_ptr(flat), _ptr(offs), n_rows, _ptr(est), _ptr(sd), current_stream_ptr()))
+    return est, sd
+
+
+def bootstrap_nested(Ws, n_boot, seed=0):
+    """n_boot two-level bootstrap replicates of mean_rows(log-mean-exp(-w)) (lsi_bootstrap_nested;
+    reference: resample_Ws, compare_near_eq_and_exact.py:293-320).  Returns a CUDA tensor (n_boot,)."""
+    require_cuda()
+    t = torch()
+    flat, offs = _ragged(Ws)
+    n_rows = offs.numel() - 1
+    out = t.empty(int(n_boot), dtype=t.float64, device=flat.device)
+    with t.cuda.device(flat.device):
+        check(lib.lsi_bootstrap_nested(_ptr(flat), _ptr(offs), n_rows, int(n_boot), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out),
+                                       current_stream_ptr()))
+    return out
+
+
 def neq_free_energy_from_moments(moments, N_eff=None):
     m = (ctypes.c_double * 8)(*[float(v) for v in moments])
     dF, var = ctypes.c_double(), ctypes.c_double()

@@ -196,6 +196,34 @@ class NonequilibriumSimulator:
         result["W_shad"] = res["W"][0, 0].item()
         return result
 
+    # ---- many trajectories at once (what the nested estimator's inner and outer loops batch into)
+    def ensemble_shadow_work(self, x_0, v_0, n_steps, n=None, seed=None, want_final=False):
+        """`n` independent trajectories of `n_steps` in ONE launch.  x_0: (n_atoms, 3) shared by all or
+        (n, n_atoms, 3); v_0: same shapes, or None for fresh Maxwell-Boltzmann velocities per trajectory.
+        Returns the works (kT) as a numpy array, plus final (x, v) arrays when want_final."""
+        eq = self.equilibrium_simulator
+        t = engine.torch()
+        x0 = np.asarray(getattr(x_0, "xyz", x_0), dtype=np.float64)
+        if x0.ndim == 2:
+            if n is None:
+                raise ValueError("give n when x_0 is a single configuration")
+            x0 = np.broadcast_to(x0, (int(n),) + x0.shape)
+        n = x0.shape[0]
+        v0 = None
+        if v_0 is not None:
+            v0 = np.asarray(v_0.value_in_unit(unit.nanometer / unit.picosecond) if unit.is_quantity(v_0) else v_0, dtype=np.float64)
+            v0 = np.broadcast_to(v0, x0.shape)
+        rid = _rngstate.reserve_replicas(n)
+        res = engine.run_protocol(eq.engine_system(), self.integrator.program, n, int(n_steps), self._kT(), n_legs=1,
+                                  seed=_rngstate.get_seed() if seed is None else int(seed), replica0=rid,
+                                  x0=np.ascontiguousarray(x0), v0=None if v0 is None else np.ascontiguousarray(v0),
+                                  precision=self.precision, want_heat=True, want_final=want_final, want_moments=False, out={})
+        self.integrator._accumulate(heat=res["heat"].nan_to_num(0.0).sum().item())
+        W = res["W"][0].cpu().numpy()
+        if want_final:
+            return W, res["x_final"].cpu().numpy(), res["v_final"].cpu().numpy()
+        return W
+
     # ---- the ensemble
     def collect_protocol_samples(self, n_protocol_samples, protocol_length, marginal="configuration",
                                  store_potential_energy_traces=False, store_W_shad_traces=False, seed=None,

@@ -42,6 +42,20 @@ def lib():
     return _lib
 
 
+def set_threads(n=None):
+    """OpenMP threads of the oracle's replica loops (torchrun exports OMP_NUM_THREADS=1; the CPU baseline
+    legs of bench.py ask for every host core explicitly).  Returns the count in effect."""
+    lib()
+    n = int(n or os.cpu_count() or 1)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(n)
+        gomp.omp_get_max_threads.restype = ctypes.c_int
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return int(os.environ.get("OMP_NUM_THREADS", 1))
+
+
 def _dp(a):
     return None if a is None else a.ctypes.data_as(c_double_p)
 
