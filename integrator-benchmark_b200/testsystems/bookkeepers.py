@@ -51,7 +51,7 @@ class EquilibriumSimulator:
         self._engine_system = None
         # sampler settings (GPU Langevin equilibration; see collect_equilibrium_samples)
         self.equilibration_collision_rate = 5.0  # 1/ps
-        self.max_equilibration_steps = 20000
+        self.max_equilibration_steps = 1000000  # 1 ns at 1 fs, the length of the reference's burn-in
 
     # ---- engine handles
     @property
@@ -70,7 +70,8 @@ class EquilibriumSimulator:
         """x ~ pi for the cache.  The reference runs one XC-GHMC chain (steps_per_hmc = 10, 15 extra
         chances) and keeps every `thinning_interval`-th state (:66-113).  Here `n_samples` INDEPENDENT
         replicas start from `positions`, relax with a short small-step high-friction Langevin leg, then run
-        VRORV Langevin dynamics at `timestep` for min(burn_in_length, max_equilibration_steps) steps; the
+        VRORV Langevin dynamics at `timestep` for min(burn_in_length * steps_per_hmc, max_equilibration_steps)
+        steps (the reference's burn-in is burn_in_length XC-GHMC iterations of steps_per_hmc steps); the
         final configurations are the cache.  (Langevin samples carry the O(dt^2) configuration bias that
         this package measures -- ~1e-4 kT at 1 fs for rigid water; the Metropolised
         sampler is the "next" row 8f-1 of the scope table.)  Returns (n_samples, n_atoms, 3) in nm."""
@@ -82,7 +83,8 @@ class EquilibriumSimulator:
         dt = self.timestep.value_in_unit(unit.picosecond) if unit.is_quantity(self.timestep) else float(self.timestep)
         x = t.as_tensor(np.ascontiguousarray(self.positions))[None].expand(n, -1, -1).contiguous().cuda()
         stages = [(0.1 * dt, 100.0, 500), (0.5 * dt, 20.0, 500),
-                  (dt, self.equilibration_collision_rate, int(min(self.burn_in_length, self.max_equilibration_steps)))]
+                  (dt, self.equilibration_collision_rate,
+                   int(min(self.burn_in_length * self.steps_per_hmc, self.max_equilibration_steps)))]
         for k, (h, gamma, n_steps) in enumerate(stages):
             prog = engine.Program("V R O R V", h, gamma)
             res = engine.run_protocol(system, prog, n, n_steps, self.kT_value, n_legs=1, seed=seed + 7919 * (k + 1),
