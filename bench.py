@@ -590,7 +590,10 @@ def main():
     hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
     roofline = {
         "bound": "fp64_fma", "kernel": "toy_protocol_kernel<double_well>", "achieved": achieved, "peak": peaks["fp64"],
-        "unit": "TFLOP/s", "frac": achieved / peaks["fp64"], "traffic": None,
+        "unit": "TFLOP/s", "frac": achieved / peaks["fp64"],
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of toy_fused_kernel, ncu --set full
+        # (profiles/r1_toy_fused_ncu_details.txt): the 8 MB equilibrium cache is read once, the works stay in L2
+        "traffic": 8.04e6 if n == (1 << 20) else None,
         "peak_source": "lsi_microbench_fma fp64, best of 6, measured in this run (fp32: %.1f TFLOP/s)" % peaks["fp32"],
         "note": "algorithmic flops exclude the Philox + Box-Muller noise generation that dominates issue slots "
                 "(n_O Gaussians per replica-step); see profiles/ for sm__inst_executed and pipe utilisation",
