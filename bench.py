@@ -471,10 +471,12 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     moments_all = torch.zeros(len(SPLITTINGS), 8, dtype=torch.float64, device=dev)
 
+    toy_precision = args.precision or "double"
+
     def one_pass(x_cache_dev):
         for j, (k, prog) in enumerate(programs.items()):
             res = engine.run_protocol(system, prog, n, steps_per_leg, 1.0 / BETA, marginal="configuration", seed=seed,
-                                      replica0=replica0, x_cache=x_cache_dev, out=bufs[k])
+                                      replica0=replica0, x_cache=x_cache_dev, out=bufs[k], precision=toy_precision)
             moments_all[j].copy_(res["moments"], non_blocking=True)
         parallel.all_reduce_moments(moments_all)
 
@@ -520,7 +522,7 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             engine.run_protocol(system, prog, n, steps_per_leg, 1.0 / BETA, marginal="configuration", seed=seed,
-                                replica0=replica0, x_cache=x_cache, out=bufs[k])
+                                replica0=replica0, x_cache=x_cache, out=bufs[k], precision=toy_precision)
             b.record()
             b.synchronize()
             k_ms[k] += a.elapsed_time(b)
@@ -548,16 +550,31 @@ def main():
     m_host = torch.empty(len(SPLITTINGS), 8, dtype=torch.float64).pin_memory()
     x_dev = torch.empty_like(x_cache)
 
+    # D2H of the works rides a copy stream so that it overlaps the next splitting's kernel (PCIe, not the SMs,
+    # bounds this loop: 100 MB per step); events order kernel -> copy and copy -> next reuse of the buffer
+    copy_stream = torch.cuda.Stream(device=dev)
+    done_k = [torch.cuda.Event() for _ in SPLITTINGS]
+    done_c = [torch.cuda.Event() for _ in SPLITTINGS]
+    for e in done_c:
+        e.record(copy_stream)
+
     def e2e_pass():
+        main = torch.cuda.current_stream()
         x_dev.copy_(x_cache_host, non_blocking=True)
         for j, (k, prog) in enumerate(programs.items()):
+            main.wait_event(done_c[j])  # the previous pass's copy of this buffer has left
             res = engine.run_protocol(system, prog, n, steps_per_leg, 1.0 / BETA, marginal="configuration", seed=seed,
-                                      replica0=replica0, x_cache=x_dev, out=bufs[k])
-            w_host[j].copy_(res["W"], non_blocking=True)
+                                      replica0=replica0, x_cache=x_dev, out=bufs[k], precision=toy_precision)
             moments_all[j].copy_(res["moments"], non_blocking=True)
+            done_k[j].record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done_k[j])
+                w_host[j].copy_(res["W"], non_blocking=True)
+                done_c[j].record(copy_stream)
         parallel.all_reduce_moments(moments_all)
         m_host.copy_(moments_all, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
+        copy_stream.synchronize()
         return [ib.evaluation.estimate_from_moments(m_host[j].numpy()) for j in range(len(SPLITTINGS))]
 
     for _ in range(3):
@@ -612,7 +629,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args, n),
+        "dtype": "f64" if toy_precision == "double" else "f64 state, f32-generated Gaussians", "data": "synthetic",
+        "config": workload_config(args, n),
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_cache_host.numel() * 8),
