@@ -241,6 +241,21 @@ int lsi_run_protocol(const lsi_system* sys, const lsi_program* prog, const lsi_p
 int lsi_sample_equilibrium_scalar(const lsi_system* sys, double kT, int64_t n, int32_t n_burn,
                                   uint64_t seed, uint64_t replica0, double* x_out, void* stream);
 
+/* Equilibrium configurations for a particle system by extra-chance HMC: the sampler behind the reference's
+ * {name}_samples.h5 caches (EquilibriumSimulator.collect_equilibrium_samples, benchmark/testsystems/
+ * bookkeepers.py:66-113, with XCGHMCIntegrator(steps_per_hmc = 10, extra_chances = 15, collision_rate = None),
+ * benchmark/integrators/kyle/xchmc.py:84-116).  n independent chains; chain c starts from x_in[c] (projected onto
+ * the constraints) and runs n_rounds rounds: fresh Maxwell-Boltzmann velocities, up to 1 + extra_chances
+ * proposals of steps_per_hmc velocity-Verlet steps, Metropolis test with one uniform per round, restore on
+ * failure.  x_in / x_out [n][n_atoms][3] (may alias), v_out optional, accept_out optional [n][2] =
+ * {fraction of rounds accepted, fraction accepted at the first chance}; device pointers.
+ * Streams: velocities Philox(replica0 + c, draw = 2 round, LSI_TAG_EQ, unit = atom), uniform
+ * Philox(replica0 + c, 2 round + 1, LSI_TAG_EQ, 0) lane 0. */
+int lsi_sample_equilibrium_particles(const lsi_system* sys, int32_t precision, double kT, int64_t n, int32_t n_rounds,
+                                     int32_t steps_per_hmc, int32_t extra_chances, double dt_ps, uint64_t seed,
+                                     uint64_t replica0, const double* x_in, double* x_out, double* v_out,
+                                     double* accept_out, void* stream);
+
 /* ------------------------------------------------------------------ estimators
  * lsi_reduce_moments: the six sums estimate_nonequilibrium_free_energy needs
  * (benchmark/evaluation/analysis.py:8-17) from device arrays W_F, W_R of length n; same

@@ -96,6 +96,8 @@ def _load():
         "lsi_protocol_workspace_bytes": (i64, [i64]),
         "lsi_run_protocol": (i32, [vp, vp, ctypes.POINTER(ProtocolArgs), vp]),
         "lsi_sample_equilibrium_scalar": (i32, [vp, dbl, i64, ctypes.c_int32, u64, u64, vp, vp]),
+        "lsi_sample_equilibrium_particles": (i32, [vp, ctypes.c_int32, dbl, i64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, dbl,
+                                                   u64, u64, vp, vp, vp, vp, vp]),
         "lsi_reduce_moments": (i32, [vp, vp, i64, vp, vp, i64, vp]),
         "lsi_neq_free_energy": (i32, [c_double_p, dbl, c_double_p, c_double_p]),
         "lsi_reduce_logmeanexp": (i32, [vp, vp, i64, vp, vp, vp]),

@@ -179,14 +179,14 @@ int env_int(const char* name, int dflt)
 }
 
 // team shape: one warp per replica up to 64 atoms (several replicas per CTA), else one CTA per replica
-int configure(const lsi_particles* p, bool mixed, int n_slots, bool generic_smem, int64_t n, bool diag, PKLaunch& L)
+int configure(const lsi_particles* p, bool mixed, int n_slots, bool generic_smem, int64_t n, bool diag, PKLaunch& L, bool hmc = false)
 {
     const int N = p->n_atoms;
     L.periodic = p->nb_method == LSI_NB_CUTOFF_PERIODIC;
     L.diag = diag;
     L.n = n;
     L.warp_team = N <= 64 && env_int("LSI_PK_WARP_TEAM", 1) != 0;
-    const size_t per_team = lsi_pk_smem_per_team(mixed, N, n_slots, p->n_tf, generic_smem, L.warp_team);
+    const size_t per_team = lsi_pk_smem_per_team(mixed, N, n_slots, p->n_tf, generic_smem, L.warp_team, hmc);
     if (L.warp_team) {
         L.apl = N <= 32 ? 1 : 2;
         L.teams = std::max(1, std::min(4, env_int("LSI_PK_TEAMS", 4)));
@@ -582,4 +582,35 @@ LSI_EXPORT int lsi_particles_energy_forces(const lsi_system* sys, int32_t precis
     rc = configure(p, mixed, 1, false, n, false, L);
     if (rc != LSI_OK) return rc;
     return mixed ? lsi_pk_launch_energy_f32(P, L, stream) : lsi_pk_launch_energy_f64(P, L, stream);
+}
+
+LSI_EXPORT int lsi_sample_equilibrium_particles(const lsi_system* sys, int32_t precision, double kT, int64_t n, int32_t n_rounds,
+                                                int32_t steps_per_hmc, int32_t extra_chances, double dt_ps, uint64_t seed,
+                                                uint64_t replica0, const double* x_in, double* x_out, double* v_out,
+                                                double* accept_out, void* stream)
+{
+    if (!sys || sys->kind != LSI_SYS_PARTICLES || !x_in || !x_out || n < 0 || n_rounds < 0 || steps_per_hmc < 1 || extra_chances < 0 ||
+        !(kT > 0.0) || !(dt_ps > 0.0))
+        return lsi_set_error(LSI_ERR_ARG, "lsi_sample_equilibrium_particles: bad argument");
+    if (precision != LSI_PRECISION_DOUBLE && precision != LSI_PRECISION_MIXED) return lsi_set_error(LSI_ERR_ARG, "unknown precision %d", precision);
+    if (n == 0) return LSI_OK;
+    if (lsi_device_count() <= 0) return lsi_set_error(LSI_ERR_CUDA, "no CUDA device: liblsi has no CPU fallback");
+    lsi_particles* p = sys->particles;
+    DevTables* t = nullptr;
+    int rc = get_tables(p, &t);
+    if (rc != LSI_OK) return rc;
+    const bool mixed = precision == LSI_PRECISION_MIXED;
+    PKParams P;
+    std::memset(&P, 0, sizeof(P));
+    fill_system_params(p, t, mixed, P);
+    P.n_slots = 2;
+    P.n = n;
+    P.seed = seed; P.replica0 = replica0;
+    P.kT = kT; P.inv_kT = 1.0 / kT;
+    P.x0 = x_in; P.x_final = x_out; P.v_final = v_out;
+    P.hmc_rounds = n_rounds; P.hmc_steps = steps_per_hmc; P.hmc_extra = extra_chances; P.hmc_dt = dt_ps; P.hmc_accept = accept_out;
+    PKLaunch L;
+    rc = configure(p, mixed, 2, p->n_generic > 0, n, false, L, true);
+    if (rc != LSI_OK) return rc;
+    return mixed ? lsi_pk_launch_hmc_f32(P, L, stream) : lsi_pk_launch_hmc_f64(P, L, stream);
 }

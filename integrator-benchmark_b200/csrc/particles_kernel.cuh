@@ -53,16 +53,18 @@ static __device__ __forceinline__ double round_fma(double d, double inv) { retur
 
 // ---- shared-memory layout of one team (host and device agree through this function)
 struct Layout {
-    uint32_t x, v, xref, mass, invm, sigv, red, ctx, xq, qk, f, tf, total;
+    uint32_t x, v, xref, xold, vold, mass, invm, sigv, red, ctx, xq, qk, f, tf, total;
 };
 template <typename real>
-__host__ __device__ inline Layout layout(int N, int n_slots, int n_tf, bool generic, bool warp_team)
+__host__ __device__ inline Layout layout(int N, int n_slots, int n_tf, bool generic, bool warp_team, bool hmc = false)
 {
     Layout L;
     uint32_t o = 0;
     L.x = o; o += (uint32_t)sizeof(double) * 3 * N;
     L.v = o; o += (uint32_t)sizeof(double) * 3 * N;
     L.xref = o; if (generic) o += (uint32_t)sizeof(double) * 3 * N;
+    L.xold = o; if (hmc) o += (uint32_t)sizeof(double) * 3 * N;  // HMC sampler: state before the proposal
+    L.vold = o; if (hmc) o += (uint32_t)sizeof(double) * 3 * N;
     L.mass = o; o += (uint32_t)sizeof(double) * N;
     L.invm = o; o += (uint32_t)sizeof(double) * N;
     L.sigv = o; o += (uint32_t)sizeof(double) * N;
@@ -1324,6 +1326,85 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
     if (P.v_final) for (int k = tid; k < D; k += T) P.v_final[r * D + k] = s.v[k];
 }
 
+// Equilibrium configurations by extra-chance HMC (the sampler behind the reference's sample caches:
+// XCGHMCIntegrator with collision_rate = None, benchmark/integrators/kyle/xchmc.py:84-116, driven by
+// EquilibriumSimulator.collect_equilibrium_samples, benchmark/testsystems/bookkeepers.py:66-113).
+// Per round: fresh Maxwell-Boltzmann velocities (projected on the constraints), E_old, one uniform u; up to
+// 1 + extra chances of `hmc_steps` velocity-Verlet steps each (V(h/2) R(h) V(h/2), projections after every
+// substep); after each, mu1 = max(mu1, min(1, exp(-(E_new - E_old)/kT))); the first chance with u <= mu1 is
+// accepted, otherwise the configuration is restored.  Targets exp(-U/kT) on the constraint manifold exactly.
+// Streams: velocities Philox(replica, draw = 2 round, TAG_EQ, unit = atom); u = Philox(replica, 2 round + 1, TAG_EQ, 0).x
+template <typename real, bool PERIODIC, bool WT, int APL>
+__global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_hmc_kernel(const __grid_constant__ PKParams P, int teams)
+{
+    const int N = P.N, D = 3 * N;
+    const int T = WT ? 32 : (int)blockDim.x;
+    const int tid = WT ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const int team = WT ? (int)(threadIdx.x >> 5) : 0;
+    const int64_t r = WT ? (int64_t)blockIdx.x * teams + team : (int64_t)blockIdx.x;
+    if (r >= P.n) return;
+    const Layout L = layout<real>(N, 2, P.n_tf, P.n_generic > 0, WT, true);
+    const uint32_t team_off = (uint32_t)team * L.total;
+    const Smem<real> s = carve<real>(pk_smem + team_off, L);
+    double* const xold = sm<double>(team_off + L.xold);
+    double* const vold = sm<double>(team_off + L.vold);
+    const uint32_t ctx = team_off + L.ctx;
+    if (tid == 0) fill_ctx<real>(sm<TeamCtx<real>>(ctx), P, L, team_off);
+    const uint64_t rid = P.replica0 + (uint64_t)r;
+    load_tables<real>(P, s, tid, T);
+    for (int k = tid; k < D; k += T) { s.x[k] = P.x0[r * D + k]; s.v[k] = 0.0; }
+    team_sync<WT>();
+    PK_FOR_UNITS(u) unit_R<real>(ctx, u, 0.0);  // project the start configuration, stage it
+    double pe = compute_forces<real, PERIODIC, WT, APL, true>(ctx, -1, 0, tid, T);
+    const double h = P.hmc_dt;
+    int n_acc = 0, n_first = 0;
+    for (int round = 0; round < P.hmc_rounds; ++round) {
+        draw_velocities<real>(ctx, rid, 2u * (uint32_t)round, LSI_TAG_EQ, P.mass, P.kT, tid, T);
+        team_sync<WT>();
+        double ke = 0.0;
+        PK_FOR_UNITS(u) ke += unit_R<real>(ctx, u, 0.0);  // velocity constraints (positions already satisfy theirs)
+        const double e_old = pe + team_sum<WT>(ke, s.red, tid, T);
+        team_sync<WT>();
+        for (int k = tid; k < D; k += T) { xold[k] = s.x[k]; vold[k] = s.v[k]; s.f[D + k] = s.f[k]; }
+        const lsi::Philox4 ur = lsi::philox_block(P.seed, rid, 2u * (uint32_t)round + 1u, LSI_TAG_EQ, 0u);
+        const double uni = ((double)ur.x + 0.5) * 2.3283064365386962890625e-10;
+        double mu1 = 0.0, pe_new = pe;
+        for (int c = 0; c <= P.hmc_extra; ++c) {
+            if (!(uni > mu1)) break;
+            for (int st = 0; st < P.hmc_steps; ++st) {
+                PK_FOR_UNITS(u) unit_V<real>(ctx, u, 0.5 * h, 0, 0);
+                PK_FOR_UNITS(u) unit_R<real>(ctx, u, h);
+                if (st + 1 < P.hmc_steps) compute_forces<real, PERIODIC, WT, APL, false>(ctx, -1, 0, tid, T);
+                else pe_new = compute_forces<real, PERIODIC, WT, APL, true>(ctx, -1, 0, tid, T);
+                PK_FOR_UNITS(u) unit_V<real>(ctx, u, 0.5 * h, 0, 0);
+            }
+            double ke1 = 0.0;
+            PK_FOR_UNITS(u) ke1 += unit_kinetic<real>(ctx, u);
+            double e_new = pe_new + team_sum<WT>(ke1, s.red, tid, T);
+            if (!(e_new == e_new)) e_new = INFINITY;  // nan_to_inf (xchmc.py:92)
+            mu1 = fmax(mu1, fmin(1.0, exp(-(e_new - e_old) * P.inv_kT)));
+            if (c == 0 && uni <= mu1) ++n_first;
+        }
+        team_sync<WT>();
+        if (uni > mu1) {  // every chance failed: back to the start of the round
+            for (int k = tid; k < D; k += T) { s.x[k] = xold[k]; s.v[k] = vold[k]; s.f[k] = s.f[D + k]; }
+            team_sync<WT>();
+            PK_FOR_UNITS(u) unit_R<real>(ctx, u, 0.0);  // re-stage the restored positions
+            team_sync<WT>();
+        } else {
+            pe = pe_new;
+            ++n_acc;
+        }
+    }
+    team_sync<WT>();
+    if (P.x_final) for (int k = tid; k < D; k += T) P.x_final[r * D + k] = s.x[k];
+    if (P.v_final) for (int k = tid; k < D; k += T) P.v_final[r * D + k] = s.v[k];
+    if (P.hmc_accept && tid == 0) {
+        P.hmc_accept[2 * r] = (double)n_acc / (double)(P.hmc_rounds > 0 ? P.hmc_rounds : 1);
+        P.hmc_accept[2 * r + 1] = (double)n_first / (double)(P.hmc_rounds > 0 ? P.hmc_rounds : 1);
+    }
+}
+
 // potential energy and forces of force group q_group for n configurations
 template <typename real, bool PERIODIC, bool WT, int APL>
 __global__ void __launch_bounds__(WT ? 128 : 384) particles_energy_kernel(const __grid_constant__ PKParams P, int teams)
@@ -1373,6 +1454,18 @@ int launch_protocol3(const PKParams& P, const PKLaunch& L, cudaStream_t st)
 }
 
 template <typename real, bool PERIODIC, bool WT, int APL>
+int launch_hmc3(const PKParams& P, const PKLaunch& L, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)(WT ? (L.n + L.teams - 1) / L.teams : L.n);
+    auto k = particles_hmc_kernel<real, PERIODIC, WT, APL>;
+    int rc;
+    if ((rc = set_smem(k, L.smem)) != LSI_OK) return rc;
+    k<<<grid, L.threads, L.smem, st>>>(P, L.teams);
+    LSI_CUDA_CHECK(cudaGetLastError());
+    return LSI_OK;
+}
+
+template <typename real, bool PERIODIC, bool WT, int APL>
 int launch_energy3(const PKParams& P, const PKLaunch& L, cudaStream_t st)
 {
     const unsigned grid = (unsigned)(WT ? (L.n + L.teams - 1) / L.teams : L.n);
@@ -1397,6 +1490,13 @@ int launch_protocol(const PKParams& P, const PKLaunch& L, void* stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     PK_DISPATCH(launch_protocol3, real)
+}
+
+template <typename real>
+int launch_hmc(const PKParams& P, const PKLaunch& L, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    PK_DISPATCH(launch_hmc3, real)
 }
 
 template <typename real>

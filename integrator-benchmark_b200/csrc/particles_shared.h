@@ -75,6 +75,10 @@ struct PKParams {
     const double* x0;
     const double* v0;
     double *W, *heat, *W_direct, *x_final, *v_final, *trace_x, *trace_v, *trace_w;
+    // ---- equilibrium sampler (particles_hmc_kernel): input P.x0, output P.x_final / P.v_final
+    int hmc_rounds, hmc_steps, hmc_extra;
+    double hmc_dt;
+    double* hmc_accept;       // [n][2]: fraction of rounds accepted, fraction accepted at the first chance
     // ---- energy / force query (particles_energy_kernel)
     int q_group;
     const double* q_x;
@@ -91,7 +95,9 @@ struct PKLaunch {
     int64_t n;        // replicas (protocol) or configurations (energy query)
 };
 
-size_t lsi_pk_smem_per_team(bool mixed, int N, int n_slots, int n_tf, bool generic, bool warp_team);
+size_t lsi_pk_smem_per_team(bool mixed, int N, int n_slots, int n_tf, bool generic, bool warp_team, bool hmc);
+int lsi_pk_launch_hmc_f32(const PKParams& P, const PKLaunch& L, void* stream);
+int lsi_pk_launch_hmc_f64(const PKParams& P, const PKLaunch& L, void* stream);
 int lsi_pk_launch_protocol_f32(const PKParams& P, const PKLaunch& L, void* stream);
 int lsi_pk_launch_protocol_f64(const PKParams& P, const PKLaunch& L, void* stream);
 int lsi_pk_launch_energy_f32(const PKParams& P, const PKLaunch& L, void* stream);

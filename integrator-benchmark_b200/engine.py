@@ -214,6 +214,24 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def sample_equilibrium_particles(system, x, kT, n_rounds, steps_per_hmc=10, extra_chances=15, dt=0.001, seed=0, replica0=0,
+                                 precision="double", want_velocities=False):
+    """Extra-chance HMC chains started from x [n, N, 3] (lsi_sample_equilibrium_particles): returns
+    (x_out, v_out or None, accept [n, 2]) as CUDA tensors."""
+    require_cuda()
+    t = torch()
+    x = _to_cuda64(x).reshape(-1, system.n_atoms, 3)
+    n = x.shape[0]
+    x_out = t.empty_like(x)
+    v_out = t.empty_like(x) if want_velocities else None
+    acc = t.zeros(n, 2, dtype=t.float64, device=x.device)
+    with t.cuda.device(x.device):
+        check(lib.lsi_sample_equilibrium_particles(system.handle, _cabi.PRECISION[precision], float(kT), n, int(n_rounds),
+                                                   int(steps_per_hmc), int(extra_chances), float(dt), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                   int(replica0), _ptr(x), _ptr(x_out), _ptr(v_out), _ptr(acc), current_stream_ptr()))
+    return x_out, v_out, acc
+
+
 def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configuration", n_legs=2, seed=0,
                  replica0=0, x_cache=None, x0=None, v0=None, precision="double", want_heat=False,
                  want_direct=False, want_final=False, traces=False, want_moments=True, device=None, out=None,

@@ -49,8 +49,10 @@ class EquilibriumSimulator:
         self.samples = None
         self._samples_dev = None
         self._engine_system = None
-        # sampler settings (GPU Langevin equilibration; see collect_equilibrium_samples)
-        self.equilibration_collision_rate = 5.0  # 1/ps
+        # sampler settings (see collect_equilibrium_samples)
+        self.extra_chances = 15
+        self.sampler_precision = "double"
+        self.acceptance = None
         self.max_equilibration_steps = 1000000  # 1 ns at 1 fs, the length of the reference's burn-in
 
     # ---- engine handles
@@ -67,14 +69,13 @@ class EquilibriumSimulator:
 
     # ---- equilibrium cache
     def collect_equilibrium_samples(self, seed=None):
-        """x ~ pi for the cache.  The reference runs one XC-GHMC chain (steps_per_hmc = 10, 15 extra
-        chances) and keeps every `thinning_interval`-th state (:66-113).  Here `n_samples` INDEPENDENT
-        replicas start from `positions`, relax with a short small-step high-friction Langevin leg, then run
-        VRORV Langevin dynamics at `timestep` for min(burn_in_length * steps_per_hmc, max_equilibration_steps)
-        steps (the reference's burn-in is burn_in_length XC-GHMC iterations of steps_per_hmc steps); the
-        final configurations are the cache.  (Langevin samples carry the O(dt^2) configuration bias that
-        this package measures -- ~1e-4 kT at 1 fs for rigid water; the Metropolised
-        sampler is the "next" row 8f-1 of the scope table.)  Returns (n_samples, n_atoms, 3) in nm."""
+        """x ~ pi for the cache (reference :66-113: XC-GHMC with steps_per_hmc = 10, 15 extra chances, no collision
+        rate, i.e. extra-chance HMC; `burn_in_length` rounds, then one sample every `thinning_interval` rounds of ONE
+        chain).  Here `n_samples` INDEPENDENT chains start from `positions`: a short small-step, high-friction Langevin
+        relaxation (the reference minimises the energy instead), then min(burn_in_length, max_equilibration_steps /
+        steps_per_hmc) rounds of the same extra-chance HMC on the GPU (lsi_sample_equilibrium_particles, fp64); the
+        final configurations are the cache -- exact samples of exp(-U/kT) on the constraint manifold, no time-step
+        bias.  Returns (n_samples, n_atoms, 3) in nm; acceptance statistics in `self.acceptance`."""
         engine.require_cuda()
         t = engine.torch()
         system = self.engine_system()
@@ -82,14 +83,15 @@ class EquilibriumSimulator:
         seed = _rngstate.get_seed() if seed is None else int(seed)
         dt = self.timestep.value_in_unit(unit.picosecond) if unit.is_quantity(self.timestep) else float(self.timestep)
         x = t.as_tensor(np.ascontiguousarray(self.positions))[None].expand(n, -1, -1).contiguous().cuda()
-        stages = [(0.1 * dt, 100.0, 500), (0.5 * dt, 20.0, 500),
-                  (dt, self.equilibration_collision_rate,
-                   int(min(self.burn_in_length * self.steps_per_hmc, self.max_equilibration_steps)))]
-        for k, (h, gamma, n_steps) in enumerate(stages):
+        for k, (h, gamma, n_steps) in enumerate([(0.1 * dt, 100.0, 500), (0.5 * dt, 20.0, 500)]):
             prog = engine.Program("V R O R V", h, gamma)
             res = engine.run_protocol(system, prog, n, n_steps, self.kT_value, n_legs=1, seed=seed + 7919 * (k + 1),
-                                      replica0=0, x0=x, want_final=True, want_moments=False, precision="double")
+                                      replica0=0, x0=x, want_final=True, want_moments=False, precision="double", out={})
             x = res["x_final"]
+        rounds = int(min(self.burn_in_length, self.max_equilibration_steps // self.steps_per_hmc))
+        x, _, acc = engine.sample_equilibrium_particles(system, x, self.kT_value, rounds, self.steps_per_hmc, self.extra_chances, dt,
+                                                        seed=seed, replica0=0, precision=self.sampler_precision)
+        self.acceptance = acc.mean(dim=0).cpu().numpy()  # (rounds accepted, accepted at the first chance)
         ok = t.isfinite(x).all(dim=(1, 2))
         if not bool(ok.all()):
             x = x[ok]
@@ -97,6 +99,10 @@ class EquilibriumSimulator:
         self.samples = self._samples_dev.cpu().numpy()
         self.cached = True
         return self.samples
+
+    def get_acceptance_rate(self):
+        """fraction of HMC rounds accepted (reference :80-83)"""
+        return float(self.acceptance[0])
 
     def load_or_simulate_samples(self):
         if not self.cached:

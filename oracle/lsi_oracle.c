@@ -862,3 +862,85 @@ ORC_API int orc_particles_protocol(const OrcParticles* S, double kT, int n_ops, 
     }
     return rc_all;
 }
+
+/*
+ * Extra-chance HMC equilibrium sampler (benchmark/integrators/kyle/xchmc.py:84-116 with collision_rate = None,
+ * hamiltonian step of kyle/ghmc.py:103-114 in RATTLE form: every substep is followed by its projection).
+ * Same streams as lsi_sample_equilibrium_particles: velocities (replica, draw = 2 round, TAG_EQ, unit = atom),
+ * uniform (replica, 2 round + 1, TAG_EQ, 0) lane 0.  accept: [n][2] = {accepted rounds, accepted at first chance} / rounds.
+ */
+ORC_API int orc_particles_hmc(const OrcParticles* S, double kT, int64_t n, int n_rounds, int steps_per_hmc, int extra_chances,
+                              double dt, uint64_t seed, uint64_t replica0, const double* x_in, double* x_out, double* v_out,
+                              double* accept)
+{
+    const int N = S->n_atoms, D = 3 * N;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t r = 0; r < n; ++r) {
+        const uint64_t rid = replica0 + (uint64_t)r;
+        double* x = (double*)malloc(sizeof(double) * D);
+        double* v = (double*)calloc(D, sizeof(double));
+        double* f = (double*)malloc(sizeof(double) * D);
+        double* xu = (double*)malloc(sizeof(double) * D);
+        double* xi = (double*)malloc(sizeof(double) * D);
+        double* xold = (double*)malloc(sizeof(double) * D);
+        double* vold = (double*)malloc(sizeof(double) * D);
+        double* fold = (double*)malloc(sizeof(double) * D);
+        memcpy(x, x_in + r * D, sizeof(double) * D);
+        memcpy(xu, x, sizeof(double) * D);
+        constrain_positions(S, xu, x);
+        double pe = particles_forces(S, x, -1, f);
+        int n_acc = 0, n_first = 0;
+        for (int round = 0; round < n_rounds; ++round) {
+            atom_normals(seed, rid, 2u * (uint32_t)round, TAG_EQ, N, 0, xi);
+            for (int i = 0; i < D; ++i) v[i] = sqrt(kT / S->mass[i / 3]) * xi[i];
+            memcpy(xu, x, sizeof(double) * D);
+            constrain_positions(S, xu, x);
+            constrain_velocities(S, x, v);
+            const double e_old = pe + kinetic_energy(S, v);
+            memcpy(xold, x, sizeof(double) * D);
+            memcpy(vold, v, sizeof(double) * D);
+            memcpy(fold, f, sizeof(double) * D);
+            uint32_t ur[4];
+            philox_block(seed, rid, 2u * (uint32_t)round + 1u, TAG_EQ, 0u, ur);
+            const double uni = ((double)ur[0] + 0.5) * 2.3283064365386962890625e-10;
+            double mu1 = 0.0, pe_new = pe;
+            for (int c = 0; c <= extra_chances; ++c) {
+                if (!(uni > mu1)) break;
+                for (int st = 0; st < steps_per_hmc; ++st) {
+                    for (int k = 0; k < D; ++k) v[k] = v[k] + 0.5 * dt * f[k] / S->mass[k / 3];
+                    constrain_velocities(S, x, v);
+                    memcpy(xu, x, sizeof(double) * D);
+                    for (int k = 0; k < D; ++k) x[k] = x[k] + dt * v[k];
+                    memcpy(xi, x, sizeof(double) * D);
+                    constrain_positions(S, xu, x);
+                    for (int k = 0; k < D; ++k) v[k] = v[k] + (x[k] - xi[k]) / dt;
+                    constrain_velocities(S, x, v);
+                    pe_new = particles_forces(S, x, -1, f);
+                    for (int k = 0; k < D; ++k) v[k] = v[k] + 0.5 * dt * f[k] / S->mass[k / 3];
+                    constrain_velocities(S, x, v);
+                }
+                double e_new = pe_new + kinetic_energy(S, v);
+                if (!(e_new == e_new)) e_new = INFINITY;
+                const double mu = fmin(1.0, exp(-(e_new - e_old) / kT));
+                if (mu > mu1) mu1 = mu;
+                if (c == 0 && uni <= mu1) ++n_first;
+            }
+            if (uni > mu1) {
+                memcpy(x, xold, sizeof(double) * D);
+                memcpy(v, vold, sizeof(double) * D);
+                memcpy(f, fold, sizeof(double) * D);
+            } else {
+                pe = pe_new;
+                ++n_acc;
+            }
+        }
+        memcpy(x_out + r * D, x, sizeof(double) * D);
+        if (v_out) memcpy(v_out + r * D, v, sizeof(double) * D);
+        if (accept) {
+            accept[2 * r] = (double)n_acc / (double)(n_rounds > 0 ? n_rounds : 1);
+            accept[2 * r + 1] = (double)n_first / (double)(n_rounds > 0 ? n_rounds : 1);
+        }
+        free(x); free(v); free(f); free(xu); free(xi); free(xold); free(vold); free(fold);
+    }
+    return 0;
+}

@@ -298,3 +298,17 @@ def particles_protocol(desc, splitting, dt, gamma, kT, n_replicas, n_steps, marg
     if traces:
         out.update(trace_x=tx, trace_v=tv, trace_pe=tpe, trace_ke=tke, trace_heat=th, trace_wdir=twd)
     return out
+
+
+def particles_hmc(desc, kT, x_in, n_rounds, steps_per_hmc=10, extra_chances=15, dt=0.001, seed=0, replica0=0):
+    """Extra-chance HMC equilibrium sampler; returns (x_out (n, N, 3), v_out, accept (n, 2))."""
+    S, _keep = make_particles(desc)
+    N = int(desc["n_atoms"])
+    x_in = _f64(x_in).reshape(-1, N, 3)
+    n = len(x_in)
+    x_out, v_out, acc = np.zeros_like(x_in), np.zeros_like(x_in), np.zeros((n, 2))
+    rc = lib().orc_particles_hmc(ctypes.byref(S), ctypes.c_double(kT), ctypes.c_int64(n), int(n_rounds), int(steps_per_hmc),
+                                 int(extra_chances), ctypes.c_double(dt), ctypes.c_uint64(seed), ctypes.c_uint64(replica0),
+                                 _dp(x_in), _dp(x_out), _dp(v_out), _dp(acc))
+    assert rc == 0
+    return x_out, v_out, acc

@@ -140,3 +140,40 @@ def test_named_reference_systems_run(ib):
         out = NonequilibriumSimulator(eq, integ).collect_protocol_samples(64, 20)
         assert np.isfinite(out["W_shads_F"]).all() and np.isfinite(out["W_shads_R"]).all()
         assert np.abs(out["W_shads_F"]).max() < 20.0
+
+
+def test_hmc_equilibrium_sampler_matches_oracle_and_target(ib, orc):
+    """lsi_sample_equilibrium_particles (extra-chance HMC, the sampler behind the reference's sample caches,
+    benchmark/integrators/kyle/xchmc.py:84-116): same chains as the oracle, and the right distribution."""
+    from integrator_benchmark_b200.testsystems import systems
+    KT = 8.3144621e-3 * 298.0
+    for builder, kw, dt in ((systems.water_cluster, dict(n_waters=20, constrained=True, seed=1), 0.002),
+                            (systems.alanine_dipeptide, dict(constrained=True), 0.002)):
+        desc, x = builder(**kw)
+        desc = dict(desc, constraint_tolerance=1e-13)
+        system = ib.engine.ParticleSystem(desc)
+        # start from a relaxed configuration so that proposals are accepted and rejected
+        x0, _, _ = orc.particles_hmc(desc, KT, x[None], 30, 5, 3, 0.0005, seed=1)
+        x0 = np.repeat(x0, 5, axis=0)
+        seen = []
+        for extra, big_dt in ((0, 4.0 * dt), (0, 2.5 * dt), (3, 3.0 * dt), (15, dt)):
+            xg, vg, ag = ib.engine.sample_equilibrium_particles(system, x0, KT, 8, 6, extra, big_dt, seed=9, replica0=40,
+                                                                precision="double", want_velocities=True)
+            xo, vo, ao = orc.particles_hmc(desc, KT, x0, 8, 6, extra, big_dt, seed=9, replica0=40)
+            np.testing.assert_allclose(ag.cpu().numpy(), ao, atol=1e-12)
+            np.testing.assert_allclose(xg.cpu().numpy(), xo, rtol=1e-7, atol=2e-9)
+            seen.append(ao[:, 0])
+        assert 0.0 < np.concatenate(seen).mean() < 1.0  # the large steps make the test see both branches
+    # exact target: independent particles in the harmonic restraint -> Gaussian with variance kT / K per coordinate
+    desc = dict(n_atoms=32, mass=np.linspace(1.0, 40.0, 32), restraint_k=50.0, groups=dict(restraint=0))
+    system = ib.engine.ParticleSystem(desc)
+    n = 4096
+    x, _, acc = ib.engine.sample_equilibrium_particles(system, np.random.RandomState(0).randn(n, 32, 3) * 0.3, KT, 40, 10, 2, 0.05, seed=2)
+    x = x.cpu().numpy()
+    var = KT / 50.0
+    assert acc[:, 0].mean().item() > 0.6
+    assert x.mean() == pytest.approx(0.0, abs=5 * np.sqrt(var / x.size))
+    assert x.var() == pytest.approx(var, rel=5 * np.sqrt(2.0 / x.size) * 3)
+    # per-atom variances do not depend on the mass
+    pv = x.reshape(n, 32, 3).var(axis=(0, 2))
+    assert np.abs(pv / var - 1.0).max() < 0.08
