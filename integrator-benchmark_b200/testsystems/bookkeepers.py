@@ -51,6 +51,8 @@ class EquilibriumSimulator:
         self._engine_system = None
         # sampler settings (see collect_equilibrium_samples)
         self.extra_chances = 15
+        self.equilibration_collision_rate = 5.0  # 1/ps, Langevin mixing stage
+        self.metropolis_rounds = 2000            # final extra-chance HMC rounds (x steps_per_hmc steps)
         self.sampler_precision = "double"
         self.acceptance = None
         self.max_equilibration_steps = 1000000  # 1 ns at 1 fs, the length of the reference's burn-in
@@ -69,13 +71,17 @@ class EquilibriumSimulator:
 
     # ---- equilibrium cache
     def collect_equilibrium_samples(self, seed=None):
-        """x ~ pi for the cache (reference :66-113: XC-GHMC with steps_per_hmc = 10, 15 extra chances, no collision
-        rate, i.e. extra-chance HMC; `burn_in_length` rounds, then one sample every `thinning_interval` rounds of ONE
-        chain).  Here `n_samples` INDEPENDENT chains start from `positions`: a short small-step, high-friction Langevin
-        relaxation (the reference minimises the energy instead), then min(burn_in_length, max_equilibration_steps /
-        steps_per_hmc) rounds of the same extra-chance HMC on the GPU (lsi_sample_equilibrium_particles, fp64); the
-        final configurations are the cache -- exact samples of exp(-U/kT) on the constraint manifold, no time-step
-        bias.  Returns (n_samples, n_atoms, 3) in nm; acceptance statistics in `self.acceptance`."""
+        """x ~ pi for the cache (reference :66-113: ONE chain of XC-GHMC with steps_per_hmc = 10, 15 extra chances
+        and no collision rate, i.e. extra-chance HMC; `burn_in_length` rounds of burn-in, then a sample every
+        `thinning_interval` rounds).  Here `n_samples` INDEPENDENT chains start from `positions`:
+          1. a short small-step, high-friction Langevin relaxation (the reference minimises the energy instead);
+          2. VRORV Langevin dynamics at `timestep`, low friction, for min(burn_in_length * steps_per_hmc,
+             max_equilibration_steps) steps -- the mixing stage (an HMC chain that redraws every velocity each
+             10 fs diffuses far too slowly to equilibrate 1000 chains from a common start);
+          3. `metropolis_rounds` rounds of the reference's extra-chance HMC (lsi_sample_equilibrium_particles, fp64),
+             which removes the O(dt^2) bias of stage 2: the cache is distributed as exp(-U/kT) on the constraint
+             manifold.
+        Returns (n_samples, n_atoms, 3) in nm; HMC acceptance statistics in `self.acceptance`."""
         engine.require_cuda()
         t = engine.torch()
         system = self.engine_system()
@@ -83,12 +89,15 @@ class EquilibriumSimulator:
         seed = _rngstate.get_seed() if seed is None else int(seed)
         dt = self.timestep.value_in_unit(unit.picosecond) if unit.is_quantity(self.timestep) else float(self.timestep)
         x = t.as_tensor(np.ascontiguousarray(self.positions))[None].expand(n, -1, -1).contiguous().cuda()
-        for k, (h, gamma, n_steps) in enumerate([(0.1 * dt, 100.0, 500), (0.5 * dt, 20.0, 500)]):
+        burn = int(min(self.burn_in_length * self.steps_per_hmc, self.max_equilibration_steps))
+        for k, (h, gamma, n_steps) in enumerate([(0.1 * dt, 100.0, 500), (0.5 * dt, 20.0, 500),
+                                                 (dt, self.equilibration_collision_rate, burn)]):
             prog = engine.Program("V R O R V", h, gamma)
             res = engine.run_protocol(system, prog, n, n_steps, self.kT_value, n_legs=1, seed=seed + 7919 * (k + 1),
-                                      replica0=0, x0=x, want_final=True, want_moments=False, precision="double", out={})
+                                      replica0=0, x0=x, want_final=True, want_moments=False,
+                                      precision="double" if k < 2 else "mixed", out={})
             x = res["x_final"]
-        rounds = int(min(self.burn_in_length, self.max_equilibration_steps // self.steps_per_hmc))
+        rounds = int(min(self.metropolis_rounds, max(1, burn // self.steps_per_hmc)))
         x, _, acc = engine.sample_equilibrium_particles(system, x, self.kT_value, rounds, self.steps_per_hmc, self.extra_chances, dt,
                                                         seed=seed, replica0=0, precision=self.sampler_precision)
         self.acceptance = acc.mean(dim=0).cpu().numpy()  # (rounds accepted, accepted at the first chance)
