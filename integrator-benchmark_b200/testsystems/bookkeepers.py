@@ -233,7 +233,7 @@ class NonequilibriumSimulator:
         rid = _rngstate.reserve_replicas(n)
         res = engine.run_protocol(eq.engine_system(), self.integrator.program, n, int(n_steps), self._kT(), n_legs=1,
                                   seed=_rngstate.get_seed() if seed is None else int(seed), replica0=rid,
-                                  x0=np.ascontiguousarray(x0), v0=None if v0 is None else np.ascontiguousarray(v0),
+                                  x0=np.array(x0, dtype=np.float64, order="C"), v0=None if v0 is None else np.array(v0, dtype=np.float64, order="C"),
                                   precision=self.precision, want_heat=True, want_final=want_final, want_moments=False, out={})
         self.integrator._accumulate(heat=res["heat"].nan_to_num(0.0).sum().item())
         W = res["W"][0].cpu().numpy()
