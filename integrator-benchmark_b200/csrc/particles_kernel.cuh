@@ -33,6 +33,14 @@
 #include "particles_shared.h"
 #include "rng.cuh"
 
+// resident CTAs per SM the register allocation is capped for: warp teams (128 threads) / CTA teams (<= 384 threads)
+#ifndef LSI_PK_WT_MINB
+#define LSI_PK_WT_MINB 4
+#endif
+#ifndef LSI_PK_CTA_MINB
+#define LSI_PK_CTA_MINB 2
+#endif
+
 namespace pk {
 
 template <typename real> struct Vec;
@@ -1198,7 +1206,7 @@ __device__ __noinline__ void draw_velocities(uint32_t ctx_off, uint64_t rid, uin
 #define PK_FOR_UNITS(u) for (int u = tid; u < P.n_units; u += T)
 
 template <typename real, bool PERIODIC, bool WT, int APL>
-__global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol_kernel(const __grid_constant__ PKParams P, int teams)
+__global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_CTA_MINB) particles_protocol_kernel(const __grid_constant__ PKParams P, int teams)
 {
     const int N = P.N, D = 3 * N;
     const int T = WT ? 32 : (int)blockDim.x;
@@ -1335,7 +1343,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_protocol
 // accepted, otherwise the configuration is restored.  Targets exp(-U/kT) on the constraint manifold exactly.
 // Streams: velocities Philox(replica, draw = 2 round, TAG_EQ, unit = atom); u = Philox(replica, 2 round + 1, TAG_EQ, 0).x
 template <typename real, bool PERIODIC, bool WT, int APL>
-__global__ void __launch_bounds__(WT ? 128 : 384, WT ? 5 : 2) particles_hmc_kernel(const __grid_constant__ PKParams P, int teams)
+__global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_CTA_MINB) particles_hmc_kernel(const __grid_constant__ PKParams P, int teams)
 {
     const int N = P.N, D = 3 * N;
     const int T = WT ? 32 : (int)blockDim.x;
