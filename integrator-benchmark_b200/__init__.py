@@ -6,6 +6,6 @@ include/lsi.h); importing the package loads that library and fails if it is miss
 """
 from . import _cabi, constants, engine, unit  # noqa: F401
 from ._rngstate import get_seed, set_seed  # noqa: F401
-from . import evaluation, integrators, testsystems, parallel  # noqa: F401,E402
+from . import evaluation, integrators, testsystems, parallel, utilities, experiments  # noqa: F401,E402
 
 __version__ = "0.1.0"
