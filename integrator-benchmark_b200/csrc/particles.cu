@@ -187,11 +187,15 @@ int configure(const lsi_particles* p, bool mixed, int n_slots, bool generic_smem
     L.n = n;
     L.warp_team = N <= 64 && env_int("LSI_PK_WARP_TEAM", 1) != 0;
     const size_t per_team = lsi_pk_smem_per_team(mixed, N, n_slots, p->n_tf, generic_smem, L.warp_team, hmc);
+    L.team_lanes = 32;
     if (L.warp_team) {
-        L.apl = N <= 32 ? 1 : 2;
-        L.teams = std::max(1, std::min(4, env_int("LSI_PK_TEAMS", 4)));
-        while (L.teams > 1 && per_team * L.teams > 200 * 1024) --L.teams;
-        L.threads = 32 * L.teams;
+        // up to 32 atoms: two replicas per warp (half-warp teams, 2 atoms per lane) keep more lanes busy
+        if (N <= 32 && env_int("LSI_PK_HALF_WARP", 1) != 0) L.team_lanes = 16;
+        L.apl = N <= L.team_lanes ? 1 : 2;
+        const int warps = std::max(1, std::min(4, env_int("LSI_PK_TEAMS", 4)));
+        L.teams = warps * (32 / L.team_lanes);
+        while (L.teams > 32 / L.team_lanes && per_team * L.teams > 200 * 1024) L.teams -= 32 / L.team_lanes;
+        L.threads = L.team_lanes * L.teams;
         L.smem = per_team * L.teams;
     } else {
         int apl = env_int("LSI_PK_APL", 2);
@@ -555,6 +559,7 @@ int lsi_particles_run_protocol(const lsi_system* sys, const lsi_program* prog, c
     P.W = a->W; P.heat = a->heat; P.W_direct = a->W_direct; P.x_final = a->x_final; P.v_final = a->v_final;
     P.trace_x = a->trace_x; P.trace_v = a->trace_v; P.trace_w = a->trace_w;
 
+    P.team_lanes = L.team_lanes;
     rc = mixed ? lsi_pk_launch_protocol_f32(P, L, stream) : lsi_pk_launch_protocol_f64(P, L, stream);
     cudaFreeAsync(dprog, st);
     return rc;
@@ -581,6 +586,7 @@ LSI_EXPORT int lsi_particles_energy_forces(const lsi_system* sys, int32_t precis
     PKLaunch L;
     rc = configure(p, mixed, 1, false, n, false, L);
     if (rc != LSI_OK) return rc;
+    P.team_lanes = L.team_lanes;
     return mixed ? lsi_pk_launch_energy_f32(P, L, stream) : lsi_pk_launch_energy_f64(P, L, stream);
 }
 
@@ -612,5 +618,6 @@ LSI_EXPORT int lsi_sample_equilibrium_particles(const lsi_system* sys, int32_t p
     PKLaunch L;
     rc = configure(p, mixed, 2, p->n_generic > 0, n, false, L, true);
     if (rc != LSI_OK) return rc;
+    P.team_lanes = L.team_lanes;
     return mixed ? lsi_pk_launch_hmc_f32(P, L, stream) : lsi_pk_launch_hmc_f64(P, L, stream);
 }

@@ -119,10 +119,18 @@ __device__ __forceinline__ Smem<real> carve(unsigned char* base, const Layout& L
     return s;
 }
 
+// lanes of this thread's team within its warp: all 32, or one half when two 16-lane teams share the warp
+// (their control flow may differ -- e.g. accept / reject in the HMC sampler -- so warp primitives name only the team)
 template <bool WT>
-__device__ __forceinline__ void team_sync()
+__device__ __forceinline__ unsigned team_mask(int T)
 {
-    if (WT) __syncwarp();
+    return (WT && T == 16) ? (0xffffu << (threadIdx.x & 16)) : 0xffffffffu;
+}
+
+template <bool WT>
+__device__ __forceinline__ void team_sync(int T)
+{
+    if (WT) __syncwarp(team_mask<WT>(T));
     else __syncthreads();
 }
 
@@ -130,9 +138,13 @@ __device__ __forceinline__ void team_sync()
 template <bool WT>
 __device__ __forceinline__ double team_sum(double val, double* red, int tid, int T)
 {
+    if (WT) {  // sub-warp team: T = 16 or 32 lanes
+        const unsigned mask = team_mask<WT>(T);
+        for (int o = T >> 1; o > 0; o >>= 1) val += __shfl_xor_sync(mask, val, o);
+        return val;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-    if (WT) return val;
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = val;
     __syncthreads();
@@ -233,7 +245,7 @@ struct PairBody {
 };
 
 template <typename real, bool PERIODIC, int APL, bool ENERGY>
-__device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typename Vec<real>::r4* __restrict__ xq, int slot0, int T,
+__device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typename Vec<real>::r4* __restrict__ xq, int slot0, int T, unsigned mask,
                                             const int (&atom)[APL], real (&fx)[APL], real (&fy)[APL], real (&fz)[APL],
                                             double (&en)[APL])
 {
@@ -249,7 +261,7 @@ __device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typena
         qi[a] = atom[a] >= 0 ? p.w : (real)0;
         hsi[a] = l.x;
         sei[a] = atom[a] >= 0 ? l.y : (real)0;
-        wlj[a] = __any_sync(0xffffffffu, sei[a] != (real)0);  // warp-uniform
+        wlj[a] = __any_sync(mask, sei[a] != (real)0);  // uniform over the team's lanes (a whole warp unless T = 16)
     }
     PairBody<real, PERIODIC, ENERGY> B;
     B.bx = C.boxr[0]; B.by = C.boxr[1]; B.bz = C.boxr[2];
@@ -445,13 +457,13 @@ __device__ __noinline__ double compute_forces(uint32_t ctx_off, int g, int out_s
         fx[a] = fy[a] = fz[a] = (real)0;
         en[a] = 0.0;
     }
-    team_sync<WT>();
-    if (do_nb) pair_forces<real, PERIODIC, APL, ENERGY>(C, s.xq, tid, T, atom, fx, fy, fz, en);
+    team_sync<WT>(T);
+    if (do_nb) pair_forces<real, PERIODIC, APL, ENERGY>(C, s.xq, tid, T, team_mask<WT>(T), atom, fx, fy, fz, en);
     double e_thread = 0.0;
     if (set >= 0) {
         const real et = eval_terms<real, PERIODIC, ENERGY>(C, s.xq, s.tf, C.set_lo[set], C.set_hi[set], tid, T);
         if (ENERGY) e_thread += (double)et;
-        team_sync<WT>();
+        team_sync<WT>(T);
     }
 #pragma unroll
     for (int a = 0; a < APL; ++a) {
@@ -475,7 +487,7 @@ __device__ __noinline__ double compute_forces(uint32_t ctx_off, int g, int out_s
         fout[3 * i] = fx[a]; fout[3 * i + 1] = fy[a]; fout[3 * i + 2] = fz[a];
         if (ENERGY) e_thread += 0.5 * en[a] + (double)er;  // every pair is visited from both ends
     }
-    team_sync<WT>();
+    team_sync<WT>(T);
     if (ENERGY) return team_sum<WT>(e_thread, s.red, tid, T);
     return 0.0;
 }
@@ -1209,11 +1221,15 @@ template <typename real, bool PERIODIC, bool WT, int APL>
 __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_CTA_MINB) particles_protocol_kernel(const __grid_constant__ PKParams P, int teams)
 {
     const int N = P.N, D = 3 * N;
-    const int T = WT ? 32 : (int)blockDim.x;
-    const int tid = WT ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-    const int team = WT ? (int)(threadIdx.x >> 5) : 0;
-    const int64_t r = WT ? (int64_t)blockIdx.x * teams + team : (int64_t)blockIdx.x;
-    if (r >= P.n) return;  // whole team (warp-team mode never uses CTA barriers)
+    // warp-team mode: teams of P.team_lanes = 32 or 16 lanes (two small replicas share a warp and run in lockstep)
+    const int T = WT ? P.team_lanes : (int)blockDim.x;
+    const int tid = WT ? (int)(threadIdx.x & (T - 1)) : (int)threadIdx.x;
+    const int team = WT ? (int)(threadIdx.x / T) : 0;
+    int64_t r = WT ? (int64_t)blockIdx.x * teams + team : (int64_t)blockIdx.x;
+    if (r >= P.n) {
+        if (!WT || (T == 32)) return;  // a whole warp (warp-team mode never uses CTA barriers)
+        r = P.n - 1;                   // half-warp team without a replica: shadow the last one (same values written twice)
+    }
     const bool DIAG = P.diag != 0;
     const Layout L = layout<real>(N, P.n_slots, P.n_tf, P.n_generic > 0, WT);
     const uint32_t team_off = (uint32_t)team * L.total;
@@ -1231,10 +1247,10 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
         if (P.v0)
             for (int k = tid; k < D; k += T) s.v[k] = P.v0[r * D + k];
     }
-    team_sync<WT>();
+    team_sync<WT>(T);
     if (!P.v0) {
         draw_velocities<real>(ctx, rid, 0u, LSI_TAG_V0, P.mass, P.kT, tid, T);
-        team_sync<WT>();
+        team_sync<WT>(T);
     }
 
     const int scratch = P.n_slots - 1;  // DIAG: an extra slot that is never a cache
@@ -1245,7 +1261,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
                 for (int k = tid; k < D; k += T) s.x[k] = (double)(float)s.x[k];
             if (P.marginal == LSI_MARGINAL_CONFIGURATION)
                 draw_velocities<real>(ctx, rid, (uint32_t)(leg - 1), LSI_TAG_VMID, P.mass, P.kT, tid, T);
-            team_sync<WT>();
+            team_sync<WT>(T);
         }
         double ke0 = 0.0;
         PK_FOR_UNITS(u) ke0 += unit_R<real>(ctx, u, 0.0);  // h = 0: project onto the constraints, stage
@@ -1262,7 +1278,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
             if (P.trace_x) for (int k = tid; k < D; k += T) P.trace_x[base * D + k] = s.x[k];
             if (P.trace_v) for (int k = tid; k < D; k += T) P.trace_v[base * D + k] = s.v[k];
             if (P.trace_w && tid == 0) P.trace_w[base] = 0.0;
-            team_sync<WT>();
+            team_sync<WT>(T);
         }
 
         for (int st = 0; st < P.n_steps; ++st) {
@@ -1298,7 +1314,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
                 }
             }
             if (DIAG) {
-                team_sync<WT>();
+                team_sync<WT>(T);
                 const int64_t idx = ((int64_t)leg * TT + st + 1) * P.n + r;
                 if (P.trace_x) for (int k = tid; k < D; k += T) P.trace_x[idx * D + k] = s.x[k];
                 if (P.trace_v) for (int k = tid; k < D; k += T) P.trace_v[idx * D + k] = s.v[k];
@@ -1309,7 +1325,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
                     const double tot = team_sum<WT>(ke - (heat_run - heat0), s.red, tid, T);
                     if (tid == 0) P.trace_w[idx] = ((pe_cur + tot) - E0) * P.inv_kT;
                 }
-                team_sync<WT>();  // trace reads of x, v finish before the owners move on
+                team_sync<WT>(T);  // trace reads of x, v finish before the owners move on
             }
         }
         // ---- end of leg: W = ((E1 - E0) - (heat1 - heat0)) / kT
@@ -1328,7 +1344,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
                 if (DIAG && P.W_direct) P.W_direct[(int64_t)leg * P.n + r] = wd_tot * P.inv_kT;
             }
         }
-        team_sync<WT>();
+        team_sync<WT>(T);
     }
     if (P.x_final) for (int k = tid; k < D; k += T) P.x_final[r * D + k] = s.x[k];
     if (P.v_final) for (int k = tid; k < D; k += T) P.v_final[r * D + k] = s.v[k];
@@ -1346,11 +1362,15 @@ template <typename real, bool PERIODIC, bool WT, int APL>
 __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_CTA_MINB) particles_hmc_kernel(const __grid_constant__ PKParams P, int teams)
 {
     const int N = P.N, D = 3 * N;
-    const int T = WT ? 32 : (int)blockDim.x;
-    const int tid = WT ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-    const int team = WT ? (int)(threadIdx.x >> 5) : 0;
-    const int64_t r = WT ? (int64_t)blockIdx.x * teams + team : (int64_t)blockIdx.x;
-    if (r >= P.n) return;
+    // warp-team mode: teams of P.team_lanes = 32 or 16 lanes (two small replicas share a warp and run in lockstep)
+    const int T = WT ? P.team_lanes : (int)blockDim.x;
+    const int tid = WT ? (int)(threadIdx.x & (T - 1)) : (int)threadIdx.x;
+    const int team = WT ? (int)(threadIdx.x / T) : 0;
+    int64_t r = WT ? (int64_t)blockIdx.x * teams + team : (int64_t)blockIdx.x;
+    if (r >= P.n) {
+        if (!WT || (T == 32)) return;
+        r = P.n - 1;  // half-warp team without a replica: shadow the last one
+    }
     const Layout L = layout<real>(N, 2, P.n_tf, P.n_generic > 0, WT, true);
     const uint32_t team_off = (uint32_t)team * L.total;
     const Smem<real> s = carve<real>(pk_smem + team_off, L);
@@ -1361,18 +1381,18 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
     const uint64_t rid = P.replica0 + (uint64_t)r;
     load_tables<real>(P, s, tid, T);
     for (int k = tid; k < D; k += T) { s.x[k] = P.x0[r * D + k]; s.v[k] = 0.0; }
-    team_sync<WT>();
+    team_sync<WT>(T);
     PK_FOR_UNITS(u) unit_R<real>(ctx, u, 0.0);  // project the start configuration, stage it
     double pe = compute_forces<real, PERIODIC, WT, APL, true>(ctx, -1, 0, tid, T);
     const double h = P.hmc_dt;
     int n_acc = 0, n_first = 0;
     for (int round = 0; round < P.hmc_rounds; ++round) {
         draw_velocities<real>(ctx, rid, 2u * (uint32_t)round, LSI_TAG_EQ, P.mass, P.kT, tid, T);
-        team_sync<WT>();
+        team_sync<WT>(T);
         double ke = 0.0;
         PK_FOR_UNITS(u) ke += unit_R<real>(ctx, u, 0.0);  // velocity constraints (positions already satisfy theirs)
         const double e_old = pe + team_sum<WT>(ke, s.red, tid, T);
-        team_sync<WT>();
+        team_sync<WT>(T);
         for (int k = tid; k < D; k += T) { xold[k] = s.x[k]; vold[k] = s.v[k]; s.f[D + k] = s.f[k]; }
         const lsi::Philox4 ur = lsi::philox_block(P.seed, rid, 2u * (uint32_t)round + 1u, LSI_TAG_EQ, 0u);
         const double uni = ((double)ur.x + 0.5) * 2.3283064365386962890625e-10;
@@ -1393,18 +1413,18 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
             mu1 = fmax(mu1, fmin(1.0, exp(-(e_new - e_old) * P.inv_kT)));
             if (c == 0 && uni <= mu1) ++n_first;
         }
-        team_sync<WT>();
+        team_sync<WT>(T);
         if (uni > mu1) {  // every chance failed: back to the start of the round
             for (int k = tid; k < D; k += T) { s.x[k] = xold[k]; s.v[k] = vold[k]; s.f[k] = s.f[D + k]; }
-            team_sync<WT>();
+            team_sync<WT>(T);
             PK_FOR_UNITS(u) unit_R<real>(ctx, u, 0.0);  // re-stage the restored positions
-            team_sync<WT>();
+            team_sync<WT>(T);
         } else {
             pe = pe_new;
             ++n_acc;
         }
     }
-    team_sync<WT>();
+    team_sync<WT>(T);
     if (P.x_final) for (int k = tid; k < D; k += T) P.x_final[r * D + k] = s.x[k];
     if (P.v_final) for (int k = tid; k < D; k += T) P.v_final[r * D + k] = s.v[k];
     if (P.hmc_accept && tid == 0) {
@@ -1418,11 +1438,15 @@ template <typename real, bool PERIODIC, bool WT, int APL>
 __global__ void __launch_bounds__(WT ? 128 : 384) particles_energy_kernel(const __grid_constant__ PKParams P, int teams)
 {
     const int N = P.N, D = 3 * N;
-    const int T = WT ? 32 : (int)blockDim.x;
-    const int tid = WT ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-    const int team = WT ? (int)(threadIdx.x >> 5) : 0;
-    const int64_t r = WT ? (int64_t)blockIdx.x * teams + team : (int64_t)blockIdx.x;
-    if (r >= P.n) return;
+    // warp-team mode: teams of P.team_lanes = 32 or 16 lanes (two small replicas share a warp and run in lockstep)
+    const int T = WT ? P.team_lanes : (int)blockDim.x;
+    const int tid = WT ? (int)(threadIdx.x & (T - 1)) : (int)threadIdx.x;
+    const int team = WT ? (int)(threadIdx.x / T) : 0;
+    int64_t r = WT ? (int64_t)blockIdx.x * teams + team : (int64_t)blockIdx.x;
+    if (r >= P.n) {
+        if (!WT || (T == 32)) return;
+        r = P.n - 1;  // half-warp team without a replica: shadow the last one
+    }
     const Layout L = layout<real>(N, 1, P.n_tf, false, WT);
     const uint32_t team_off = (uint32_t)team * L.total;
     const Smem<real> s = carve<real>(pk_smem + team_off, L);
@@ -1430,7 +1454,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384) particles_energy_kernel(const 
     if (tid == 0) fill_ctx<real>(sm<TeamCtx<real>>(ctx), P, L, team_off);
     load_tables<real>(P, s, tid, T);
     for (int k = tid; k < D; k += T) s.x[k] = P.q_x[r * D + k];
-    team_sync<WT>();
+    team_sync<WT>(T);
     {
         const UnitOps<real> ops{*sm<TeamCtx<real>>(ctx), s};
         for (int i = tid; i < N; i += T) ops.stage_atom(i, s.x[3 * i], s.x[3 * i + 1], s.x[3 * i + 2]);

@@ -69,6 +69,7 @@ struct PKParams {
     uint64_t seed, replica0;
     int64_t n;
     int n_steps, n_legs, marginal, flags, diag;
+    int team_lanes;           // warp-team mode: lanes per replica (32, or 16 when n_atoms <= 32)
     double kT, inv_kT;
     const double* x_cache;
     int64_t n_cache;
@@ -91,6 +92,7 @@ struct PKLaunch {
     int apl;          // atoms per lane in the force loop: 1 or 2
     int threads;      // CTA size
     int teams;        // replicas per CTA (warp-team mode), else 1
+    int team_lanes;   // lanes per replica in warp-team mode
     size_t smem;      // dynamic shared memory per CTA
     int64_t n;        // replicas (protocol) or configurations (energy query)
 };
