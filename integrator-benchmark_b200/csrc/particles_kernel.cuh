@@ -29,6 +29,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "lsi_internal.h"
 #include "particles_shared.h"
 #include "rng.cuh"
@@ -1469,6 +1471,9 @@ template <typename K>
 int set_smem(K kernel, size_t bytes)
 {
     if (bytes > 48 * 1024) LSI_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // tuning knob: preferred shared-memory carve-out in percent (measured: the driver's default choice is the fastest)
+    if (const char* c = getenv("LSI_PK_CARVEOUT"))
+        if (*c) LSI_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c)));
     return LSI_OK;
 }
 
