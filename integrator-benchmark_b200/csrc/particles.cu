@@ -162,7 +162,7 @@ void fill_system_params(const lsi_particles* p, const DevTables* t, bool mixed, 
     P.nbp = mixed ? t->nbp_f : t->nbp_d;
     P.excl = t->excl;
     P.n_lj = p->n_lj; P.iperm = t->iperm;
-    P.perm = t->perm; P.n_perm = p->n_atoms;
+    P.perm = t->perm;
     P.units = t->units;
     P.gc_off = t->gc_off; P.gc_pairs = t->gc_pairs; P.gc_dist = t->gc_dist;
     P.gc_atom_off = t->gc_atom_off; P.gc_atoms = t->gc_atoms;

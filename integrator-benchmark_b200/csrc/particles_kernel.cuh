@@ -7,15 +7,17 @@
 //   systems                                        benchmark/testsystems/{watercluster,waterbox,alanine_dipeptide}.py
 // OpenMM supplies forces, SETTLE/CCMA and the `gaussian` stream there.  Here:
 //
-//   * a replica belongs to a TEAM: one warp when N <= 64 (several replicas per CTA, only
-//     __syncwarp between phases), otherwise one CTA.  Its state (x, v fp64) stays in shared memory
-//     for the whole protocol (forward leg, midpoint, reverse leg).
-//   * FORCE phases are atom-mapped: a lane owns APL atoms (LJ-active atoms packed into the first
-//     lanes) and runs a full-shell loop over all partners, whose positions {x, y, z, q sqrt(K)} are
-//     shared-memory broadcasts (one LDS.128 feeds APL pair evaluations).  Forces accumulate in
-//     registers: no atomics, no cross-thread reduction, bit-reproducible.  The Lennard-Jones part
-//     is behind a warp-uniform branch on the partner (skipped for TIP3P hydrogens); exclusions are
-//     per-atom bitmasks; minimum image by magic-number rounding (full-rate FP32).
+//   * a replica belongs to a TEAM: half a warp when N <= 32 (two replicas in lockstep per warp), one warp
+//     when N <= 64 (several replicas per CTA, only __syncwarp over the team's lanes between phases),
+//     otherwise one CTA.  Its state (x, v fp64) stays in shared memory for the whole protocol (forward
+//     leg, midpoint, reverse leg).
+//   * FORCE phases are atom-mapped: a lane owns APL atoms and runs a full-shell loop over all partners,
+//     whose records {x, y, z, q sqrt(K)}, {sigma/2, 2 sqrt(eps)} are shared-memory broadcasts staged in
+//     SLOT order (Lennard-Jones-active atoms first; one LDS.128 feeds APL pair evaluations).  Forces
+//     accumulate in registers: no atomics, no cross-thread reduction, bit-reproducible.  The first n_lj
+//     partners get the Coulomb + LJ body (only in warps that own LJ-active atoms), the rest (TIP3P
+//     hydrogens) a Coulomb-only body with the lane's charge factored out; exclusions are per-slot
+//     bitmasks; minimum image by magic-number rounding (full-rate FP32).
 //   * bonded terms and 1-4 exceptions: one lane per TERM computes all role gradients once into a
 //     shared buffer; every atom then gathers its entries in a fixed order (deterministic).
 //     Periodic torsions use cos/sin of the dihedral and the multiple-angle recurrence (no atan2).
@@ -24,6 +26,9 @@
 //     SETTLE / a Newton solve of the star (positions) and an exact 3x3 solve (velocities), and
 //     stages the new positions for the next force phase.  Consecutive unit-mapped substeps need no
 //     synchronisation; heat and shadow work are accumulated per lane and reduced once per leg.
+//   * every phase is a non-inlined function that receives shared-memory OFFSETS (loads stay LDS) and
+//     reads its constants from a per-team context in shared memory: small kernels (instruction cache),
+//     separate register allocation for the fp64 constraint algebra.
 //   * per-force-group force caches with validity bits: a group is re-evaluated only after R.
 //   * O noise: Philox-4x32-10 keyed by (replica, leg, draw, atom).
 #pragma once
@@ -46,8 +51,8 @@
 namespace pk {
 
 template <typename real> struct Vec;
-template <> struct Vec<float> { using r4 = float4; using r2 = float2; };
-template <> struct Vec<double> { using r4 = double4; using r2 = double2; };
+template <> struct Vec<float> { using r4 = float4; };
+template <> struct Vec<double> { using r4 = double4; };
 
 // MUFU.RSQ without the denormal pre/post-scaling of rsqrtf (squared distances are never denormal; 2 ulp)
 static __device__ __forceinline__ float rsqrt_(float x)

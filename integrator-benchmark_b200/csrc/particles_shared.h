@@ -45,7 +45,6 @@ struct PKParams {
     int n_lj;                 // slots [0, n_lj) hold the Lennard-Jones-active atoms
     const int32_t* iperm;     // [N] atom -> slot
     const int32_t* perm;      // [N] slot -> atom (LJ-active atoms first)
-    int n_perm;
     const PKUnit* units;      // [n_units], constrained units first
     const int32_t* gc_off;    // generic clusters: constraints [gc_off[c], gc_off[c+1])
     const int32_t* gc_pairs;  // [n][2]
