@@ -234,3 +234,17 @@ def test_waterbox_fixture_geometry(golden_dir):
     hh = np.linalg.norm(xyz[:, 1::3] - xyz[:, 2::3], axis=-1)
     assert np.abs(oh1 - 0.09572).max() < 2e-6 and np.abs(hh - 0.15139).max() < 2e-6
     np.testing.assert_allclose(z["potential_energy"], [-4136.6406, -4029.0005, -4030.8572, -4068.7595], atol=1e-3)
+
+
+def test_waterbox_fixture_energies_track_the_stored_pme_energies(golden_dir):
+    """oracle energies (cutoff 0.6 nm + reaction field, no LJ tail) of the reference's four stored frames against the
+    PME + dispersion-correction energies stored with them: 95.6-96.2 %, same order."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from integrator_benchmark_b200.testsystems import systems as ts
+    z = np.load(os.path.join(golden_dir, "waterbox_frames.npz"))
+    desc, _ = ts.tiny_waterbox()
+    e = np.array([orc.particles_energy_forces(desc, z["xyz"][k].astype(np.float64))[0] for k in range(4)])
+    ratio = e / z["potential_energy"]
+    assert np.all(ratio > 0.95) and np.all(ratio < 0.97), ratio
+    assert np.argsort(e).tolist() == np.argsort(z["potential_energy"]).tolist()
