@@ -17,7 +17,9 @@
  *     thread-local message for the last failure on the calling thread
  *   - handles are opaque, owned by the caller, freed with the matching
  *     *_destroy; one handle must not be used from two threads at once
- *   - no call synchronises the stream or the device unless stated
+ *   - no call synchronises the stream or the device unless stated (lsi_run_protocol synchronises the stream once
+ *     when the program has more than 96 substeps (particle systems) / 160 (scalar systems): long multi-timestep
+ *     strings are staged in device memory)
  *   - there is NO CPU fallback: compute calls fail with LSI_ERR_CUDA when no
  *     device is usable
  *   - units are OpenMM's: nm, ps, amu, kJ/mol, K, e   (toy systems: reduced units)

@@ -539,18 +539,24 @@ int lsi_particles_run_protocol(const lsi_system* sys, const lsi_program* prog, c
     if (rc != LSI_OK) return rc;
 
     unsigned char* dprog = nullptr;
-    const size_t nb = (size_t)n_ops * (2 * sizeof(double)) + 2 * (size_t)n_ops;
-    LSI_CUDA_CHECK(cudaMallocAsync((void**)&dprog, nb, st));
-    double* d0 = (double*)dprog;
-    double* d1 = d0 + n_ops;
-    unsigned char* dk = (unsigned char*)(d1 + n_ops);
-    unsigned char* ds = dk + n_ops;
-    LSI_CUDA_CHECK(cudaMemcpyAsync(d0, c0.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
-    LSI_CUDA_CHECK(cudaMemcpyAsync(d1, c1.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
-    LSI_CUDA_CHECK(cudaMemcpyAsync(dk, kinds.data(), n_ops, cudaMemcpyHostToDevice, st));
-    LSI_CUDA_CHECK(cudaMemcpyAsync(ds, slots.data(), n_ops, cudaMemcpyHostToDevice, st));
-    LSI_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors die at return
-    P.op_c0 = d0; P.op_c1 = d1; P.op_kind = dk; P.op_slot = ds;
+    if (n_ops <= kMaxInlineOps) {
+        for (int i = 0; i < n_ops; ++i) { P.op_kind[i] = kinds[i]; P.op_slot[i] = slots[i]; P.op_c0[i] = c0[i]; P.op_c1[i] = c1[i]; }
+    } else {
+        // long multi-timestep strings: stage the program in device memory (stream-ordered; the one host
+        // synchronisation of this call, because the host vectors die at return)
+        const size_t nb = (size_t)n_ops * (2 * sizeof(double)) + 2 * (size_t)n_ops;
+        LSI_CUDA_CHECK(cudaMallocAsync((void**)&dprog, nb, st));
+        double* d0 = (double*)dprog;
+        double* d1 = d0 + n_ops;
+        unsigned char* dk = (unsigned char*)(d1 + n_ops);
+        unsigned char* ds = dk + n_ops;
+        LSI_CUDA_CHECK(cudaMemcpyAsync(d0, c0.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
+        LSI_CUDA_CHECK(cudaMemcpyAsync(d1, c1.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
+        LSI_CUDA_CHECK(cudaMemcpyAsync(dk, kinds.data(), n_ops, cudaMemcpyHostToDevice, st));
+        LSI_CUDA_CHECK(cudaMemcpyAsync(ds, slots.data(), n_ops, cudaMemcpyHostToDevice, st));
+        LSI_CUDA_CHECK(cudaStreamSynchronize(st));
+        P.ext_c0 = d0; P.ext_c1 = d1; P.ext_kind = dk; P.ext_slot = ds;
+    }
 
     P.seed = a->seed; P.replica0 = a->replica0; P.n = a->n_replicas;
     P.n_steps = a->n_steps; P.n_legs = a->n_legs; P.marginal = a->marginal; P.flags = a->flags;
@@ -561,7 +567,7 @@ int lsi_particles_run_protocol(const lsi_system* sys, const lsi_program* prog, c
 
     P.team_lanes = L.team_lanes;
     rc = mixed ? lsi_pk_launch_protocol_f32(P, L, stream) : lsi_pk_launch_protocol_f64(P, L, stream);
-    cudaFreeAsync(dprog, st);
+    if (dprog) cudaFreeAsync(dprog, st);
     return rc;
 }
 

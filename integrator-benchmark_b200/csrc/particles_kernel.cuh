@@ -1290,8 +1290,8 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
 
         for (int st = 0; st < P.n_steps; ++st) {
             for (int op = 0; op < P.n_ops; ++op) {
-                const int kind = P.op_kind[op];
-                const double c0 = P.op_c0[op];
+                const int kind = P.ext_kind ? P.ext_kind[op] : P.op_kind[op];
+                const double c0 = P.ext_c0 ? P.ext_c0[op] : P.op_c0[op];
                 if (kind == LSI_OP_R) {
                     double dke = 0.0;
                     PK_FOR_UNITS(u) dke += unit_R<real>(ctx, u, c0);
@@ -1303,7 +1303,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
                         pe_cur = pe_new;
                     }
                 } else if (kind == LSI_OP_V) {
-                    const int slot = P.op_slot[op];
+                    const int slot = P.ext_slot ? P.ext_slot[op] : P.op_slot[op];
                     if (!((valid >> slot) & 1u)) {
                         compute_forces<real, PERIODIC, WT, APL, false>(ctx, P.slot_group[slot], slot, tid, T);
                         valid |= 1u << slot;
@@ -1312,7 +1312,7 @@ __global__ void __launch_bounds__(WT ? 128 : 384, WT ? LSI_PK_WT_MINB : LSI_PK_C
                     PK_FOR_UNITS(u) dke += unit_V<real>(ctx, u, c0, slot, DIAG ? 1 : 0);
                     if (DIAG) wd_ke += dke;
                 } else {
-                    const double a = c0, b = P.op_c1[op];
+                    const double a = c0, b = P.ext_c1 ? P.ext_c1[op] : P.op_c1[op];
                     const uint32_t draw = ((uint32_t)leg << 26) | q;
                     ++q;
                     double dke = 0.0;

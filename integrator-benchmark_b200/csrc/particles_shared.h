@@ -10,6 +10,7 @@ enum { UNIT_FREE = 0, UNIT_WATER = 1, UNIT_STAR = 2, UNIT_GENERIC = 3 };
 
 constexpr int kMaxSets = 8;    // term sets: [0] = all terms, [1..] = one per distinct force group
 constexpr int kMaxSlots = 4;   // force caches (distinct V tokens of a splitting)
+constexpr int kMaxInlineOps = 96;
 
 // One bonded term or 1-4 exception, evaluated by one lane; its role gradients go to the
 // term-force buffer at slot .. slot + n_roles - 1.
@@ -60,10 +61,16 @@ struct PKParams {
     // ---- program (device arrays)
     int n_ops, n_slots;
     int slot_group[kMaxSlots];
-    const unsigned char* op_kind;
-    const unsigned char* op_slot;
-    const double* op_c0;  // R: h   V: h   O: a
-    const double* op_c1;  //               O: b
+    // programs of up to kMaxInlineOps substeps travel in the kernel parameters (constant bank, no allocation,
+    // no host synchronisation); longer multi-timestep strings are staged in device memory (ext_* != NULL)
+    unsigned char op_kind[kMaxInlineOps];
+    unsigned char op_slot[kMaxInlineOps];
+    double op_c0[kMaxInlineOps];  // R: h   V: h   O: a
+    double op_c1[kMaxInlineOps];  //               O: b
+    const unsigned char* ext_kind;
+    const unsigned char* ext_slot;
+    const double* ext_c0;
+    const double* ext_c1;
     // ---- protocol
     uint64_t seed, replica0;
     int64_t n;

@@ -176,7 +176,8 @@ def test_alanine_protocol_matches_oracle_incl_mts(ib, orc, systems, name):
     x0 = _jitter(x, 3, 0.001 if "unconstrained" in name else 0.0, 9)
     dt = 0.001 if "unconstrained" in name else 0.002
     mts = ["V0 V1 R O R V1 V0", "V1 V0 R R O R R V0 V1", generate_baoab_mts_string([([0], 1), ([1], 2)]),
-           generate_gbaoab_solvent_solute_string(K_r=2, slow_group=[0], fast_group=[1])]
+           generate_gbaoab_solvent_solute_string(K_r=2, slow_group=[0], fast_group=[1]),
+           generate_baoab_mts_string([([0], 1), ([1], 30)])]  # 152 substeps: the program travels in device memory
     for j, splitting in enumerate(EIGHT + mts):
         _compare_protocol(ib, orc, desc, x0, splitting, dt, 91.0 if j % 2 else 1.0, 10, ["configuration", "full"][j % 2],
                           seed=60 + j)
