@@ -102,6 +102,7 @@ def _load():
         "lsi_neq_free_energy": (i32, [c_double_p, dbl, c_double_p, c_double_p]),
         "lsi_reduce_logmeanexp": (i32, [vp, vp, i64, vp, vp, vp]),
         "lsi_microbench_fma": (i32, [i32, i64, i32, vp, vp]),
+        "lsi_test_fastmath": (i32, [i32, i64, vp, vp, vp, vp]),
         "lsi_bootstrap_nested": (i32, [vp, vp, i64, ctypes.c_int32, u64, vp, vp]),
     }
     for name, (res, args) in sig.items():

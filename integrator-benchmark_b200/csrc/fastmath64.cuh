@@ -1,0 +1,127 @@
+// fp64 log / sincos(pi x) / sincos(x) / sqrt for the toy kernels' Box-Muller noise and the double-well force.
+//
+// Why not the CUDA math library: its polynomial coefficients are 64-bit immediates that the compiler
+// materialises with pairs of UMOV on every evaluation -- 17 % of all instructions executed by
+// toy_fused_kernel were UMOV (profiles/README.md) -- and it carries special-case paths (denormals, huge
+// arguments, NaN) that cannot occur here.  These versions read their coefficients from the constant bank
+// (operands of DFMA, no extra instruction), assume normal, bounded inputs, and are accurate to ~1 ulp
+// (tests/test_toy_gpu.py::test_fastmath_accuracy).  Algorithms: the classic kernels of fdlibm
+// (k_sin, k_cos, e_log), reciprocal / rsqrt from the hardware seed plus two Newton steps.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fm {
+
+static __constant__ double kLg[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                                     2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                                     1.479819860511658591e-01};
+static __constant__ double kS[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                                    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+static __constant__ double kC[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+static __constant__ double kMisc[10] = {
+    6.93147180369123816490e-01,  // 0 ln2_hi
+    1.90821492927058770002e-10,  // 1 ln2_lo
+    3.141592653589793116,        // 2 pi_hi
+    1.2246467991473532e-16,      // 3 pi_lo
+    6.36619772367581382433e-01,  // 4 2/pi
+    1.57079632673412561417e+00,  // 5 pio2_1  (first 33 bits of pi/2)
+    6.07710050650619224932e-11,  // 6 pio2_1t (pi/2 - pio2_1)
+    6755399441055744.0,          // 7 1.5 * 2^52: adding it rounds to the nearest integer, left in the low word
+    1.4142135623730951,          // 8 sqrt(2)
+    0.0};
+
+__device__ __forceinline__ double rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(fma(-x, y, 1.0), y, y);
+    return fma(fma(-x, y, 1.0), y, y);
+}
+
+// sqrt of a positive normal number
+__device__ __forceinline__ double sqrt_pos(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    const double r = x * y;
+    return fma(fma(-r, r, x), 0.5 * y, r);
+}
+
+// (r + 0.5) * 2^-32 (or 2^-31) without an integer-to-double conversion: r becomes the top 32 fraction
+// bits of a double with exponent 2^32, i.e. 2^32 + r exactly; one fma removes the offset (all exact)
+__device__ __forceinline__ double uniform_from_u32(unsigned r, bool times_two)
+{
+    const double x = __hiloint2double((int)(0x41f00000u | (r >> 12)), (int)(r << 20));  // 2^32 + r
+    return times_two ? fma(x, 4.656612873077392578125e-10, -2.0 + 2.3283064365386962890625e-10)    // (r + 0.5) 2^-31
+                     : fma(x, 2.3283064365386962890625e-10, -1.0 + 1.16415321826934814453125e-10);  // (r + 0.5) 2^-32
+}
+
+// natural logarithm of a positive NORMAL double (fdlibm e_log.c without the special cases)
+__device__ __forceinline__ double log_pos(double x)
+{
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    double m = __hiloint2double(hi, lo);  // [1, 2)
+    const bool big = m > kMisc[8];
+    m = big ? 0.5 * m : m;                // [sqrt(1/2), sqrt(2))
+    e += big ? 1 : 0;
+    const double f = m - 1.0;
+    const double s = f * rcp(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, kLg[5], kLg[3]), kLg[1]);
+    const double t2 = z * fma(w, fma(w, fma(w, kLg[6], kLg[4]), kLg[2]), kLg[0]);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double k = (double)e;
+    return fma(k, kMisc[0], -((hfsq - fma(s, hfsq + R, k * kMisc[1])) - f));
+}
+
+// sin and cos of t, |t| <= pi/4 (fdlibm k_sin.c / k_cos.c)
+__device__ __forceinline__ void sincos_kernel(double t, double& s, double& c)
+{
+    const double z = t * t;
+    const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, kS[5], kS[4]), kS[3]), kS[2]), kS[1]), kS[0]);
+    const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, kC[5], kC[4]), kC[3]), kC[2]), kC[1]), kC[0]);
+    s = fma(t * z, ps, t);
+    c = fma(z * z, pc, fma(z, -0.5, 1.0));
+}
+
+// quadrant n: (sin, cos)(t + n pi/2) from (sin, cos)(t); sign flips are exact bit operations
+__device__ __forceinline__ void rotate_quadrant(int n, double& s, double& c)
+{
+    const double s0 = (n & 1) ? c : s, c0 = (n & 1) ? s : c;
+    const int ss = (int)(((unsigned)n & 2u) << 30), cs = (int)((((unsigned)n + 1u) & 2u) << 30);  // sign bits
+    s = __hiloint2double(__double2hiint(s0) ^ ss, __double2loint(s0));
+    c = __hiloint2double(__double2hiint(c0) ^ cs, __double2loint(c0));
+}
+
+// sin(pi x), cos(pi x) for 0 <= x < 4
+__device__ __forceinline__ void sincospi_small(double x, double& s, double& c)
+{
+    const double t = fma(x, 2.0, kMisc[7]);
+    const int n = __double2loint(t);
+    const double r = fma(t - kMisc[7], -0.5, x);  // exact, |r| <= 1/4
+    sincos_kernel(fma(r, kMisc[3], r * kMisc[2]), s, c);
+    rotate_quadrant(n, s, c);
+}
+
+// sin(x), cos(x) for |x| < ~1e5 (two-term Cody-Waite reduction)
+__device__ __forceinline__ void sincos_medium(double x, double& s, double& c)
+{
+    const double t = fma(x, kMisc[4], kMisc[7]);
+    const int n = __double2loint(t);
+    const double nd = t - kMisc[7];
+    double r = fma(-nd, kMisc[5], x);
+    r = fma(-nd, kMisc[6], r);
+    sincos_kernel(r, s, c);
+    rotate_quadrant(n, s, c);
+}
+
+}  // namespace fm

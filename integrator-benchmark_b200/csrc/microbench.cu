@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "lsi_internal.h"
+#include "rng.cuh"
 
 namespace {
 
@@ -20,7 +21,42 @@ __global__ void __launch_bounds__(256) fma_kernel(int64_t iters, T seed, T* __re
     if (s == (T)-1.2345) sink[0] = s;  // never true; keeps the chains alive
 }
 
+// test hook: the lean fp64 functions of fastmath64.cuh, element-wise
+__global__ void fastmath_kernel(int which, int64_t n, const double* __restrict__ x, double* __restrict__ out0, double* __restrict__ out1)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = 0.0, b = 0.0;
+    if (which == 0) a = fm::log_pos(x[i]);
+    else if (which == 1) fm::sincospi_small(x[i], a, b);
+    else if (which == 2) fm::sincos_medium(x[i], a, b);
+    else if (which == 3) a = fm::sqrt_pos(x[i]);
+    else if (which == 4) a = fm::rcp(x[i]);
+    else if (which == 5) {  // x holds integers < 2^32: the uniforms of the Box-Muller pair
+        a = fm::uniform_from_u32((unsigned)x[i], false);
+        b = fm::uniform_from_u32((unsigned)x[i], true);
+    } else {  // 6: Box-Muller, lean vs library, from the words (x[i], x[i] * 2654435761 mod 2^32)
+        const unsigned ra = (unsigned)x[i], rb = ra * 2654435761u;
+        double c, d;
+        lsi::box_muller_lean(ra, rb, a, b);
+        lsi::box_muller(ra, rb, c, d);
+        a -= c; b -= d;
+    }
+    out0[i] = a;
+    if (out1) out1[i] = b;
+}
+
 }  // namespace
+
+// test hook for tests/test_toy_gpu.py::test_fastmath_accuracy (device pointers)
+LSI_EXPORT int lsi_test_fastmath(int which, int64_t n, const double* x, double* out0, double* out1, void* stream)
+{
+    if (!x || !out0 || n < 0 || which < 0 || which > 6) return lsi_set_error(LSI_ERR_ARG, "lsi_test_fastmath: bad argument");
+    if (n == 0) return LSI_OK;
+    fastmath_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(which, n, x, out0, out1);
+    LSI_CUDA_CHECK(cudaGetLastError());
+    return LSI_OK;
+}
 
 // Launches blocks x 256 threads, each doing iters x 8 FMAs; flops = blocks * 256 * iters * 16.
 LSI_EXPORT int lsi_microbench_fma(int precision, int64_t iters, int blocks, void* sink, void* stream)

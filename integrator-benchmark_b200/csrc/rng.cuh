@@ -11,6 +11,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "fastmath64.cuh"
+
 namespace lsi {
 
 struct Philox4 { uint32_t x, y, z, w; };
@@ -37,6 +39,19 @@ __device__ __forceinline__ Philox4 philox_block(uint64_t seed, uint64_t replica,
 {
     return philox4x32_10((uint32_t)replica, (uint32_t)(replica >> 32), draw, (tag << 28) | unit,
                          (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// fp64 Box-Muller on one pair of words, lean arithmetic (fastmath64.cuh): same formula, ~1 ulp from the
+// library version below; used by the fused toy kernels
+__device__ __forceinline__ void box_muller_lean(uint32_t ra, uint32_t rb, double& n0, double& n1)
+{
+    const double u1 = fm::uniform_from_u32(ra, false);
+    const double u2x2 = fm::uniform_from_u32(rb, true);
+    const double rad = fm::sqrt_pos(-2.0 * fm::log_pos(u1));
+    double s, c;
+    fm::sincospi_small(u2x2, s, c);
+    n0 = rad * c;
+    n1 = rad * s;
 }
 
 // fp64 Box-Muller on one pair of words

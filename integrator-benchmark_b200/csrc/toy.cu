@@ -24,6 +24,14 @@
 #include "lsi_internal.h"
 #include "rng.cuh"
 
+// fp64 Box-Muller and the double well's sin / cos: lean versions of fastmath64.cuh (define LSI_TOY_LIBM for the
+// CUDA math library instead; same formulas, results agree to ~1 ulp)
+#ifdef LSI_TOY_LIBM
+#define LSI_BM64 lsi::box_muller
+#else
+#define LSI_BM64 lsi::box_muller_lean
+#endif
+
 namespace {
 
 constexpr int kMaxOps = 160;  // fits the 4 KB parameter space; longer programs use the global copy
@@ -62,7 +70,13 @@ __device__ __forceinline__ double potential(double x, double p0)
         return x2 * x2;
     } else if (POT == LSI_POT_DOUBLE_WELL) {
         const double x2 = x * x;
+#ifdef LSI_TOY_LIBM
         return x2 * x2 * x2 + 2.0 * cos(5.0 * (x + 1.0));
+#else
+        double s, c;
+        fm::sincos_medium(5.0 * (x + 1.0), s, c);
+        return x2 * x2 * x2 + 2.0 * c;
+#endif
     } else {
         return 0.5 * p0 * x * x;
     }
@@ -75,7 +89,13 @@ __device__ __forceinline__ double force(double x, double p0)
         return -4.0 * x * x * x;
     } else if (POT == LSI_POT_DOUBLE_WELL) {
         const double x2 = x * x;
+#ifdef LSI_TOY_LIBM
         return -(6.0 * x2 * x2 * x - 10.0 * sin(5.0 * (x + 1.0)));
+#else
+        double s, c;
+        fm::sincos_medium(5.0 * (x + 1.0), s, c);
+        return -(6.0 * x2 * x2 * x - 10.0 * s);
+#endif
     } else {
         return -p0 * x;
     }
@@ -93,8 +113,8 @@ __device__ __forceinline__ void normal_block(uint64_t seed, uint64_t replica, ui
         lsi::box_muller(r.z, r.w, c, d);
         n0 = (double)a; n1 = (double)b; n2 = (double)c; n3 = (double)d;
     } else {
-        lsi::box_muller(r.x, r.y, n0, n1);
-        lsi::box_muller(r.z, r.w, n2, n3);
+        LSI_BM64(r.x, r.y, n0, n1);
+        LSI_BM64(r.z, r.w, n2, n3);
     }
 }
 
@@ -104,8 +124,8 @@ __device__ __forceinline__ double scalar_normal(uint64_t seed, uint64_t replica,
 {
     const lsi::Philox4 q = lsi::philox_block(seed, replica, k >> 2, tag, 0u);
     double a, b;
-    if ((k & 2u) == 0u) lsi::box_muller(q.x, q.y, a, b);
-    else lsi::box_muller(q.z, q.w, a, b);
+    if ((k & 2u) == 0u) LSI_BM64(q.x, q.y, a, b);
+    else LSI_BM64(q.z, q.w, a, b);
     return (k & 1u) ? b : a;
 }
 
