@@ -39,14 +39,12 @@ __device__ __forceinline__ double rcp(double x)
     return fma(fma(-x, y, 1.0), y, y);
 }
 
-// sqrt of a positive normal number
+// sqrt of a positive normal number: seed (2^-23) -> one Newton step on 1/sqrt (2^-46) -> one Heron step on sqrt
 __device__ __forceinline__ double sqrt_pos(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x * y, y, 1.0);
-    y = fma(0.5 * y, e, y);
-    e = fma(-x * y, y, 1.0);
+    const double e = fma(-x * y, y, 1.0);
     y = fma(0.5 * y, e, y);
     const double r = x * y;
     return fma(fma(-r, r, x), 0.5 * y, r);
@@ -122,6 +120,29 @@ __device__ __forceinline__ void sincos_medium(double x, double& s, double& c)
     r = fma(-nd, kMisc[6], r);
     sincos_kernel(r, s, c);
     rotate_quadrant(n, s, c);
+}
+
+// sin(x) alone for |x| < ~1e5: one polynomial, its coefficients picked by the quadrant's parity
+// (sin: t + t z S(z); cos: 1 - z/2 + z^2 C(z); both are base + w P(z))
+__device__ __forceinline__ double sin_medium(double x)
+{
+    const double t0 = fma(x, kMisc[4], kMisc[7]);
+    const int n = __double2loint(t0);
+    const double nd = t0 - kMisc[7];
+    double t = fma(-nd, kMisc[5], x);
+    t = fma(-nd, kMisc[6], t);
+    const bool odd = n & 1;
+    const double z = t * t;
+    double p = odd ? kC[5] : kS[5];
+    p = fma(z, p, odd ? kC[4] : kS[4]);
+    p = fma(z, p, odd ? kC[3] : kS[3]);
+    p = fma(z, p, odd ? kC[2] : kS[2]);
+    p = fma(z, p, odd ? kC[1] : kS[1]);
+    p = fma(z, p, odd ? kC[0] : kS[0]);
+    const double base = odd ? fma(z, -0.5, 1.0) : t;
+    const double w = z * (odd ? z : t);
+    const double r = fma(w, p, base);
+    return __hiloint2double(__double2hiint(r) ^ (int)(((unsigned)n & 2u) << 30), __double2loint(r));
 }
 
 }  // namespace fm

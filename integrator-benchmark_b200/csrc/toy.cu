@@ -74,8 +74,8 @@ __device__ __forceinline__ double potential(double x, double p0)
         return x2 * x2 * x2 + 2.0 * cos(5.0 * (x + 1.0));
 #else
         double s, c;
-        fm::sincos_medium(5.0 * (x + 1.0), s, c);
-        return x2 * x2 * x2 + 2.0 * c;
+        fm::sincos_medium(fma(5.0, x, 5.0), s, c);
+        return fma(x2 * x2, x2, 2.0 * c);
 #endif
     } else {
         return 0.5 * p0 * x * x;
@@ -92,9 +92,7 @@ __device__ __forceinline__ double force(double x, double p0)
 #ifdef LSI_TOY_LIBM
         return -(6.0 * x2 * x2 * x - 10.0 * sin(5.0 * (x + 1.0)));
 #else
-        double s, c;
-        fm::sincos_medium(5.0 * (x + 1.0), s, c);
-        return -(6.0 * x2 * x2 * x - 10.0 * s);
+        return fma(-6.0 * x2 * x2, x, 10.0 * fm::sin_medium(fma(5.0, x, 5.0)));
 #endif
     } else {
         return -p0 * x;
@@ -206,9 +204,10 @@ struct FusedStep {
                 valid = true;
                 v = v + P.hV * f;
             } else {
-                const double ke_old = half_m * v * v;
-                v = P.oa * v + P.oc * xi[o];
-                heat += half_m * v * v - ke_old;
+                // heat += m/2 (v_new^2 - v_old^2): three fp64 instructions instead of six
+                const double v_old2 = v * v;
+                v = fma(P.oa, v, P.oc * xi[o]);
+                heat = fma(half_m, fma(v, v, -v_old2), heat);
                 ++o;
             }
         }
