@@ -1,11 +1,12 @@
-"""Drop-in for benchmark/experiments/driver.py:12-82 -- the canonical caller of the hot path: one
-(system, splitting, dt, marginal, collision rate, H-mass factor) experiment, run as ONE ensemble launch,
-saved as the reference's pickle {"result": {"W_shads_F", "W_shads_R"[, ...]}, "descriptor": {...}} so that
-benchmark/plotting/plotting_utilities.py:125-176 consumes the output unchanged."""
-from collections import namedtuple
-from pickle import dump
+"""One (system, splitting, dt, marginal, collision rate, H-mass factor) experiment as a single ensemble launch.
 
-import numpy as np
+API-compatible with the reference's canonical caller of the hot path (benchmark/experiments/driver.py:12-82):
+the same descriptor fields, `Experiment(descriptor, filename).run() / .save() / .run_and_save()`, and the same
+pickle layout {"result": {"W_shads_F", "W_shads_R", ...}, "descriptor": {...without the simulator...}}, so that
+benchmark/plotting/plotting_utilities.py:125-176 reads the output unchanged.
+"""
+import pickle
+from collections import namedtuple
 
 from .. import unit
 from ..evaluation import estimate_nonequilibrium_free_energy
@@ -13,70 +14,57 @@ from ..integrators import LangevinSplittingIntegrator
 from ..testsystems import NonequilibriumSimulator
 from ..utilities.openmm_utilities import repartition_hydrogen_mass_amber_masses
 
-ExperimentDescriptor = namedtuple("ExperimentDescriptor", ["experiment_name",
-                                                           "system_name", "equilibrium_simulator",
-                                                           "splitting_name", "splitting_string",
-                                                           "timestep_in_fs",
-                                                           "marginal",
-                                                           "collision_rate_name", "collision_rate",
-                                                           "n_protocol_samples", "protocol_length", "h_mass_factor"])
+_FIELDS = ("experiment_name", "system_name", "equilibrium_simulator", "splitting_name", "splitting_string",
+           "timestep_in_fs", "marginal", "collision_rate_name", "collision_rate", "n_protocol_samples",
+           "protocol_length", "h_mass_factor")
+ExperimentDescriptor = namedtuple("ExperimentDescriptor", _FIELDS)
 
 
-class Experiment():
+def _apply_hydrogen_mass_factor(eq_sim, factor):
+    """Hydrogen-mass repartitioning on the system description (utilities/openmm_utilities.py:223-269); a system
+    can be modified once, as in the reference."""
+    if getattr(eq_sim, "MODIFIED_H_MASS", False):
+        raise Exception("H mass of this system was already modified! Can't guarantee correct behavior")
+    desc = dict(eq_sim.system)
+    missing = [k for k in ("elements", "bonds_topology") if k not in desc]
+    if missing:
+        raise Exception("hydrogen-mass repartitioning needs %s in the system description" % " and ".join(missing))
+    desc["mass"] = repartition_hydrogen_mass_amber_masses(desc["elements"], desc["bonds_topology"], desc["mass"], factor)
+    eq_sim.system = desc
+    eq_sim._engine_system = None  # masses are part of the compiled system tables
+    eq_sim.MODIFIED_H_MASS = True
+
+
+class Experiment:
     def __init__(self, experiment_descriptor, filename, store_potential_energy_traces=False):
         self.experiment_descriptor = experiment_descriptor
         self.filename = filename
-        exp = self.experiment_descriptor
         self.store_potential_energy_traces = store_potential_energy_traces
-
-        if exp.h_mass_factor != 1:
-            eq = exp.equilibrium_simulator
-            if hasattr(eq, "MODIFIED_H_MASS"):
-                raise (Exception("H mass of this system was already modified! Can't guarantee correct behavior"))
-            desc = dict(eq.system)
-            if "elements" not in desc or "bonds_topology" not in desc:
-                raise Exception("hydrogen-mass repartitioning needs `elements` and `bonds_topology` in the system description")
-            desc["mass"] = repartition_hydrogen_mass_amber_masses(desc["elements"], desc["bonds_topology"], desc["mass"],
-                                                                  exp.h_mass_factor)
-            eq.system = desc
-            eq._engine_system = None  # masses are part of the compiled system tables
-            eq.MODIFIED_H_MASS = True
+        self.result = None
+        if experiment_descriptor.h_mass_factor != 1:
+            _apply_hydrogen_mass_factor(experiment_descriptor.equilibrium_simulator, experiment_descriptor.h_mass_factor)
 
     def run(self):
-        exp = self.experiment_descriptor
-        simulator = NonequilibriumSimulator(exp.equilibrium_simulator,
-                                            LangevinSplittingIntegrator(
-                                                splitting=exp.splitting_string,
-                                                timestep=exp.timestep_in_fs * unit.femtosecond,
-                                                collision_rate=exp.collision_rate))
-
-        self.result = simulator.collect_protocol_samples(
-            exp.n_protocol_samples, exp.protocol_length, exp.marginal,
-            store_potential_energy_traces=(exp.marginal == "full" and self.store_potential_energy_traces))
-
-        W_shads_F, W_shads_R = self.result["W_shads_F"], self.result["W_shads_R"]
-        DeltaF_neq, squared_uncertainty = estimate_nonequilibrium_free_energy(W_shads_F, W_shads_R)
-        self.DeltaF_neq, self.squared_uncertainty = DeltaF_neq, squared_uncertainty
-        print(self)
-        print("\t{:.3f} +/- {:.3f}".format(DeltaF_neq, np.sqrt(squared_uncertainty)))
+        d = self.experiment_descriptor
+        integrator = LangevinSplittingIntegrator(splitting=d.splitting_string, timestep=d.timestep_in_fs * unit.femtosecond,
+                                                 collision_rate=d.collision_rate)
+        want_pe = bool(self.store_potential_energy_traces) and d.marginal == "full"
+        self.result = NonequilibriumSimulator(d.equilibrium_simulator, integrator).collect_protocol_samples(
+            d.n_protocol_samples, d.protocol_length, d.marginal, store_potential_energy_traces=want_pe)
+        self.DeltaF_neq, self.squared_uncertainty = estimate_nonequilibrium_free_energy(self.result["W_shads_F"],
+                                                                                        self.result["W_shads_R"])
+        print("%s\n\t%.3f +/- %.3f" % (self, self.DeltaF_neq, self.squared_uncertainty ** 0.5))
 
     def save(self):
+        descriptor = {k: v for k, v in self.experiment_descriptor._asdict().items() if k != "equilibrium_simulator"}
         with open(self.filename, "wb") as f:
-            everything_but_the_simulator = self.experiment_descriptor._asdict()
-            everything_but_the_simulator.pop("equilibrium_simulator")
-            dump({"result": self.result, "descriptor": everything_but_the_simulator}, f)
+            pickle.dump({"result": self.result, "descriptor": descriptor}, f)
 
     def run_and_save(self):
         self.run()
         self.save()
 
     def __str__(self):
-        exp = self.experiment_descriptor
-        properties = [exp.system_name,
-                      exp.splitting_name,
-                      "dt={}fs".format(exp.timestep_in_fs),
-                      "marginal: {}".format(exp.marginal),
-                      "collision rate: {}".format(exp.collision_rate_name),
-                      "H-mass scale: {}".format(exp.h_mass_factor)
-                      ]
-        return "\n\t".join(["{}"] * len(properties)).format(*properties)
+        d = self.experiment_descriptor
+        return "\n\t".join([str(d.system_name), str(d.splitting_name), "dt=%sfs" % d.timestep_in_fs, "marginal: %s" % d.marginal,
+                            "collision rate: %s" % d.collision_rate_name, "H-mass scale: %s" % d.h_mass_factor])
