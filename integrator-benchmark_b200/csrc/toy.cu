@@ -214,8 +214,11 @@ struct FusedStep {
     }
 };
 
+#ifndef LSI_TOY_MINB
+#define LSI_TOY_MINB 1
+#endif
 template <int POT, uint32_t CODE, int NOPS, bool NOISE32>
-__global__ void __launch_bounds__(kThreads) toy_fused_kernel(const __grid_constant__ ToyParams P)
+__global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const __grid_constant__ ToyParams P)
 {
     constexpr int NO = code_count(CODE, NOPS, LSI_OP_O);  // normals per step
     constexpr int U = (NO == 0) ? 1 : ((4 % NO == 0) ? 4 / NO : 4);  // steps per noise refill when NO | 4
