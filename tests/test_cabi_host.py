@@ -92,3 +92,36 @@ def test_product_does_not_import_oracle():
                 for pat in (r"^\s*(from|import)\s+oracle", r"liblsi_oracle", r"oracle[/.]", r"#include.*oracle"):
                     assert not re.search(pat, text, flags=re.M), (pat, os.path.join(dirpath, f))
     assert ib.__version__
+
+
+def test_particle_system_validation_is_host_only_and_loud():
+    """lsi_system_create_particles copies and checks its tables on the host (no CUDA call): bad descriptions are
+    rejected with the boundary's error codes, and compute entry points fail loudly without a device."""
+    import numpy as np
+    import integrator_benchmark_b200 as ib
+    from integrator_benchmark_b200.testsystems import systems as ts
+    desc, x = ts.water_cluster(4, constrained=True)
+    system = ib.engine.ParticleSystem(desc)            # fine without a GPU
+    assert system.n_dof == 36
+    with pytest.raises(ValueError):                    # atom index out of range
+        ib.engine.ParticleSystem(dict(desc, exclusions=[(0, 99)]))
+    with pytest.raises(ValueError):                    # a pair constraint on an atom of a rigid water
+        ib.engine.ParticleSystem(dict(desc, constraint_atoms=[(0, 3)], constraint_dist=[0.3]))
+    with pytest.raises(ValueError):                    # impossible triangle
+        ib.engine.ParticleSystem(dict(desc, settle_hh=0.3))
+    with pytest.raises(ValueError):                    # massless site
+        ib.engine.ParticleSystem(dict(desc, mass=np.zeros(12)))
+    with pytest.raises(ValueError):                    # box smaller than twice the cutoff
+        ib.engine.ParticleSystem(dict(desc, nonbonded_method="CutoffPeriodic", cutoff=0.6, box=(1.0, 1.0, 1.0)))
+    with pytest.raises(NotImplementedError):           # waters with different masses cannot share the SETTLE constants
+        m = np.array(desc["mass"], dtype=float)
+        m[3] = 18.0
+        ib.engine.ParticleSystem(dict(desc, mass=m))
+    big, _ = ts.tiny_waterbox(n_waters=300, box_edge=2.2)
+    with pytest.raises(ValueError):                    # more atoms than one CTA holds
+        ib.engine.ParticleSystem(big)
+    if ib._cabi.lib.lsi_device_count() == 0:
+        with pytest.raises(ib._cabi.LsiCudaError):
+            system.energy_forces(x[None])
+        with pytest.raises(ib._cabi.LsiCudaError):
+            ib.engine.run_protocol(system, ib.engine.Program("V R O R V", 0.001, 1.0), 2, 3, 2.5, x0=np.repeat(x[None], 2, 0))
