@@ -116,6 +116,14 @@ def test_collect_protocol_samples_ensemble_matches_oracle_and_estimator(ib, orc)
         wf, wr = ref["W"][:, 0], ref["W"][:, 1]
         assert dF == pytest.approx(0.5 * (wf.mean() - wr.mean()), abs=1e-6)
         assert var == pytest.approx((np.var(wf) + np.var(wr) - 2 * np.cov(wf, wr)[0, 1]) / (4 * n), rel=1e-4)
+    # potential-energy traces of the reverse leg (store_potential_energy_traces, bookkeepers.py:272-274,288-293)
+    sim = NonequilibriumSimulator(eq, integ, precision="double")
+    ib.set_seed(7, next_replica=0)
+    out_pe = sim.collect_protocol_samples(6, 5, "full", store_potential_energy_traces=True)
+    ref_pe = orc.particles_protocol(eq.system, "V R O R V", 0.004, 1.0, eq.kT_value, 6, 5, marginal="full", seed=7, replica0=0,
+                                    x_cache=samples, round_midpoint=True, traces=True)
+    assert len(out_pe["potential_energies"]) == 6 and out_pe["potential_energies"][2].shape == (6,)
+    np.testing.assert_allclose(np.array(out_pe["potential_energies"]), ref_pe["trace_pe"][:, 1], rtol=1e-8, atol=1e-6)
     with pytest.raises(NotImplementedError):
         sim.collect_protocol_samples(4, 4, "momentum")
     # mixed precision (the reference's CUDA configuration) stays close to the fp64 run
