@@ -195,7 +195,9 @@ int lsi_system_num_dof(const lsi_system* s);
  * `moments` (device, 8 doubles, optional) receives, over replicas whose works are all
  * finite: {count, sum wF, sum wR, sum wF^2, sum wR^2, sum wF wR, count_nonfinite, 0};
  * it needs n_legs == 2.  Scratch for the block partials is taken from `workspace`
- * (device, at least lsi_protocol_workspace_bytes(n_replicas) bytes). */
+ * (device, at least lsi_protocol_workspace_bytes(n_replicas) bytes).  Scalar systems fuse the block
+ * partials into the protocol kernel; particle systems reduce W with the kernel of lsi_reduce_moments
+ * on the same stream. */
 /* flags: positions pass through a float32 frame at the midpoint, as the reference's mdtraj
  * round trip does (bookkeepers.py:266,298-305).  Particle systems only. */
 #define LSI_FLAG_ROUND_MIDPOINT_X_FP32 1

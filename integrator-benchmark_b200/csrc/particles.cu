@@ -495,7 +495,11 @@ int lsi_particles_run_protocol(const lsi_system* sys, const lsi_program* prog, c
     if ((int64_t)a->n_steps * (int64_t)(prog->n_O > 0 ? prog->n_O : 1) >= ((int64_t)1 << 26))
         return lsi_set_error(LSI_ERR_ARG, "n_steps * n_O exceeds the 2^26 draws a leg's noise stream holds");
     if (a->n_replicas > 0x7fffffff) return lsi_set_error(LSI_ERR_ARG, "at most 2^31 - 1 replicas per launch");
-    if (a->moments) return lsi_set_error(LSI_ERR_ARG, "particle systems: reduce the returned works with lsi_reduce_moments");
+    if (a->moments) {
+        if (a->n_legs != 2) return lsi_set_error(LSI_ERR_ARG, "moments need n_legs == 2");
+        if (!a->workspace || a->workspace_bytes < lsi_protocol_workspace_bytes(a->n_replicas))
+            return lsi_set_error(LSI_ERR_ARG, "workspace too small: need %lld bytes", (long long)lsi_protocol_workspace_bytes(a->n_replicas));
+    }
 
     DevTables* t = nullptr;
     int rc = get_tables(p, &t);
@@ -568,6 +572,8 @@ int lsi_particles_run_protocol(const lsi_system* sys, const lsi_program* prog, c
     P.team_lanes = L.team_lanes;
     rc = mixed ? lsi_pk_launch_protocol_f32(P, L, stream) : lsi_pk_launch_protocol_f64(P, L, stream);
     if (dprog) cudaFreeAsync(dprog, st);
+    if (rc == LSI_OK && a->moments)  // works are leg-major: W_F = W[0 .. n), W_R = W[n .. 2n)
+        rc = lsi_reduce_moments(a->W, a->W + a->n_replicas, a->n_replicas, a->moments, a->workspace, a->workspace_bytes, stream);
     return rc;
 }
 

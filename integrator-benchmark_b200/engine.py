@@ -287,7 +287,7 @@ def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configurati
         a.trace_x = _ptr(buf("trace_x", *tshape))
         a.trace_v = _ptr(buf("trace_v", *tshape))
         a.trace_w = _ptr(buf("trace_w", n_legs, n_steps + 1, n))
-    if want_moments and n_legs == 2 and scalar:
+    if want_moments and n_legs == 2 and n > 0:
         a.moments = _ptr(buf("moments", 8))
         nbytes = lib.lsi_protocol_workspace_bytes(n)
         ws = out.get("_workspace")
@@ -298,14 +298,6 @@ def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configurati
     out["_keepalive"] = (x_cache, x0, v0)
     with t.cuda.device(dev):
         check(lib.lsi_run_protocol(system.handle, program.handle, ctypes.byref(a), current_stream_ptr()))
-        if want_moments and n_legs == 2 and not scalar and n > 0:
-            m = buf("moments", 8)
-            ws = out.get("_workspace")
-            if ws is None or ws.numel() < 1024 * 8 or ws.device != dev:
-                ws = t.empty(1024 * 8, dtype=t.float64, device=dev)
-                out["_workspace"] = ws
-            check(lib.lsi_reduce_moments(_ptr(out["W"][0]), _ptr(out["W"][1]), n, _ptr(m), _ptr(ws), ws.numel() * 8,
-                                         current_stream_ptr()))
     return out
 
 
