@@ -1,1 +1,2 @@
 from .system_xml import load_system_xml, system_to_xml  # noqa: F401
+from .mdtraj_hdf5 import load_mdtraj_hdf5  # noqa: F401

@@ -8,6 +8,8 @@ ensemble of `n_protocol_samples` replicas is ONE launch of the fused protocol ke
 CPU path: frames are plain (n_atoms, 3) arrays in nm (an object with an `.xyz` attribute, as an
 mdtraj frame has, is accepted too).
 """
+import os
+
 import numpy as np
 
 from .. import _rngstate, engine, unit
@@ -56,6 +58,7 @@ class EquilibriumSimulator:
         self.sampler_precision = "double"
         self.acceptance = None
         self.max_equilibration_steps = 1000000  # 1 ns at 1 fs, the length of the reference's burn-in
+        self.use_disk_cache = False              # the reference always caches to DATA_PATH; opt in here
 
     # ---- engine handles
     @property
@@ -114,8 +117,57 @@ class EquilibriumSimulator:
         return float(self.acceptance[0])
 
     def load_or_simulate_samples(self):
-        if not self.cached:
-            self.collect_equilibrium_samples()
+        """If equilibrium samples were collected and stored before, load them, else collect and store them
+        (reference :66-76).  The cache is `{name}_samples.npz` in DATA_PATH; a `{name}_samples.h5` written by the
+        reference (an mdtraj HDF5 trajectory, e.g. data/tiny_waterbox_constrained_samples.h5) is read too.
+        Off by default (collecting a cache takes seconds here, not hours): set `use_disk_cache = True`."""
+        if self.cached:
+            return
+        if self.use_disk_cache and self.check_for_cached_samples():
+            self.set_samples(self._read_cache())
+            return
+        self.collect_equilibrium_samples()
+        if self.use_disk_cache:
+            self.save_samples()
+
+    def get_path_to_samples(self):
+        """Samples are {name}_samples.npz in DATA_PATH (reference :115-118 uses .h5)"""
+        from .. import DATA_PATH
+        return os.path.join(DATA_PATH, "{}_samples.npz".format(self.name))
+
+    def _candidate_paths(self):
+        npz = self.get_path_to_samples()
+        return [npz, npz[:-4] + ".h5"]
+
+    def check_for_cached_samples(self):
+        """Check if there's a file where we expect to find cached samples (reference :120-125)"""
+        return any(os.path.exists(p) for p in self._candidate_paths())
+
+    def _read_cache(self):
+        n_atoms = self.positions.shape[0]
+        for path in self._candidate_paths():
+            if not os.path.exists(path):
+                continue
+            if path.endswith(".npz"):
+                with np.load(path) as d:
+                    xyz = np.asarray(d["xyz"], dtype=np.float64)
+            else:
+                from ..serialization.mdtraj_hdf5 import load_mdtraj_hdf5
+                xyz = load_mdtraj_hdf5(path, n_atoms)["xyz"].astype(np.float64)
+            if xyz.ndim != 3 or xyz.shape[1:] != (n_atoms, 3):
+                raise ValueError("{}: cached samples have shape {}, expected (*, {}, 3)".format(path, xyz.shape, n_atoms))
+            return xyz
+        raise FileNotFoundError(self.get_path_to_samples())
+
+    def save_samples(self, path=None):
+        """Store the cache (float32 nm, like the reference's mdtraj file) next to its acceptance statistics."""
+        path = self.get_path_to_samples() if path is None else path
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        tmp = path + ".tmp.npz"
+        np.savez_compressed(tmp, xyz=np.asarray(self.samples, dtype=np.float32),
+                            acceptance=np.zeros(0) if self.acceptance is None else np.asarray(self.acceptance))
+        os.replace(tmp, path)
+        return path
 
     def set_samples(self, samples):
         """Install an externally produced cache, e.g. the frames of the reference's

@@ -138,3 +138,87 @@ def test_experiment_pickle_layout(tmp_path):
     assert set(got) == {"result", "descriptor"} and "equilibrium_simulator" not in got["descriptor"]
     assert got["descriptor"]["splitting_string"] == "O V R V O" and got["descriptor"]["h_mass_factor"] == 1
     assert "dt=2.0fs" in str(e)
+
+
+# ------------------------------------------------------------------ equilibrium-sample caches
+def _shuffled_zlib(a):
+    import zlib
+    raw = np.ascontiguousarray(a, "<f4").view(np.uint8).reshape(-1, 4).T.copy().tobytes()
+    return zlib.compress(raw, 6)
+
+
+def test_mdtraj_hdf5_chunks_synthetic(tmp_path):
+    """byte-shuffled zlib chunks between unrelated bytes (some of them 0x78) are found, unshuffled and trimmed"""
+    from importlib import import_module
+    h5 = import_module("integrator-benchmark_b200.serialization.mdtraj_hdf5")
+    rng = np.random.default_rng(5)
+    n_atoms, n_frames, chunk_frames = 7, 5, 8
+    xyz = np.zeros((chunk_frames, n_atoms, 3), np.float32)
+    xyz[:n_frames] = rng.normal(size=(n_frames, n_atoms, 3))
+    lengths = np.zeros((64, 3), np.float32)
+    lengths[:n_frames] = 1.5
+    angles = np.zeros((64, 3), np.float32)
+    angles[:n_frames] = 90.0
+    blob = (b"\x89HDF\r\n\x1a\n" + b"\x78\x9cnot a stream" + bytes(rng.integers(0, 256, 300, dtype=np.uint8))
+            + _shuffled_zlib(lengths) + b"\x00" * 17 + _shuffled_zlib(angles) + b"x\x01x\xda"
+            + _shuffled_zlib(np.arange(50, dtype=np.float32)) + _shuffled_zlib(xyz) + b"tail")
+    path = tmp_path / "fake_samples.h5"
+    path.write_bytes(blob)
+    out = h5.load_mdtraj_hdf5(str(path), n_atoms)
+    assert out["xyz"].shape == (n_frames, n_atoms, 3)
+    np.testing.assert_array_equal(out["xyz"], xyz[:n_frames])
+    np.testing.assert_array_equal(out["cell_lengths"], lengths[:n_frames])
+    np.testing.assert_array_equal(out["cell_angles"], angles[:n_frames])
+    with pytest.raises(ValueError):
+        h5.load_mdtraj_hdf5(str(path), n_atoms + 1000)
+    (tmp_path / "not.h5").write_bytes(b"hello")
+    with pytest.raises(ValueError):
+        h5.load_mdtraj_hdf5(str(tmp_path / "not.h5"), n_atoms)
+
+
+REF_H5 = "/root/reference/data/tiny_waterbox_constrained_samples.h5"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_H5), reason="reference checkout not present")
+def test_mdtraj_hdf5_reference_cache():
+    """the one cache the reference ships decodes to the committed fixture frames"""
+    from importlib import import_module
+    h5 = import_module("integrator-benchmark_b200.serialization.mdtraj_hdf5")
+    out = h5.load_mdtraj_hdf5(REF_H5, 306)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "waterbox_frames.npz"))
+    assert out["xyz"].shape[1:] == (306, 3) and out["xyz"].shape[0] >= 4
+    np.testing.assert_array_equal(out["xyz"][:4], gold["xyz"])
+    np.testing.assert_allclose(out["cell_lengths"][:4], 1.5)
+    np.testing.assert_allclose(out["cell_angles"][:4], 90.0)
+
+
+def test_equilibrium_cache_on_disk(tmp_path, monkeypatch):
+    """get_path_to_samples / check_for_cached_samples / load_or_simulate_samples (bookkeepers.py:66-125) without a GPU:
+    a stored cache is picked up and never re-simulated"""
+    from importlib import import_module
+    pkg = import_module("integrator-benchmark_b200")
+    bk = import_module("integrator-benchmark_b200.testsystems.bookkeepers")
+    monkeypatch.setattr(pkg, "DATA_PATH", str(tmp_path))
+    eq = bk.EquilibriumSimulator(platform=None, topology=None, system={}, positions=np.zeros((5, 3)), temperature=298.0,
+                                 timestep=0.001, burn_in_length=10, n_samples=3, thinning_interval=1, name="five_atoms")
+    eq.use_disk_cache = True
+    assert eq.get_path_to_samples() == os.path.join(str(tmp_path), "five_atoms_samples.npz")
+    assert not eq.check_for_cached_samples()
+    frames = np.random.default_rng(1).normal(size=(3, 5, 3)).astype(np.float32)
+    eq.samples = frames
+    eq.save_samples()
+    assert eq.check_for_cached_samples()
+    eq2 = bk.EquilibriumSimulator(platform=None, topology=None, system={}, positions=np.zeros((5, 3)), temperature=298.0,
+                                  timestep=0.001, burn_in_length=10, n_samples=3, thinning_interval=1, name="five_atoms")
+    eq2.use_disk_cache = True
+    eq2.collect_equilibrium_samples = lambda *a, **k: pytest.fail("cache ignored")
+    eq2.load_or_simulate_samples()
+    assert eq2.cached and eq2.samples.dtype == np.float64
+    np.testing.assert_array_equal(eq2.samples, frames.astype(np.float64))
+    assert eq2.sample_x_from_equilibrium().shape == (5, 3)
+    # wrong atom count in the file is an error, not a silent reshape
+    eq3 = bk.EquilibriumSimulator(platform=None, topology=None, system={}, positions=np.zeros((6, 3)), temperature=298.0,
+                                  timestep=0.001, burn_in_length=10, n_samples=3, thinning_interval=1, name="five_atoms")
+    eq3.use_disk_cache = True
+    with pytest.raises(ValueError):
+        eq3.load_or_simulate_samples()
