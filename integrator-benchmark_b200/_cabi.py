@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblsi.so")
+# LSI_LIB_PATH: load another build of the same library (kernel experiments, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("LSI_LIB_PATH") or os.path.join(_HERE, "lib", "liblsi.so")
 
 OK, ERR_ASSERT, ERR_VALUE, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_KEY = 0, -1, -2, -3, -4, -5, -6
 OP_R, OP_V, OP_O = 0, 1, 2

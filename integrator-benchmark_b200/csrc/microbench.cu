@@ -24,10 +24,26 @@ __global__ void __launch_bounds__(256) fma_kernel(int64_t iters, T seed, T* __re
 // test hook: the lean fp64 functions of fastmath64.cuh, element-wise
 __global__ void fastmath_kernel(int which, int64_t n, const double* __restrict__ x, double* __restrict__ out0, double* __restrict__ out1)
 {
+    __shared__ fm::Tables T;
+    if (which >= 7) {
+        fm::load_tables(T);
+        __syncthreads();
+    }
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double a = 0.0, b = 0.0;
     if (which == 0) a = fm::log_pos(x[i]);
+    else if (which == 7) a = fm::neg2log_tab(T, x[i]);
+    else if (which == 8) fm::sincos2pi_u32_tab(T, (unsigned)x[i], a, b);
+    else if (which == 10) a = fm::sin_tab(T, x[i]);
+    else if (which == 11) a = fm::sqrt_pos_scaled(x[i], 1.0);
+    else if (which == 9) {  // Box-Muller, table-driven vs library
+        const unsigned ra = (unsigned)x[i], rb = ra * 2654435761u;
+        double c, d;
+        lsi::box_muller_tab(T, ra, rb, 1.0, a, b);
+        lsi::box_muller(ra, rb, c, d);
+        a -= c; b -= d;
+    }
     else if (which == 1) fm::sincospi_small(x[i], a, b);
     else if (which == 2) {  // sin from the single-polynomial version, cos from the pair
         double s2;
@@ -56,7 +72,7 @@ __global__ void fastmath_kernel(int which, int64_t n, const double* __restrict__
 // test hook for tests/test_toy_gpu.py::test_fastmath_accuracy (device pointers)
 LSI_EXPORT int lsi_test_fastmath(int which, int64_t n, const double* x, double* out0, double* out1, void* stream)
 {
-    if (!x || !out0 || n < 0 || which < 0 || which > 6) return lsi_set_error(LSI_ERR_ARG, "lsi_test_fastmath: bad argument");
+    if (!x || !out0 || n < 0 || which < 0 || which > 11) return lsi_set_error(LSI_ERR_ARG, "lsi_test_fastmath: bad argument");
     if (n == 0) return LSI_OK;
     fastmath_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(which, n, x, out0, out1);
     LSI_CUDA_CHECK(cudaGetLastError());

@@ -34,6 +34,40 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{c0, c1, c2, c3};
 }
 
+// Round keys of one seed, computed once on the host (philox_round_keys) and carried in the kernel parameters:
+// the key operand of every round's XOR then comes straight from the constant bank instead of 20 additions
+// per block.  Same function as philox4x32_10.
+struct PhiloxKeys { uint32_t k[20]; };
+
+inline __host__ __device__ PhiloxKeys philox_round_keys(uint64_t seed)
+{
+    PhiloxKeys K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k[2 * r] = k0;
+        K.k[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return K;
+}
+
+__device__ __forceinline__ Philox4 philox_block(const PhiloxKeys& K, uint64_t replica, uint32_t draw, uint32_t tag,
+                                                uint32_t unit)
+{
+    uint32_t c0 = (uint32_t)replica, c1 = (uint32_t)(replica >> 32), c2 = draw, c3 = (tag << 28) | unit;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ K.k[2 * r];
+        c2 = hi0 ^ c3 ^ K.k[2 * r + 1];
+        c1 = lo1;
+        c3 = lo0;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
 __device__ __forceinline__ Philox4 philox_block(uint64_t seed, uint64_t replica, uint32_t draw, uint32_t tag,
                                                 uint32_t unit)
 {
@@ -50,6 +84,17 @@ __device__ __forceinline__ void box_muller_lean(uint32_t ra, uint32_t rb, double
     const double rad = fm::sqrt_pos(-2.0 * fm::log_pos(u1));
     double s, c;
     fm::sincospi_small(u2x2, s, c);
+    n0 = rad * c;
+    n1 = rad * s;
+}
+
+// the same pair with the table-driven -2 log and sincos (tables staged in shared memory by the caller)
+// and the five-instruction sqrt; `scale` multiplies both normals
+__device__ __forceinline__ void box_muller_tab(const fm::Tables& T, uint32_t ra, uint32_t rb, double scale, double& n0, double& n1)
+{
+    const double rad = fm::sqrt_pos_scaled(fm::neg2log_tab(T, fm::uniform_from_u32(ra, false)), scale);
+    double s, c;
+    fm::sincos2pi_u32_tab(T, rb, s, c);
     n0 = rad * c;
     n1 = rad * s;
 }

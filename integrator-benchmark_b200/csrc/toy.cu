@@ -26,10 +26,13 @@
 
 // fp64 Box-Muller and the double well's sin / cos: lean versions of fastmath64.cuh (define LSI_TOY_LIBM for the
 // CUDA math library instead; same formulas, results agree to ~1 ulp)
-#ifdef LSI_TOY_LIBM
-#define LSI_BM64 lsi::box_muller
+#if defined(LSI_TOY_LIBM)
+#define LSI_BM64(T, ra, rb, sc, n0, n1) do { lsi::box_muller(ra, rb, n0, n1); n0 *= sc; n1 *= sc; } while (0)
+#elif defined(LSI_TOY_POLY)
+#define LSI_BM64(T, ra, rb, sc, n0, n1) do { lsi::box_muller_lean(ra, rb, n0, n1); n0 *= sc; n1 *= sc; } while (0)
 #else
-#define LSI_BM64 lsi::box_muller_lean
+#define LSI_BM64(T, ra, rb, sc, n0, n1) lsi::box_muller_tab(T, ra, rb, sc, n0, n1)
+#define LSI_TOY_TABLES 1
 #endif
 
 namespace {
@@ -49,6 +52,7 @@ struct ToyProgram {
 };
 
 struct ToyParams {
+    lsi::PhiloxKeys keys;  // round keys of `seed`
     uint64_t seed, replica0;
     int64_t n;
     int n_steps, n_legs, marginal;
@@ -83,7 +87,7 @@ __device__ __forceinline__ double potential(double x, double p0)
 }
 
 template <int POT>
-__device__ __forceinline__ double force(double x, double p0)
+__device__ __forceinline__ double force(const fm::Tables& T, double x, double p0)
 {
     if (POT == LSI_POT_QUARTIC) {
         return -4.0 * x * x * x;
@@ -91,39 +95,41 @@ __device__ __forceinline__ double force(double x, double p0)
         const double x2 = x * x;
 #ifdef LSI_TOY_LIBM
         return -(6.0 * x2 * x2 * x - 10.0 * sin(5.0 * (x + 1.0)));
-#else
+#elif defined(LSI_TOY_POLY)
         return fma(-6.0 * x2 * x2, x, 10.0 * fm::sin_medium(fma(5.0, x, 5.0)));
+#else
+        return fma(-6.0 * x2 * x2, x, 10.0 * fm::sin_tab(T, fma(5.0, x, 5.0)));
 #endif
     } else {
         return -p0 * x;
     }
 }
 
-// four normals of one block of a replica's scalar stream
+// four normals of one block of a replica's scalar stream, each multiplied by `scale`
 template <bool NOISE32>
-__device__ __forceinline__ void normal_block(uint64_t seed, uint64_t replica, uint32_t draw, uint32_t tag,
-                                             double& n0, double& n1, double& n2, double& n3)
+__device__ __forceinline__ void normal_block(const fm::Tables& T, const lsi::PhiloxKeys& seed, uint64_t replica, uint32_t draw, uint32_t tag,
+                                             double scale, double& n0, double& n1, double& n2, double& n3)
 {
     const lsi::Philox4 r = lsi::philox_block(seed, replica, draw, tag, 0u);
     if (NOISE32) {
         float a, b, c, d;
         lsi::box_muller(r.x, r.y, a, b);
         lsi::box_muller(r.z, r.w, c, d);
-        n0 = (double)a; n1 = (double)b; n2 = (double)c; n3 = (double)d;
+        n0 = scale * (double)a; n1 = scale * (double)b; n2 = scale * (double)c; n3 = scale * (double)d;
     } else {
-        LSI_BM64(r.x, r.y, n0, n1);
-        LSI_BM64(r.z, r.w, n2, n3);
+        LSI_BM64(T, r.x, r.y, scale, n0, n1);
+        LSI_BM64(T, r.z, r.w, scale, n2, n3);
     }
 }
 
 // normal number k of a (replica, tag) scalar stream: block k >> 2, lane k & 3 (always fp64:
 // start and midpoint velocities are drawn once per leg)
-__device__ __forceinline__ double scalar_normal(uint64_t seed, uint64_t replica, uint32_t tag, uint32_t k)
+__device__ __forceinline__ double scalar_normal(const fm::Tables& T, const lsi::PhiloxKeys& seed, uint64_t replica, uint32_t tag, uint32_t k)
 {
     const lsi::Philox4 q = lsi::philox_block(seed, replica, k >> 2, tag, 0u);
     double a, b;
-    if ((k & 2u) == 0u) LSI_BM64(q.x, q.y, a, b);
-    else LSI_BM64(q.z, q.w, a, b);
+    if ((k & 2u) == 0u) LSI_BM64(T, q.x, q.y, 1.0, a, b);
+    else LSI_BM64(T, q.z, q.w, 1.0, a, b);
     return (k & 1u) ? b : a;
 }
 
@@ -185,10 +191,10 @@ constexpr bool code_entry_valid(uint32_t code, int nops)
 
 template <int POT, uint32_t CODE, int NOPS>
 struct FusedStep {
-    // one application of the splitting; xi[] are this step's normals in substep order
+    // one application of the splitting; xi[] are this step's normals in substep order, already multiplied by b sigma
     template <int NO>
-    static __device__ __forceinline__ void run(double& x, double& v, double& f, double& heat, const ToyParams& P,
-                                               double half_m, const double (&xi)[NO])
+    static __device__ __forceinline__ void run(const fm::Tables& FT, double& x, double& v, double& f, double& heat,
+                                               const ToyParams& P, double half_m, const double (&xi)[NO])
     {
         bool valid = code_entry_valid(CODE, NOPS);  // folded at compile time after unrolling
         int o = 0;
@@ -200,13 +206,13 @@ struct FusedStep {
                 x = x + P.hR * v;
                 valid = false;
             } else if (kind == LSI_OP_V) {
-                if (!valid) f = force<POT>(x, P.p0);
+                if (!valid) f = force<POT>(FT, x, P.p0);
                 valid = true;
                 v = v + P.hV * f;
             } else {
                 // heat += m/2 (v_new^2 - v_old^2): three fp64 instructions instead of six
                 const double v_old2 = v * v;
-                v = fma(P.oa, v, P.oc * xi[o]);
+                v = fma(P.oa, v, xi[o]);
                 heat = fma(half_m, fma(v, v, -v_old2), heat);
                 ++o;
             }
@@ -215,7 +221,7 @@ struct FusedStep {
 };
 
 #ifndef LSI_TOY_MINB
-#define LSI_TOY_MINB 1
+#define LSI_TOY_MINB 4
 #endif
 template <int POT, uint32_t CODE, int NOPS, bool NOISE32>
 __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const __grid_constant__ ToyParams P)
@@ -223,6 +229,11 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
     constexpr int NO = code_count(CODE, NOPS, LSI_OP_O);  // normals per step
     constexpr int U = (NO == 0) ? 1 : ((4 % NO == 0) ? 4 / NO : 4);  // steps per noise refill when NO | 4
     constexpr bool ALIGNED = (NO > 0) && (4 % NO == 0);
+    __shared__ fm::Tables FT;
+#ifdef LSI_TOY_TABLES
+    fm::load_tables(FT);
+    __syncthreads();
+#endif
 
     const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool active = r < P.n;
@@ -232,14 +243,14 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
     if (active) {
         const uint64_t rid = P.replica0 + (uint64_t)r;
         double x = P.x0 ? P.x0[r] : P.x_cache[lsi::cache_index(P.seed, rid, P.n_cache)];
-        double v = P.v0 ? P.v0[r] : P.sigma * scalar_normal(P.seed, rid, LSI_TAG_V0, 0u);
+        double v = P.v0 ? P.v0[r] : P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_V0, 0u);
         double heat = 0.0;
         const double half_m = 0.5 * P.mass;
-        double f = code_entry_valid(CODE, NOPS) ? force<POT>(x, P.p0) : 0.0;
+        double f = code_entry_valid(CODE, NOPS) ? force<POT>(FT, x, P.p0) : 0.0;
 
         for (int leg = 0; leg < P.n_legs; ++leg) {
             if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
-                v = P.sigma * scalar_normal(P.seed, rid, LSI_TAG_VMID, (uint32_t)(leg - 1));
+                v = P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_VMID, (uint32_t)(leg - 1));
             const double E0 = potential<POT>(x, P.p0) + half_m * v * v;
             const double Q0 = heat;
             const uint32_t leg_base = (uint32_t)leg << 26;
@@ -250,25 +261,25 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
                 uint32_t blk = 0;
                 for (; s + U <= P.n_steps; s += U, ++blk) {
                     double n[4];
-                    normal_block<NOISE32>(P.seed, rid, leg_base | blk, LSI_TAG_O, n[0], n[1], n[2], n[3]);
+                    normal_block<NOISE32>(FT, P.keys, rid, leg_base | blk, LSI_TAG_O, P.oc, n[0], n[1], n[2], n[3]);
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         double xi[NO > 0 ? NO : 1];
 #pragma unroll
                         for (int o = 0; o < NO; ++o) xi[o] = n[u * NO + o];
-                        FusedStep<POT, CODE, NOPS>::run(x, v, f, heat, P, half_m, xi);
+                        FusedStep<POT, CODE, NOPS>::run(FT, x, v, f, heat, P, half_m, xi);
                     }
                 }
                 if (s < P.n_steps) {
                     double n[4];
-                    normal_block<NOISE32>(P.seed, rid, leg_base | blk, LSI_TAG_O, n[0], n[1], n[2], n[3]);
+                    normal_block<NOISE32>(FT, P.keys, rid, leg_base | blk, LSI_TAG_O, P.oc, n[0], n[1], n[2], n[3]);
 #pragma unroll
                     for (int u = 0; u < U - 1; ++u) {
                         if (s + u < P.n_steps) {
                             double xi[NO > 0 ? NO : 1];
 #pragma unroll
                             for (int o = 0; o < NO; ++o) xi[o] = n[u * NO + o];
-                            FusedStep<POT, CODE, NOPS>::run(x, v, f, heat, P, half_m, xi);
+                            FusedStep<POT, CODE, NOPS>::run(FT, x, v, f, heat, P, half_m, xi);
                         }
                     }
                 }
@@ -281,11 +292,11 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
 #pragma unroll
                     for (int o = 0; o < NO; ++o) {
                         const uint32_t lane = q & 3u;
-                        if (lane == 0u) normal_block<NOISE32>(P.seed, rid, leg_base | (q >> 2), LSI_TAG_O, n0, n1, n2, n3);
+                        if (lane == 0u) normal_block<NOISE32>(FT, P.keys, rid, leg_base | (q >> 2), LSI_TAG_O, P.oc, n0, n1, n2, n3);
                         xi[o] = lane == 0u ? n0 : (lane == 1u ? n1 : (lane == 2u ? n2 : n3));
                         ++q;
                     }
-                    FusedStep<POT, CODE, NOPS>::run(x, v, f, heat, P, half_m, xi);
+                    FusedStep<POT, CODE, NOPS>::run(FT, x, v, f, heat, P, half_m, xi);
                 }
             }
 
@@ -316,6 +327,11 @@ template <int POT, bool DIRECT, bool TRACE, bool EXT, bool NOISE32>
 __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_constant__ ToyProgram prog,
                                                                 const __grid_constant__ ToyParams P)
 {
+    __shared__ fm::Tables FT;
+#ifdef LSI_TOY_TABLES
+    fm::load_tables(FT);
+    __syncthreads();
+#endif
     const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool active = r < P.n;
     double wF = 0.0, wR = 0.0;
@@ -324,14 +340,14 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
     if (active) {
         const uint64_t rid = P.replica0 + (uint64_t)r;
         double x = P.x0 ? P.x0[r] : P.x_cache[lsi::cache_index(P.seed, rid, P.n_cache)];
-        double v = P.v0 ? P.v0[r] : P.sigma * scalar_normal(P.seed, rid, LSI_TAG_V0, 0u);
+        double v = P.v0 ? P.v0[r] : P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_V0, 0u);
         double heat = 0.0;
         const double half_m = 0.5 * P.mass;
         const int64_t T = (int64_t)P.n_steps + 1;
 
         for (int leg = 0; leg < P.n_legs; ++leg) {
             if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
-                v = P.sigma * scalar_normal(P.seed, rid, LSI_TAG_VMID, (uint32_t)(leg - 1));
+                v = P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_VMID, (uint32_t)(leg - 1));
             const double E0 = potential<POT>(x, P.p0) + half_m * v * v;
             const double Q0 = heat;
             const uint32_t leg_base = (uint32_t)leg << 26;
@@ -358,12 +374,12 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
                         }
                     } else if (kind == LSI_OP_V) {
                         const double v_old = v;
-                        v = v + c0 * force<POT>(x, P.p0);
+                        v = v + c0 * force<POT>(FT, x, P.p0);
                         if (DIRECT) wd += half_m * v * v - half_m * v_old * v_old;
                     } else {
                         const double c1 = ProgRead<EXT>::c1(prog, i);
                         const uint32_t lane = q & 3u;
-                        if (lane == 0u) normal_block<NOISE32>(P.seed, rid, leg_base | (q >> 2), LSI_TAG_O, n0, n1, n2, n3);
+                        if (lane == 0u) normal_block<NOISE32>(FT, P.keys, rid, leg_base | (q >> 2), LSI_TAG_O, 1.0, n0, n1, n2, n3);
                         ++q;
                         const double xi = lane == 0u ? n0 : (lane == 1u ? n1 : (lane == 2u ? n2 : n3));
                         const double ke_old = half_m * v * v;
@@ -556,6 +572,7 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
 
     ToyParams P;
     P.seed = a->seed; P.replica0 = a->replica0; P.n = a->n_replicas;
+    P.keys = lsi::philox_round_keys(a->seed);
     P.n_steps = a->n_steps; P.n_legs = a->n_legs; P.marginal = a->marginal;
     P.mass = sys->mass; P.kT = a->kT; P.inv_kT = 1.0 / a->kT; P.sigma = sigma; P.p0 = sys->params[0];
     P.hR = P.hV = P.oa = P.oc = 0.0;

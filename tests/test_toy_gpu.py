@@ -286,3 +286,24 @@ def test_fastmath_accuracy(ib):
     assert np.abs(s - np.sin(th)).max() < 3e-16 and np.abs(c - np.cos(th)).max() < 3e-16
     d0, d1 = run(6, words, two=True)  # lean minus library normals
     assert np.abs(d0).max() < 2e-14 and np.abs(d1).max() < 2e-14
+    # table-driven versions (what the toy kernels use): -2 log(u) to 2 ulp, sincos to 3e-16 absolute
+    got = run(7, u1)
+    sample = np.concatenate([idx, np.argsort(u1)[:50], np.argsort(u1)[-50:], np.argsort(np.abs(u1 - 0.685))[:50],
+                             np.argsort(np.abs(u1 - 0.5))[:50]])
+    ref_l = np.array([float(-2 * mpmath.log(mpmath.mpf(float(u1[i])))) for i in sample])
+    assert ulps(got[sample], ref_l).max() <= 2.0
+    assert ulps(got, -2.0 * np.log(u1)).max() <= 3.0
+    near_one = 1.0 - np.ldexp(rng.uniform(0.5, 1.0, 2000), rng.randint(-33, -1, 2000))  # u close to 1: result tiny
+    ref_n = np.array([float(-2 * mpmath.log(mpmath.mpf(float(v)))) for v in near_one])
+    assert ulps(run(7, near_one), ref_n).max() <= 2.0
+    s, c = run(8, words, two=True)
+    ref_s = np.array([float(mpmath.sin(mpmath.pi * mpmath.mpf(float(u2[i])))) for i in idx])
+    ref_c = np.array([float(mpmath.cos(mpmath.pi * mpmath.mpf(float(u2[i])))) for i in idx])
+    assert np.abs(s[idx] - ref_s).max() < 3e-16 and np.abs(c[idx] - ref_c).max() < 3e-16
+    assert np.abs(s - np.sin(np.pi * u2)).max() < 1.5e-15 and np.abs(s * s + c * c - 1.0).max() < 6e-16
+    sub = th[:3000]
+    ref_t = np.array([float(mpmath.sin(mpmath.mpf(float(a)))) for a in sub])
+    assert np.abs(run(10, sub) - ref_t).max() < 3e-16 and np.abs(run(10, th) - np.sin(th)).max() < 4e-16
+    assert ulps(run(11, pos), np.sqrt(pos)).max() <= 2.0
+    d0, d1 = run(9, words, two=True)  # table-driven minus library normals
+    assert np.abs(d0).max() < 2e-14 and np.abs(d1).max() < 2e-14
