@@ -233,6 +233,19 @@ __device__ __forceinline__ double sin_tab(const Tables& T, double x)
     return fma(e.x, cm, fma(e.y, sd, e.x));
 }
 
+// cos(x) likewise
+__device__ __forceinline__ double cos_tab(const Tables& T, double x)
+{
+    const double t0 = fma(x, kL2[8], kMisc[7]);
+    const double2 e = T.tr[__double2loint(t0) & 1023];
+    const double nd = t0 - kMisc[7];
+    double d = fma(-nd, kL2[9], x);
+    d = fma(-nd, kL2[10], d);
+    double sd, cm;
+    sincos_tiny(d, sd, cm);
+    return fma(e.y, cm, fma(-e.x, sd, e.y));
+}
+
 // sqrt of a positive normal number in five instructions: with e = 1 - x y^2 for the hardware seed y (|e| < 2^-22),
 // sqrt x = x y (1 + e/2 + 3 e^2/8 + O(e^3)); `scale` multiplies the result (the O substep's b sigma)
 __device__ __forceinline__ double sqrt_pos_scaled(double x, double scale)

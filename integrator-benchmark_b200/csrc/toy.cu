@@ -67,7 +67,7 @@ struct ToyParams {
 };
 
 template <int POT>
-__device__ __forceinline__ double potential(double x, double p0)
+__device__ __forceinline__ double potential(const fm::Tables& T, double x, double p0)
 {
     if (POT == LSI_POT_QUARTIC) {
         const double x2 = x * x;
@@ -76,10 +76,12 @@ __device__ __forceinline__ double potential(double x, double p0)
         const double x2 = x * x;
 #ifdef LSI_TOY_LIBM
         return x2 * x2 * x2 + 2.0 * cos(5.0 * (x + 1.0));
-#else
+#elif defined(LSI_TOY_POLY)
         double s, c;
         fm::sincos_medium(fma(5.0, x, 5.0), s, c);
         return fma(x2 * x2, x2, 2.0 * c);
+#else
+        return fma(x2 * x2, x2, 2.0 * fm::cos_tab(T, fma(5.0, x, 5.0)));
 #endif
     } else {
         return 0.5 * p0 * x * x;
@@ -247,11 +249,12 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
         double heat = 0.0;
         const double half_m = 0.5 * P.mass;
         double f = code_entry_valid(CODE, NOPS) ? force<POT>(FT, x, P.p0) : 0.0;
+        double pe = potential<POT>(FT, x, P.p0);  // x does not move between the legs: one evaluation per leg boundary
 
         for (int leg = 0; leg < P.n_legs; ++leg) {
             if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
                 v = P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_VMID, (uint32_t)(leg - 1));
-            const double E0 = potential<POT>(x, P.p0) + half_m * v * v;
+            const double E0 = pe + half_m * v * v;
             const double Q0 = heat;
             const uint32_t leg_base = (uint32_t)leg << 26;
 
@@ -300,7 +303,8 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
                 }
             }
 
-            const double E1 = potential<POT>(x, P.p0) + half_m * v * v;
+            pe = potential<POT>(FT, x, P.p0);
+            const double E1 = pe + half_m * v * v;
             const double w = ((E1 - E0) - (heat - Q0)) * P.inv_kT;
             P.W[(int64_t)leg * P.n + r] = w;
             if (P.heat) P.heat[(int64_t)leg * P.n + r] = heat - Q0;
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
         for (int leg = 0; leg < P.n_legs; ++leg) {
             if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
                 v = P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_VMID, (uint32_t)(leg - 1));
-            const double E0 = potential<POT>(x, P.p0) + half_m * v * v;
+            const double E0 = potential<POT>(FT, x, P.p0) + half_m * v * v;
             const double Q0 = heat;
             const uint32_t leg_base = (uint32_t)leg << 26;
             double wd = 0.0;
@@ -366,9 +370,9 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
                     const double c0 = ProgRead<EXT>::c0(prog, i);
                     if (kind == LSI_OP_R) {
                         if (DIRECT) {
-                            const double pe_old = potential<POT>(x, P.p0);
+                            const double pe_old = potential<POT>(FT, x, P.p0);
                             x = x + c0 * v;
-                            wd += potential<POT>(x, P.p0) - pe_old;
+                            wd += potential<POT>(FT, x, P.p0) - pe_old;
                         } else {
                             x = x + c0 * v;
                         }
@@ -392,12 +396,12 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
                     if (P.trace_x) P.trace_x[idx] = x;
                     if (P.trace_v) P.trace_v[idx] = v;
                     if (P.trace_w) {
-                        const double E = potential<POT>(x, P.p0) + half_m * v * v;
+                        const double E = potential<POT>(FT, x, P.p0) + half_m * v * v;
                         P.trace_w[idx] = ((E - E0) - (heat - Q0)) * P.inv_kT;
                     }
                 }
             }
-            const double E1 = potential<POT>(x, P.p0) + half_m * v * v;
+            const double E1 = potential<POT>(FT, x, P.p0) + half_m * v * v;
             const double w = ((E1 - E0) - (heat - Q0)) * P.inv_kT;
             P.W[(int64_t)leg * P.n + r] = w;
             if (P.heat) P.heat[(int64_t)leg * P.n + r] = heat - Q0;
@@ -417,6 +421,11 @@ __global__ void __launch_bounds__(kThreads) toy_metropolis_kernel(uint64_t seed,
                                                                   int n_burn, double inv_kT, double p0,
                                                                   double* __restrict__ x_out)
 {
+    __shared__ fm::Tables FT;
+#ifdef LSI_TOY_TABLES
+    fm::load_tables(FT);
+    __syncthreads();
+#endif
     const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (c >= n) return;
     const uint64_t rid = replica0 + (uint64_t)c;
@@ -426,13 +435,13 @@ __global__ void __launch_bounds__(kThreads) toy_metropolis_kernel(uint64_t seed,
         lsi::box_muller(q.x, q.y, n0, n1);
     }
     double x = n0;
-    double u_x = potential<POT>(x, p0);
+    double u_x = potential<POT>(FT, x, p0);
     for (int i = 1; i <= n_burn; ++i) {
         const lsi::Philox4 q = lsi::philox_block(seed, rid, (uint32_t)i, LSI_TAG_EQ, 0u);
         lsi::box_muller(q.x, q.y, n0, n1);
         const double accept_eps = ((double)q.z + 0.5) * 2.3283064365386962890625e-10;
         const double x_prop = x + n0;
-        const double u_prop = potential<POT>(x_prop, p0);
+        const double u_prop = potential<POT>(FT, x_prop, p0);
         if (exp(-(u_prop - u_x) * inv_kT) > accept_eps) { x = x_prop; u_x = u_prop; }
     }
     x_out[c] = x;
