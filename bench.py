@@ -447,7 +447,8 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "double", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "ours" and args.warmup:
+        args.warmup = max(args.warmup, 3)  # timing rule: at least three warm-up steps
     if args.workload != "double_well":
         args.steps, args.warmup = args.steps or 4, args.warmup or 3
         return run_particles(args)
@@ -642,14 +643,15 @@ def main():
         pass
     hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
     roofline = {
-        "bound": "fp64_fma", "kernel": "toy_protocol_kernel<double_well>", "achieved": achieved, "peak": peaks["fp64"],
+        "bound": "fp64_fma", "kernel": "toy_fused_kernel<double_well, splitting>", "achieved": achieved, "peak": peaks["fp64"],
         "unit": "TFLOP/s", "frac": achieved / peaks["fp64"],
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of toy_fused_kernel, ncu --set full
         # (profiles/r1_toy_fused_ncu_details.txt): the 8 MB equilibrium cache is read once, the works stay in L2
         "traffic": 8.04e6 if n == (1 << 20) else None,
         "peak_source": "lsi_microbench_fma fp64, best of 6, measured in this run (fp32: %.1f TFLOP/s)" % peaks["fp32"],
-        "note": "algorithmic flops exclude the Philox + Box-Muller noise generation that dominates issue slots "
-                "(n_O Gaussians per replica-step); see profiles/ for sm__inst_executed and pipe utilisation",
+        "note": "algorithmic flops exclude the Philox + Box-Muller noise generation that dominates the instruction count "
+                "(n_O Gaussians per replica-step); ncu (profiles/r1_ncu_summary.json): issue slots 64 % + FP64 pipe 53 % / 2 "
+                "= 91 % of the dispatch limit of the 16-lane fp64 sub-partitions",
         "replica_steps_per_s_kernel_only": len(SPLITTINGS) * n * 2 * steps_per_leg / kernel_s,
         "kernel_ms_per_splitting": kernel_ms,
         "flops_per_replica_step": {k: flops_per_step(s) for k, s in SPLITTINGS.items()},
@@ -659,9 +661,12 @@ def main():
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, secs = cpu_port_throughput(args.ref_replicas * 2, args.protocol_length)
+        _, warm = cpu_port_throughput(args.ref_replicas * 2, args.protocol_length)        # also warms the thread pool
+        repeats = int(min(64, max(1, round(10.0 / max(warm, 1e-3)))))                     # about 10 s of CPU work
+        v, secs = cpu_port_throughput(args.ref_replicas * 2, args.protocol_length, repeats=repeats)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": "%d replicas x 6 splittings (1 pass, %.1f s, OpenMP over replicas)" % (args.ref_replicas * 2, secs)}
+               "sample": "%d replicas x 6 splittings x %d passes (%.1f s, OpenMP over replicas)"
+                         % (args.ref_replicas * 2, repeats, secs)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
