@@ -189,6 +189,47 @@ def estimate_kl_div_adaptive_outer_loop(noneq_sim, marginal, outer_sample_fxn, n
     return result
 
 
+def estimate_kl_div_adaptive_outer_loop_sharded(noneq_sim, marginal, outer_sample_fxn, n_steps=1000, initial_size=100,
+                                                batch_size=1, threshold=0.1, max_samples=1000, return_samples=False):
+    """The adaptive outer loop with the OUTER samples sharded over the ranks of torch.distributed (one process per
+    GPU; every rank runs its own inner ensembles on its own device).  Rank r starts with its share of
+    `initial_size` (parallel.shard_range) and adds `batch_size` samples per round; the stopping rule of
+    estimate_kl_div_adaptive_outer_loop (:257-290) is evaluated on the union through one all-reduce of
+    (n, sum, sum of squares) of the per-sample estimates per round -- 24 bytes -- so all ranks stop together.
+    Returns the global estimate and stdev, the global sample count, and this rank's Ws / samples."""
+    import torch
+    import torch.distributed as dist
+    from .. import parallel
+    rank, world, _ = parallel.world()
+    on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    device = "cuda" if (on and dist.get_backend() == "nccl") else "cpu"
+    collect = lambda: outer_sample_fxn(noneq_sim=noneq_sim, marginal=marginal, n_steps=n_steps)  # noqa: E731
+    lo, hi = parallel.shard_range(initial_size, rank, world)
+    outer_samples = [collect() for _ in range(hi - lo)]
+
+    def global_stats():
+        e = np.array([s["estimate"] for s in outer_samples], dtype=np.float64)
+        m = torch.tensor([float(len(e)), e.sum(), (e * e).sum()], dtype=torch.float64, device=device)
+        if on:
+            dist.all_reduce(m, op=dist.ReduceOp.SUM)
+        n, s1, s2 = (float(v) for v in m.cpu())
+        mean = s1 / n
+        var = max(s2 / n - (s1 / n) ** 2, 0.0)  # np.std, ddof = 0
+        return int(n), mean, float(np.sqrt(var) / np.sqrt(n))
+    n, mean, sd = global_stats()
+    while sd > threshold and n <= max_samples - batch_size * world:
+        for _ in range(batch_size):
+            outer_samples.append(collect())
+        n, mean, sd = global_stats()
+    if sd > threshold and rank == 0:
+        warnings.warn("stdev_kl_div(outer_samples) > threshold\n({:.3f} > {:.3f})".format(sd, threshold), RuntimeWarning)
+    result = {"new_estimate": mean, "stdev": sd, "n_outer_samples": n,
+              "Ws": np.array([s["Ws"] for s in outer_samples], dtype=object)}
+    if return_samples:
+        result["samples"] = outer_samples
+    return result
+
+
 def resample_Ws(Ws):
     """One two-level bootstrap sample of the ragged Ws structure on the host, as the reference (:293-320)."""
     Ws = np.asarray(Ws, dtype=object) if not isinstance(Ws, np.ndarray) else Ws

@@ -65,6 +65,51 @@ def test_gloo_world2_matches_single_process(tmp_path):
     assert (got[0][6], got[0][7], got[1][6], got[1][7]) == (0, 501, 501, 1001)
 
 
+def _fake_outer_sample(noneq_sim=None, marginal=None, n_steps=None):
+    """stands in for outer_sample_adaptive: a deterministic per-rank stream of estimates, no GPU"""
+    st = noneq_sim
+    est = st["values"][st["next"]]
+    st["next"] += 1
+    return {"estimate": float(est), "Ws": np.array([est, est])}
+
+
+def _nested_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from integrator_benchmark_b200 import parallel
+    from integrator_benchmark_b200.evaluation import compare_near_eq_and_exact as nested
+    parallel.init_process_group(backend="gloo")
+    values = np.random.RandomState(100 + rank).randn(500) * 0.8 + 0.3
+    state = {"values": values, "next": 0}
+    res = nested.estimate_kl_div_adaptive_outer_loop_sharded(state, "full", _fake_outer_sample, initial_size=11, batch_size=2,
+                                                             threshold=0.05, max_samples=900)
+    np.save(os.path.join(out_dir, "n%d.npy" % rank), np.array([res["new_estimate"], res["stdev"], res["n_outer_samples"],
+                                                                 state["next"], len(res["Ws"])]))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_nested_outer_loop_stops_together(tmp_path):
+    """outer samples sharded over two ranks: both stop in the same round, on the statistics of the union"""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_nested_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(os.path.join(str(tmp_path), "n%d.npy" % r)) for r in range(2)]
+    assert got[0][2] == got[1][2] and got[0][0] == got[1][0] and got[0][1] == got[1][1]
+    n0, n1 = int(got[0][3]), int(got[1][3])
+    assert n0 + n1 == int(got[0][2]) and (n0 - 6) == (n1 - 5) and (n0 - 6) % 2 == 0  # 6 + 5 initial, then 2 per round each
+    vals = np.concatenate([np.random.RandomState(100).randn(500)[:n0] * 0.8 + 0.3,
+                           np.random.RandomState(101).randn(500)[:n1] * 0.8 + 0.3])
+    assert got[0][0] == pytest.approx(vals.mean(), rel=1e-12)
+    assert got[0][1] == pytest.approx(vals.std() / np.sqrt(len(vals)), rel=1e-9)
+    assert got[0][1] <= 0.05
+    # one round earlier the rule had not been met
+    prev = np.concatenate([np.random.RandomState(100).randn(500)[:n0 - 2] * 0.8 + 0.3,
+                           np.random.RandomState(101).randn(500)[:n1 - 2] * 0.8 + 0.3])
+    assert prev.std() / np.sqrt(len(prev)) > 0.05
+
+
 def test_shard_ranges_partition():
     sys.path.insert(0, ROOT)
     from integrator_benchmark_b200 import parallel
