@@ -294,7 +294,9 @@ int lsi_microbench_fma(int precision, int64_t iters, int blocks, void* sink, voi
 /* Test hook (no reference counterpart): evaluates the lean fp64 functions the toy kernels use for Box-Muller noise
  * and the double-well force (csrc/fastmath64.cuh) element-wise on x[n]: which = 0 log, 1 sincos(pi x) for 0 <= x < 4,
  * 2 sincos(x), 3 sqrt, 4 reciprocal, 5 the two uniforms made from the 32-bit word x, 6 lean minus library Box-Muller
- * normals made from the word x.  out1 may be NULL.  Device pointers. */
+ * normals made from the word x; the table-driven versions the kernels run: 7 -2 log(x), 8 sincos(2 pi (x + 1/2) / 2^32)
+ * for the word x, 9 table-driven minus library Box-Muller normals, 10 sin(x), 11 five-instruction sqrt.
+ * out1 may be NULL.  Device pointers. */
 int lsi_test_fastmath(int which, int64_t n, const double* x, double* out0, double* out1, void* stream);
 
 #ifdef __cplusplus
