@@ -201,6 +201,13 @@ int lsi_system_num_dof(const lsi_system* s);
 /* flags: positions pass through a float32 frame at the midpoint, as the reference's mdtraj
  * round trip does (bookkeepers.py:266,298-305).  Particle systems only. */
 #define LSI_FLAG_ROUND_MIDPOINT_X_FP32 1
+/* scalar systems: traces in the reference's own layout (low_dimensional_systems.py:160-184 returns arrays of shape
+ * (n, n_steps) and (n, n_steps, 2)): trace_w is [leg][replica][step], trace_x holds (x, v) pairs
+ * [leg][replica][step][2] and trace_v is not used.  Default layout: [leg][step][replica] for each of the three. */
+#define LSI_FLAG_TRACE_REPLICA_MAJOR 2
+/* scalar systems: default [leg][step][replica] order, but trace_x holds (x, v) pairs [leg][step][replica][2]
+ * (trace_v not used): coalesced stores, and a transposed VIEW of it has the reference's shape (n, n_steps, 2). */
+#define LSI_FLAG_TRACE_XV_PAIRS 4
 typedef struct lsi_protocol_args {
     uint64_t seed;
     uint64_t replica0;

@@ -63,8 +63,26 @@ struct ToyParams {
     const double* x0;
     const double* v0;
     double *W, *heat, *W_direct, *x_final, *v_final, *trace_x, *trace_v, *trace_w;
+    int trace_rm;      // 1: traces replica-major, trace_w [leg][r][step], trace_x = (x, v) pairs [leg][r][step][2]
+                       // 2: step-major, trace_x = (x, v) pairs [leg][step][r][2]
     double* partials;  // [gridDim.x][8]
 };
+
+// one trace record of replica r at step index s (0 = start of the leg) of `leg`; T = n_steps + 1
+__device__ __forceinline__ void store_trace(const ToyParams& P, int leg, int64_t T, int64_t s, int64_t r, double x, double v,
+                                            double w)
+{
+    if (P.trace_rm) {
+        const int64_t idx = P.trace_rm == 1 ? ((int64_t)leg * P.n + r) * T + s : ((int64_t)leg * T + s) * P.n + r;
+        if (P.trace_x) reinterpret_cast<double2*>(P.trace_x)[idx] = make_double2(x, v);
+        if (P.trace_w) P.trace_w[idx] = w;
+    } else {
+        const int64_t idx = ((int64_t)leg * T + s) * P.n + r;
+        if (P.trace_x) P.trace_x[idx] = x;
+        if (P.trace_v) P.trace_v[idx] = v;
+        if (P.trace_w) P.trace_w[idx] = w;
+    }
+}
 
 template <int POT>
 __device__ __forceinline__ double potential(const fm::Tables& T, double x, double p0)
@@ -225,7 +243,7 @@ struct FusedStep {
 #ifndef LSI_TOY_MINB
 #define LSI_TOY_MINB 4
 #endif
-template <int POT, uint32_t CODE, int NOPS, bool NOISE32>
+template <int POT, uint32_t CODE, int NOPS, bool NOISE32, bool TRACE = false>
 __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const __grid_constant__ ToyParams P)
 {
     constexpr int NO = code_count(CODE, NOPS, LSI_OP_O);  // normals per step
@@ -257,6 +275,13 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
             const double E0 = pe + half_m * v * v;
             const double Q0 = heat;
             const uint32_t leg_base = (uint32_t)leg << 26;
+            const int64_t T = (int64_t)P.n_steps + 1;
+            // cumulative work after a step, for the traces (one extra potential evaluation per step)
+            auto record = [&](int64_t s_done) {
+                const double w = P.trace_w ? ((potential<POT>(FT, x, P.p0) + half_m * v * v - E0) - (heat - Q0)) * P.inv_kT : 0.0;
+                store_trace(P, leg, T, s_done, r, x, v, w);
+            };
+            if (TRACE) store_trace(P, leg, T, 0, r, x, v, 0.0);
 
             if (ALIGNED) {
                 // one Philox block feeds exactly U steps: every lane index is a constant
@@ -271,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
 #pragma unroll
                         for (int o = 0; o < NO; ++o) xi[o] = n[u * NO + o];
                         FusedStep<POT, CODE, NOPS>::run(FT, x, v, f, heat, P, half_m, xi);
+                        if (TRACE) record(s + u + 1);
                     }
                 }
                 if (s < P.n_steps) {
@@ -283,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
 #pragma unroll
                             for (int o = 0; o < NO; ++o) xi[o] = n[u * NO + o];
                             FusedStep<POT, CODE, NOPS>::run(FT, x, v, f, heat, P, half_m, xi);
+                            if (TRACE) record(s + u + 1);
                         }
                     }
                 }
@@ -300,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
                         ++q;
                     }
                     FusedStep<POT, CODE, NOPS>::run(FT, x, v, f, heat, P, half_m, xi);
+                    if (TRACE) record(s + 1);
                 }
             }
 
@@ -358,12 +386,7 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
             double wd = 0.0;
             uint32_t q = 0;  // O draws so far in this leg (warp-uniform)
             double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-            if (TRACE) {
-                const int64_t base = ((int64_t)leg * T) * P.n + r;
-                if (P.trace_x) P.trace_x[base] = x;
-                if (P.trace_v) P.trace_v[base] = v;
-                if (P.trace_w) P.trace_w[base] = 0.0;
-            }
+            if (TRACE) store_trace(P, leg, T, 0, r, x, v, 0.0);
             for (int s = 0; s < P.n_steps; ++s) {
                 for (int i = 0; i < prog.n_ops; ++i) {
                     const int kind = ProgRead<EXT>::kind(prog, i);
@@ -392,13 +415,8 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
                     }
                 }
                 if (TRACE) {
-                    const int64_t idx = ((int64_t)leg * T + s + 1) * P.n + r;
-                    if (P.trace_x) P.trace_x[idx] = x;
-                    if (P.trace_v) P.trace_v[idx] = v;
-                    if (P.trace_w) {
-                        const double E = potential<POT>(FT, x, P.p0) + half_m * v * v;
-                        P.trace_w[idx] = ((E - E0) - (heat - Q0)) * P.inv_kT;
-                    }
+                    const double w = P.trace_w ? ((potential<POT>(FT, x, P.p0) + half_m * v * v - E0) - (heat - Q0)) * P.inv_kT : 0.0;
+                    store_trace(P, leg, T, s + 1, r, x, v, w);
                 }
             }
             const double E1 = potential<POT>(FT, x, P.p0) + half_m * v * v;
@@ -495,12 +513,14 @@ constexpr int slen(const char* s)
     X("OVRRVO") X("VROORV") X("RVOOVR") X("RVO") X("ROV") X("VRRORRV") X("VRRRORRRV")
 
 template <int POT, bool NOISE32>
-bool launch_fused2(uint32_t code, int nops, const ToyParams& P, cudaStream_t st, cudaError_t* err)
+bool launch_fused2(uint32_t code, int nops, bool trace, const ToyParams& P, cudaStream_t st, cudaError_t* err)
 {
     const unsigned grid = (unsigned)((P.n + kThreads - 1) / kThreads);
+    if (trace && NOISE32) return false;  // traced mixed-precision runs go through the interpreter
 #define X(S)                                                                                       \
     if (nops == slen(S) && code == pack(S)) {                                                      \
-        toy_fused_kernel<POT, pack(S), slen(S), NOISE32><<<grid, kThreads, 0, st>>>(P);            \
+        if (trace) toy_fused_kernel<POT, pack(S), slen(S), false, true><<<grid, kThreads, 0, st>>>(P);  \
+        else toy_fused_kernel<POT, pack(S), slen(S), NOISE32><<<grid, kThreads, 0, st>>>(P);       \
         *err = cudaGetLastError();                                                                 \
         return true;                                                                               \
     }
@@ -509,19 +529,19 @@ bool launch_fused2(uint32_t code, int nops, const ToyParams& P, cudaStream_t st,
     return false;
 }
 
-bool launch_fused(int pot, bool noise32, uint32_t code, int nops, const ToyParams& P, cudaStream_t st,
+bool launch_fused(int pot, bool noise32, uint32_t code, int nops, bool trace, const ToyParams& P, cudaStream_t st,
                   cudaError_t* err)
 {
     switch (pot) {
     case LSI_POT_QUARTIC:
-        return noise32 ? launch_fused2<LSI_POT_QUARTIC, true>(code, nops, P, st, err)
-                       : launch_fused2<LSI_POT_QUARTIC, false>(code, nops, P, st, err);
+        return noise32 ? launch_fused2<LSI_POT_QUARTIC, true>(code, nops, trace, P, st, err)
+                       : launch_fused2<LSI_POT_QUARTIC, false>(code, nops, trace, P, st, err);
     case LSI_POT_DOUBLE_WELL:
-        return noise32 ? launch_fused2<LSI_POT_DOUBLE_WELL, true>(code, nops, P, st, err)
-                       : launch_fused2<LSI_POT_DOUBLE_WELL, false>(code, nops, P, st, err);
+        return noise32 ? launch_fused2<LSI_POT_DOUBLE_WELL, true>(code, nops, trace, P, st, err)
+                       : launch_fused2<LSI_POT_DOUBLE_WELL, false>(code, nops, trace, P, st, err);
     default:
-        return noise32 ? launch_fused2<LSI_POT_HARMONIC, true>(code, nops, P, st, err)
-                       : launch_fused2<LSI_POT_HARMONIC, false>(code, nops, P, st, err);
+        return noise32 ? launch_fused2<LSI_POT_HARMONIC, true>(code, nops, trace, P, st, err)
+                       : launch_fused2<LSI_POT_HARMONIC, false>(code, nops, trace, P, st, err);
     }
 }
 
@@ -588,6 +608,8 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
     P.x_cache = a->x_cache; P.n_cache = a->n_cache; P.x0 = a->x0; P.v0 = a->v0;
     P.W = a->W; P.heat = a->heat; P.W_direct = a->W_direct; P.x_final = a->x_final; P.v_final = a->v_final;
     P.trace_x = a->trace_x; P.trace_v = a->trace_v; P.trace_w = a->trace_w;
+    P.trace_rm = (a->flags & LSI_FLAG_TRACE_REPLICA_MAJOR) ? 1 : ((a->flags & LSI_FLAG_TRACE_XV_PAIRS) ? 2 : 0);
+    if (P.trace_rm && a->trace_v) return lsi_set_error(LSI_ERR_ARG, "these trace layouts keep (x, v) pairs in trace_x; trace_v must be NULL");
     P.partials = nullptr;
     const int64_t grid = (a->n_replicas + kThreads - 1) / kThreads;
     if (a->moments) {
@@ -603,7 +625,7 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
     // ---- fused path: every substep of a kind has the same length (true for lsi_compile output)
     bool launched = false;
     cudaError_t err = cudaSuccess;
-    if (!direct && !trace && n_ops <= 16) {
+    if (!direct && n_ops <= 16) {
         uint32_t code = 0;
         bool uniform = true;
         double fr[3] = {-1, -1, -1}, oa = 0, ob = 0;
@@ -621,7 +643,7 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
             P.hR = prog->dt * (fr[LSI_OP_R] > 0 ? fr[LSI_OP_R] : 0.0);
             P.hV = prog->dt * (fr[LSI_OP_V] > 0 ? fr[LSI_OP_V] : 0.0) / sys->mass;
             P.oa = oa; P.oc = ob * sigma;
-            launched = launch_fused(sys->potential, noise32, code, n_ops, P, st, &err);
+            launched = launch_fused(sys->potential, noise32, code, n_ops, trace, P, st, &err);
         }
     }
 

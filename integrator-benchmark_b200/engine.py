@@ -54,7 +54,7 @@ class Program:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:  # module globals may already be gone at interpreter shutdown
             lib.lsi_program_destroy(h)
 
     @property
@@ -100,7 +100,7 @@ class ScalarSystem:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:
             lib.lsi_system_destroy(h)
 
     @property
@@ -189,7 +189,7 @@ class ParticleSystem:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:
             lib.lsi_system_destroy(h)
 
     @property
@@ -239,7 +239,10 @@ def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configurati
     """One launch of the whole protocol for `n_replicas` replicas (lsi_run_protocol).
 
     Tensors in/out are float64 CUDA tensors; outputs are leg-major: W[leg, replica],
-    traces [leg, step, replica(, dof)].  Returns a dict of tensors (no host sync)."""
+    traces [leg, step, replica(, dof)].  traces="replica_major" (scalar systems) gives the reference's own layout instead:
+    trace_w_rm [leg, replica, step] and trace_xv_rm [leg, replica, step, 2]; traces="pairs" keeps the coalesced step-major
+    order with (x, v) interleaved, trace_xv [leg, step, replica, 2] (a permuted view of it has the reference's shape).
+    Returns a dict of tensors (no host sync)."""
     require_cuda()
     t = torch()
     dev = t.device("cuda", t.cuda.current_device()) if device is None else t.device(device)
@@ -282,7 +285,19 @@ def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configurati
     if want_final:
         a.x_final = _ptr(buf("x_final", *state_shape))
         a.v_final = _ptr(buf("v_final", *state_shape))
-    if traces:
+    if traces == "replica_major":
+        if not scalar:
+            raise ValueError("replica-major traces are a scalar-system layout")
+        a.flags |= 2  # LSI_FLAG_TRACE_REPLICA_MAJOR
+        a.trace_x = _ptr(buf("trace_xv_rm", n_legs, n, n_steps + 1, 2))
+        a.trace_w = _ptr(buf("trace_w_rm", n_legs, n, n_steps + 1))
+    elif traces == "pairs":
+        if not scalar:
+            raise ValueError("(x, v)-pair traces are a scalar-system layout")
+        a.flags |= 4  # LSI_FLAG_TRACE_XV_PAIRS
+        a.trace_x = _ptr(buf("trace_xv", n_legs, n_steps + 1, n, 2))
+        a.trace_w = _ptr(buf("trace_w", n_legs, n_steps + 1, n))
+    elif traces:
         tshape = (n_legs, n_steps + 1, n) if scalar else (n_legs, n_steps + 1, n, dof // 3, 3)
         a.trace_x = _ptr(buf("trace_x", *tshape))
         a.trace_v = _ptr(buf("trace_v", *tshape))

@@ -119,16 +119,17 @@ class NumbaNonequilibriumSimulator:
             raise NotImplementedError("`marginal` must be either 'configuration' or 'full'")
         integ, gamma, dt = self._unwrap()
         res = integ.ensemble(n_protocol_samples, protocol_length, gamma, dt, marginal=marginal,
-                             x_cache=self.equilibrium_simulator.x_samples_device(), traces=traces, seed=seed,
-                             out=self._buffers)
+                             x_cache=self.equilibrium_simulator.x_samples_device(), seed=seed,
+                             traces="pairs" if traces else False, out=self._buffers)
         self.last_moments = res.get("moments")
         if traces:
+            # the kernel stores step-major (coalesced); the reference's shapes (n, protocol_length) and
+            # (n, protocol_length, 2) are permuted views of those buffers, no extra pass over the traces
             kT = integ.kT
-            W_F = res["trace_w"][0].transpose(0, 1) * kT
-            W_R = res["trace_w"][1].transpose(0, 1) * kT
-            t = engine.torch()
-            xv_F = t.stack([res["trace_x"][0].transpose(0, 1), res["trace_v"][0].transpose(0, 1)], dim=-1)
-            xv_R = t.stack([res["trace_x"][1].transpose(0, 1), res["trace_v"][1].transpose(0, 1)], dim=-1)
+            W_F, W_R = res["trace_w"][0].transpose(0, 1), res["trace_w"][1].transpose(0, 1)
+            if kT != 1.0:
+                W_F, W_R = W_F * kT, W_R * kT
+            xv_F, xv_R = res["trace_xv"][0].permute(1, 0, 2), res["trace_xv"][1].permute(1, 0, 2)
         else:
             W_F, W_R = res["W"][0].unsqueeze(1) * integ.kT, res["W"][1].unsqueeze(1) * integ.kT
             xv_F = xv_R = None

@@ -228,6 +228,39 @@ def test_estimators_match_reference_fixtures(ib, golden_dir):
     assert n >= 8
 
 
+def test_trace_layouts_and_fused_trace_kernel(ib, orc):
+    """Traces from the fused kernel (both layouts) and from the interpreter agree with each other and with the oracle;
+    the replica-major layout is the reference's (n, n_steps) / (n, n_steps, 2)."""
+    system = ib.engine.ScalarSystem("double_well", 10.0)
+    cache = orc.sample_equilibrium_scalar("double_well", 257, 40, seed=5)
+    n, steps = 1000, 7
+    for splitting in ["O V R V O", "V R O R V", "R V O V R", "V R R R O R R R V", "V O V R O"]:  # the last one is not pre-instantiated
+        prog = ib.engine.Program(splitting, 0.3, 10.0)
+        a = ib.engine.run_protocol(system, prog, n, steps, 1.0, marginal="configuration", seed=9, replica0=17, x_cache=cache,
+                                   traces=True, out={})
+        b = ib.engine.run_protocol(system, prog, n, steps, 1.0, marginal="configuration", seed=9, replica0=17, x_cache=cache,
+                                   traces="replica_major", out={})
+        c = ib.engine.run_protocol(system, prog, n, steps, 1.0, marginal="configuration", seed=9, replica0=17, x_cache=cache,
+                                   out={})
+        d = ib.engine.run_protocol(system, prog, n, steps, 1.0, marginal="configuration", seed=9, replica0=17, x_cache=cache,
+                                   traces="pairs", out={})
+        np.testing.assert_array_equal(d["trace_w"].cpu().numpy(), a["trace_w"].cpu().numpy())
+        np.testing.assert_array_equal(d["trace_xv"][..., 0].cpu().numpy(), a["trace_x"].cpu().numpy())
+        np.testing.assert_array_equal(d["trace_xv"][..., 1].cpu().numpy(), a["trace_v"].cpu().numpy())
+        assert b["trace_w_rm"].shape == (2, n, steps + 1) and b["trace_xv_rm"].shape == (2, n, steps + 1, 2)
+        np.testing.assert_array_equal(b["trace_w_rm"].cpu().numpy(), a["trace_w"].permute(0, 2, 1).cpu().numpy())
+        np.testing.assert_array_equal(b["trace_xv_rm"][..., 0].cpu().numpy(), a["trace_x"].permute(0, 2, 1).cpu().numpy())
+        np.testing.assert_array_equal(b["trace_xv_rm"][..., 1].cpu().numpy(), a["trace_v"].permute(0, 2, 1).cpu().numpy())
+        # the last trace entry is the work of the leg, up to the rounding of one more energy difference
+        np.testing.assert_allclose(a["trace_w"][:, -1].cpu().numpy(), c["W"].cpu().numpy(), rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(a["W"].cpu().numpy(), c["W"].cpu().numpy(), rtol=1e-13, atol=1e-14)
+        ref = orc.toy_protocol("double_well", splitting, 0.3, 10.0, n, steps, marginal="configuration", seed=9, replica0=17,
+                               x_cache=cache, traces=True)
+        tame = np.isfinite(ref["W"]).all(axis=1) & (np.abs(ref["W"]).max(axis=1) < 50)
+        np.testing.assert_allclose(b["trace_xv_rm"][0, :, :, 0].cpu().numpy()[tame], ref["trace_x"][tame, 0], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(b["trace_w_rm"][1].cpu().numpy()[tame], ref["trace_w"][tame, 1], rtol=1e-7, atol=1e-8)
+
+
 def test_full_size_properties(ib):
     """BASELINE config 2 size (1 048 576 replicas x 10): size-independent properties.
     (a) time-reversal/Crooks sanity: for the harmonic well at tiny dt both works vanish;
