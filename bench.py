@@ -348,12 +348,13 @@ def run_particles(args):
     m_host = torch.empty(len(splittings), 8, dtype=torch.float64).pin_memory()
     cache2 = torch.empty_like(cache)
 
-    def e2e_pass():
+    def e2e_pass(copy_works=True):
         cache2.copy_(cache_host, non_blocking=True)
         for j, (k, prog) in enumerate(programs.items()):
             res = engine.run_protocol(system, prog, n, steps_per_leg, KT_298, seed=seed, replica0=replica0, x_cache=cache2,
                                       precision=precision, out=bufs[k])
-            w_host[j].copy_(res["W"], non_blocking=True)
+            if copy_works:
+                w_host[j].copy_(res["W"], non_blocking=True)
             moments_all[j].copy_(res["moments"], non_blocking=True)
         parallel.all_reduce_moments(moments_all)
         m_host.copy_(moments_all, non_blocking=True)

@@ -502,30 +502,29 @@ __device__ __noinline__ double compute_forces(uint32_t ctx_off, int g, int out_s
 // ------------------------------------------------------------------------------------------ constraints (fp64)
 // fp64 reciprocal square root / square root / reciprocal without the special-case slow paths of the
 // CUDA math library: hardware seed (2^-22.9 relative) + two Newton steps; ~1 ulp for normal inputs
+// One higher-order correction of the hardware seed y (relative error e, |e| < 2^-22) instead of two Newton steps:
+// 1/sqrt(x) = y (1 + e/2 + 3 e^2/8 + O(e^3)) with e = 1 - x y^2, and 1/x = y (1 + e + e^2 + O(e^3)) with e = 1 - x y.
 static __device__ __forceinline__ double fast_rsqrt(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const double e = fma(-x * y, y, 1.0);
-        y = fma(0.5 * y, e, y);
-    }
-    return y;
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y, e * fma(e, 0.375, 0.5), y);
 }
 static __device__ __forceinline__ double fast_sqrt(double x)
 {
-    const double y = fast_rsqrt(x);
-    const double r = x * y;
-    return fma(fma(-r, r, x), 0.5 * y, r);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    return fma(t, e * fma(e, 0.375, 0.5), t);
 }
 static __device__ __forceinline__ double fast_rcp(double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#pragma unroll
-    for (int it = 0; it < 2; ++it) y = fma(fma(-x, y, 1.0), y, y);
-    return y;
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
 }
 
 static __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
