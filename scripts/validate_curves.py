@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--max-dt", type=float, default=100.0, help="only time steps up to this many fs")
     ap.add_argument("--skip-quartic", action="store_true")
     ap.add_argument("--cache-dt-fs", type=float, default=1.0, help="time step of the Langevin equilibration of the cache")
+    ap.add_argument("--cache-seed", type=int, default=None, help="seed of the equilibrium cache (default: the global seed)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "validate_curves.json"))
     args = ap.parse_args()
     import integrator_benchmark_b200 as ib
@@ -58,7 +59,8 @@ def main():
     eq.timestep = args.cache_dt_fs * unit.femtosecond
     out["precision"], out["cache_dt_fs"] = args.precision, args.cache_dt_fs
     t0 = time.time()
-    eq.collect_equilibrium_samples()
+    eq.collect_equilibrium_samples(seed=args.cache_seed)
+    out["cache_seed"] = args.cache_seed
     out["equilibration_s"] = time.time() - t0
     out["cache"] = {"n": len(eq.samples), "steps_each": int(min(eq.burn_in_length * eq.steps_per_hmc, eq.max_equilibration_steps)) + 1000}
     t0 = time.time()
