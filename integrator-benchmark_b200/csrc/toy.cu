@@ -189,6 +189,39 @@ __device__ __forceinline__ void block_moments(double* __restrict__ partials, boo
     }
 }
 
+// persistent variant: each thread adds its replicas' contributions to its own column of a shared accumulator
+// (no shuffles per chunk); one block reduction at the end of the kernel
+struct MomentAcc { double m[7][kThreads]; };
+
+__device__ __forceinline__ void moments_add(MomentAcc& A, bool finite, double wF, double wR)
+{
+    const int t = threadIdx.x;
+    if (finite) {
+        A.m[0][t] += 1.0; A.m[1][t] += wF; A.m[2][t] += wR;
+        A.m[3][t] += wF * wF; A.m[4][t] += wR * wR; A.m[5][t] += wF * wR;
+    } else {
+        A.m[6][t] += 1.0;
+    }
+}
+
+__device__ __forceinline__ void moments_flush(const MomentAcc& A, double* __restrict__ partials)
+{
+    __shared__ double sh[kThreads / 32][7];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const double s = warp_sum(A.m[j][threadIdx.x]);
+        if (lane == 0) sh[warp][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double s = 0.0;
+        if (threadIdx.x < 7)
+            for (int w = 0; w < kThreads / 32; ++w) s += sh[w][threadIdx.x];
+        partials[(int64_t)blockIdx.x * 8 + threadIdx.x] = s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // compile-time splitting: CODE holds 2 bits per substep (substep i at bits 2i, 2i+1)
 constexpr int code_op(uint32_t code, int i) { return (int)((code >> (2 * i)) & 3u); }
@@ -250,17 +283,22 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
     constexpr int U = (NO == 0) ? 1 : ((4 % NO == 0) ? 4 / NO : 4);  // steps per noise refill when NO | 4
     constexpr bool ALIGNED = (NO > 0) && (4 % NO == 0);
     __shared__ fm::Tables FT;
+    __shared__ MomentAcc ACC;
 #ifdef LSI_TOY_TABLES
     fm::load_tables(FT);
-    __syncthreads();
 #endif
+#pragma unroll
+    for (int j = 0; j < 7; ++j) ACC.m[j][threadIdx.x] = 0.0;
+    __syncthreads();
 
-    const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const bool active = r < P.n;
-    double wF = 0.0, wR = 0.0;
-    bool finite = true;
-
-    if (active) {
+    // persistent CTAs: the grid is (at most) one full wave; CTA b takes the 256-replica chunks b, b + gridDim.x, ...
+    // (tables staged and moments reduced once per CTA, no launch tail)
+    const int64_t n_chunks = (P.n + kThreads - 1) / kThreads;
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t r = chunk * kThreads + threadIdx.x;
+        if (r >= P.n) continue;
+        double wF = 0.0, wR = 0.0;
+        bool finite = true;
         const uint64_t rid = P.replica0 + (uint64_t)r;
         double x = P.x0 ? P.x0[r] : P.x_cache[lsi::cache_index(P.seed, rid, P.n_cache)];
         double v = P.v0 ? P.v0[r] : P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_V0, 0u);
@@ -342,8 +380,9 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
         }
         if (P.x_final) P.x_final[r] = x;
         if (P.v_final) P.v_final[r] = v;
+        if (P.partials) moments_add(ACC, finite, wF, wR);
     }
-    if (P.partials) block_moments(P.partials, active, finite, wF, wR);
+    if (P.partials) moments_flush(ACC, P.partials);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -512,10 +551,24 @@ constexpr int slen(const char* s)
     X("OVRVO") X("ORVRO") X("RVOVR") X("ROVOR") X("VRORV") X("VOROV")                              \
     X("OVRRVO") X("VROORV") X("RVOOVR") X("RVO") X("ROV") X("VRRORRV") X("VRRRORRRV")
 
+// grid of the persistent fused kernels: one full wave (resident CTAs per SM x SMs), or fewer when there are fewer chunks
+unsigned fused_grid(int64_t n)
+{
+    static int wave = 0;
+    if (wave == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+        wave = sms * LSI_TOY_MINB;
+    }
+    const int64_t chunks = (n + kThreads - 1) / kThreads;
+    return (unsigned)(chunks < wave ? chunks : wave);
+}
+
 template <int POT, bool NOISE32>
 bool launch_fused2(uint32_t code, int nops, bool trace, const ToyParams& P, cudaStream_t st, cudaError_t* err)
 {
-    const unsigned grid = (unsigned)((P.n + kThreads - 1) / kThreads);
+    const unsigned grid = fused_grid(P.n);
     if (trace && NOISE32) return false;  // traced mixed-precision runs go through the interpreter
 #define X(S)                                                                                       \
     if (nops == slen(S) && code == pack(S)) {                                                      \
@@ -686,6 +739,6 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
     }
     if (err != cudaSuccess) return lsi_set_error(LSI_ERR_CUDA, "toy kernel launch failed: %s", cudaGetErrorString(err));
     if (ext) LSI_CUDA_CHECK(cudaFreeAsync(ext, st));
-    if (a->moments) return lsi_finalize_moments(P.partials, (int)grid, a->moments, stream);
+    if (a->moments) return lsi_finalize_moments(P.partials, launched ? (int)fused_grid(a->n_replicas) : (int)grid, a->moments, stream);
     return LSI_OK;
 }
