@@ -533,6 +533,8 @@ int lsi_particles_run_protocol(const lsi_system* sys, const lsi_program* prog, c
         }
     }
     if (n_slots == 0) n_slots = 1;
+    if (a->flags & (LSI_FLAG_TRACE_REPLICA_MAJOR | LSI_FLAG_TRACE_XV_PAIRS))
+        return lsi_set_error(LSI_ERR_UNSUPPORTED, "replica-major / (x, v)-pair traces are layouts of scalar systems");
     const bool diag = a->W_direct || a->trace_x || a->trace_v || a->trace_w;
     if (diag) ++n_slots;  // scratch slot for the per-substep energy evaluations
     P.n_ops = n_ops; P.n_slots = n_slots; P.diag = diag ? 1 : 0;
