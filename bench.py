@@ -651,8 +651,8 @@ def main():
         "traffic": 8.04e6 if n == (1 << 20) else None,
         "peak_source": "lsi_microbench_fma fp64, best of 6, measured in this run (fp32: %.1f TFLOP/s)" % peaks["fp32"],
         "note": "algorithmic flops exclude the Philox + Box-Muller noise generation that dominates the instruction count "
-                "(n_O Gaussians per replica-step); ncu (profiles/r1_ncu_summary.json): issue slots 64 % + FP64 pipe 53 % / 2 "
-                "= 91 % of the dispatch limit of the 16-lane fp64 sub-partitions",
+                "(n_O Gaussians per replica-step); ncu (profiles/r1_ncu_summary.json): issue slots busy + FP64 pipe busy / 2 "
+                "= 86-91 % of the dispatch limit of the 16-lane fp64 sub-partitions",
         "replica_steps_per_s_kernel_only": len(SPLITTINGS) * n * 2 * steps_per_leg / kernel_s,
         "kernel_ms_per_splitting": kernel_ms,
         "flops_per_replica_step": {k: flops_per_step(s) for k, s in SPLITTINGS.items()},
