@@ -112,3 +112,18 @@ def test_ghmc_ensemble(ib):
     n_dof = 3 * 22 - 12
     assert ke == pytest.approx(0.5 * n_dof * eq.kT_value, rel=0.06)
     assert acc.float().mean().item() > 0.9
+
+
+def test_hmr_threshold_curve_runs_and_restores_the_system(ib):
+    """thresholds.py:106-130 with a short search: heavier hydrogens do not lower the stability threshold, and the
+    test system gets its own masses back"""
+    from integrator_benchmark_b200.evaluation import thresholds
+    from integrator_benchmark_b200.testsystems import systems
+    eq = _eq(systems.alanine_dipeptide, "ala_hmr", n_samples=32, burn=200, constrained=True)
+    eq.load_or_simulate_samples()
+    masses = np.array(eq.system["mass"], dtype=float).copy()
+    h, thr = thresholds.get_hmr_stability_threshold_curve(eq, "V R O R V", traj_length=300, h_masses=[1.0, 3.0], n_iterations=14,
+                                                          n_samples=8)
+    assert list(h) == [1.0, 3.0] and len(thr) == 2
+    assert 1.0 < thr[0] < 9.5 and thr[1] >= thr[0] - 0.8, thr
+    np.testing.assert_array_equal(np.array(eq.system["mass"], dtype=float), masses)
