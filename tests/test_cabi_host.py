@@ -4,6 +4,7 @@ import ctypes
 import json
 import os
 import re
+import sys
 
 import pytest
 
@@ -125,3 +126,17 @@ def test_particle_system_validation_is_host_only_and_loud():
             system.energy_forces(x[None])
         with pytest.raises(ib._cabi.LsiCudaError):
             ib.engine.run_protocol(system, ib.engine.Program("V R O R V", 0.001, 1.0), 2, 3, 2.5, x0=np.repeat(x[None], 2, 0))
+
+
+def test_bench_reference_arm_runs_without_a_gpu():
+    """`bench.py --impl reference` times the CPU oracle port and prints the contract's JSON line (no CUDA needed)"""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--ref-replicas", "2048"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "replica-steps/s"
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["higher_is_better"] is True and line["steps"] == 2 and line["gpu_launches"] == 0
