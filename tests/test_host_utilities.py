@@ -81,3 +81,27 @@ def test_alanine_description_is_consistent():
         assert abs(np.linalg.norm(pos[a] - pos[b]) - d) < 1e-3
     e, f = orc.particles_energy_forces(desc, pos)
     assert np.isfinite(e) and np.abs(f).max() < 5e3  # a sane, unstrained start geometry
+
+
+def test_fastmath_tables_header_is_what_the_generator_writes(tmp_path):
+    """csrc/fastmath64_tables.h is generated (scripts/gen_fastmath_tables.py, mpmath at 200 bits); the committed copy must
+    not drift from the generator, and a few entries are checked against their definitions directly"""
+    import importlib.util
+    import math
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_tables", os.path.join(root, "scripts", "gen_fastmath_tables.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    out = tmp_path / "tables.h"
+    gen.main(str(out))
+    committed = open(os.path.join(root, "integrator-benchmark_b200", "csrc", "fastmath64_tables.h")).read()
+    assert out.read_text() == committed
+    rows = [tuple(float.fromhex(v) for v in line.strip(" {},\n").split(", "))
+            for line in committed.splitlines() if line.startswith("    {")]
+    log_rows, trig_rows = rows[:128], rows[128:]
+    assert len(trig_rows) == 1024
+    assert log_rows[80] == (1.0, 0.0)                         # the interval centred on z = 1
+    c0 = gen.bits_to_double(0x3FE60000)
+    assert log_rows[0][0] == pytest.approx(1.0 / c0, rel=1e-16) and log_rows[0][1] == pytest.approx(-2.0 * math.log(c0), rel=1e-15)
+    assert trig_rows[0] == (0.0, 1.0) and trig_rows[256] == pytest.approx((1.0, 0.0), abs=1e-16)
+    assert trig_rows[100] == pytest.approx((math.sin(2 * math.pi * 100 / 1024), math.cos(2 * math.pi * 100 / 1024)), rel=1e-15)
