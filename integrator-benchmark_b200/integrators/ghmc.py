@@ -156,6 +156,7 @@ class CustomizableGHMC:
             x = t.where(m, x_new, x)
             v = t.where(m, v_new, -v)
             accepts[trial] = acc
+        if int(n_trials) > 0:  # the per-trial globals show the last chain's last trial (one host sync, after the loop)
             self._globals["shadow_work"] = float(w[-1].item()) * kT
             self._globals["acc_ratio"] = float(ratio[-1].item())
             self._globals["accept"] = float(acc[-1].item())
