@@ -189,6 +189,79 @@ def estimate_kl_div_adaptive_outer_loop(noneq_sim, marginal, outer_sample_fxn, n
     return result
 
 
+GPU_FILL = 16384  # trajectories per launch that keep a B200 busy for 60-atom systems
+GPU_MAX_LAUNCH = 262144  # cap on one launch of the batched outer loop (host staging of the start states)
+
+
+def collect_outer_samples_batched(noneq_sim, marginal, n_outer, n_steps, initial_size=100, batch_size=5, threshold=0.1,
+                                  max_samples=1000, n_collisions=2):
+    """`n_outer` outer samples at once: what `[outer_sample_adaptive(...) for _ in range(n_outer)]` computes, with the
+    inner loops of ALL outer samples advanced together, one launch per round (the reference spreads outer samples over a
+    Pool(32): compare_near_eq_and_exact.py:357-368).  Every outer sample keeps its own stopping rule -- stdev_log_rho_pi
+    tested at the counts initial_size + k batch_size, result cut at the first count that passes (:119-139) -- but the
+    trajectories of a round are drawn ahead of the rule (each unfinished sample grows by half its size, at least
+    GPU_FILL trajectories per launch in total), so some are computed and then cut."""
+    if marginal not in ("full", "configuration"):
+        raise Exception("marginal must be `full` or `configuration`")
+    rho = sample_from_rho(noneq_sim, n_collisions=n_collisions, n=n_outer)
+    xs, vs = np.asarray(rho["x"]), np.asarray(rho["v"])
+    Ws = [np.zeros(0) for _ in range(n_outer)]
+    checked = [initial_size] * n_outer   # next count the stopping rule has to look at
+    final = [None] * n_outer
+    active = list(range(n_outer))
+    while active:
+        want = [initial_size if len(Ws[i]) == 0 else max(batch_size, (len(Ws[i]) + 1) // 2) for i in active]
+        want = [min(w, max(batch_size, max_samples - len(Ws[i]))) for w, i in zip(want, active)]
+        scale = max(1, -(-GPU_FILL // max(1, sum(want)))) if len(Ws[active[0]]) > 0 else 1
+        want = [min(w * scale, max(batch_size, max_samples - len(Ws[i]))) for w, i in zip(want, active)]
+        offsets = np.concatenate([[0], np.cumsum(want)])
+        W = np.empty(int(offsets[-1]))
+        lo = 0
+        while lo < len(active):  # launches of at most GPU_MAX_LAUNCH trajectories
+            hi = lo + 1
+            while hi < len(active) and offsets[hi + 1] - offsets[lo] <= GPU_MAX_LAUNCH:
+                hi += 1
+            x0 = np.repeat(xs[active[lo:hi]], want[lo:hi], axis=0)
+            v0 = np.repeat(vs[active[lo:hi]], want[lo:hi], axis=0) if marginal == "full" else None
+            W[offsets[lo]:offsets[hi]] = noneq_sim.ensemble_shadow_work(x0, v0, n_steps)
+            lo = hi
+        still = []
+        for k, i in enumerate(active):
+            Ws[i] = np.concatenate([Ws[i], W[offsets[k]:offsets[k + 1]]])
+            counts = np.arange(checked[i], len(Ws[i]) + 1, batch_size)
+            if len(counts) > 0:
+                sd = _running_stdev(Ws[i], counts)
+                hit = np.nonzero(~(sd > threshold) | ~(counts <= (max_samples - batch_size)))[0]
+                if len(hit) > 0:
+                    final[i] = Ws[i][:counts[hit[0]]]
+                    continue
+                checked[i] = counts[-1] + batch_size
+            still.append(i)
+        active = still
+    return [{"xv": (xs[i], vs[i]), "Ws": final[i], "estimate": estimate_from_work_samples(final[i])} for i in range(n_outer)]
+
+
+def estimate_kl_div_adaptive_outer_loop_batched(noneq_sim, marginal, outer_sample_fxn=None, n_steps=1000, initial_size=100,
+                                                batch_size=1, threshold=0.1, max_samples=1000, return_samples=False,
+                                                inner=None):
+    """estimate_kl_div_adaptive_outer_loop (:257-290) with each batch of outer samples collected by
+    collect_outer_samples_batched.  `inner` = dict(initial_size, batch_size, threshold, max_samples) of the inner loop
+    (or a functools.partial of outer_sample_adaptive carrying them, as the reference's __main__ builds)."""
+    if inner is None:
+        inner = dict(getattr(outer_sample_fxn, "keywords", {}) or {})
+    collect = lambda n: collect_outer_samples_batched(noneq_sim, marginal, n, n_steps, **inner)  # noqa: E731
+    outer_samples = collect(initial_size)
+    while (stdev_kl_div(outer_samples) > threshold) and (len(outer_samples) <= (max_samples - batch_size)):
+        outer_samples.extend(collect(batch_size))
+    if stdev_kl_div(outer_samples) > threshold:
+        warnings.warn("stdev_kl_div(outer_samples) > threshold\n({:.3f} > {:.3f})".format(stdev_kl_div(outer_samples), threshold),
+                      RuntimeWarning)
+    result = {"new_estimate": process_outer_samples(outer_samples), "Ws": np.array([s["Ws"] for s in outer_samples], dtype=object)}
+    if return_samples:
+        result["samples"] = outer_samples
+    return result
+
+
 def estimate_kl_div_adaptive_outer_loop_sharded(noneq_sim, marginal, outer_sample_fxn, n_steps=1000, initial_size=100,
                                                 batch_size=1, threshold=0.1, max_samples=1000, return_samples=False):
     """The adaptive outer loop with the OUTER samples sharded over the ranks of torch.distributed (one process per

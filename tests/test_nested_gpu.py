@@ -104,3 +104,37 @@ def test_adaptive_inner_loop_cuts_where_the_reference_would(ib):
     res = nested.estimate_kl_div_naive_outer_loop(sim, "full", lambda **kw: nested.outer_sample_naive(n_inner_samples=64, **kw),
                                                   n_outer_samples=3, n_steps=20)
     assert np.isfinite(res["new_estimate"]) and len(res["Ws"]) == 3
+
+
+def test_batched_outer_samples_keep_the_reference_stopping_rule(ib):
+    """collect_outer_samples_batched advances the inner loops of all outer samples together; every returned work array
+    is cut exactly where the reference's rule (tested every `batch_size` from `initial_size`) first passes"""
+    from functools import partial
+    from integrator_benchmark_b200 import unit
+    from integrator_benchmark_b200.evaluation import compare_near_eq_and_exact as nested
+    from integrator_benchmark_b200.integrators import LangevinSplittingIntegrator
+    from integrator_benchmark_b200.testsystems import EquilibriumSimulator, NonequilibriumSimulator, configure_platform, systems
+    desc, pos = systems.water_cluster(20, constrained=True, seed=1)
+    eq = EquilibriumSimulator(platform=configure_platform("CUDA"), topology=None, system=desc, positions=pos,
+                              temperature=298 * unit.kelvin, timestep=1.0 * unit.femtosecond, burn_in_length=300, n_samples=16,
+                              thinning_interval=10, name="wc")
+    eq.metropolis_rounds = 20
+    integ = LangevinSplittingIntegrator("O V R V O", collision_rate=1.0 / unit.picosecond, timestep=4.0 * unit.femtosecond)
+    sim = NonequilibriumSimulator(eq, integ)
+    ib.set_seed(21, next_replica=0)
+    ref_sd = lambda w: np.std(np.exp(-w)) / (np.mean(np.exp(-w)) * np.sqrt(len(w)))  # noqa: E731
+    for marginal in ("full", "configuration"):
+        samples = nested.collect_outer_samples_batched(sim, marginal, 6, 25, initial_size=40, batch_size=3, threshold=0.03,
+                                                       max_samples=2000)
+        assert len(samples) == 6
+        for s in samples:
+            w = s["Ws"]
+            assert np.isfinite(w).all() and (len(w) - 40) % 3 == 0 and 40 <= len(w) <= 2000
+            assert not (ref_sd(w) > 0.03) or not (len(w) <= 2000 - 3)          # the rule passes here ...
+            assert all(ref_sd(w[:c]) > 0.03 for c in range(40, len(w), 3))     # ... and nowhere before
+            assert s["estimate"] == pytest.approx(np.log(np.mean(np.exp(-w))), rel=1e-10)
+            assert s["xv"][0].shape == (60, 3)
+    outer = partial(nested.outer_sample_adaptive, initial_size=40, batch_size=3, threshold=0.05, max_samples=500)
+    res = nested.estimate_kl_div_adaptive_outer_loop_batched(sim, "full", outer, n_steps=25, initial_size=5, batch_size=4,
+                                                             threshold=0.02, max_samples=13)
+    assert np.isfinite(res["new_estimate"]) and 5 <= len(res["Ws"]) <= 13 and (len(res["Ws"]) - 5) % 4 == 0
