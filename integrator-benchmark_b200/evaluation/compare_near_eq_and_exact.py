@@ -263,12 +263,15 @@ def estimate_kl_div_adaptive_outer_loop_batched(noneq_sim, marginal, outer_sampl
 
 
 def estimate_kl_div_adaptive_outer_loop_sharded(noneq_sim, marginal, outer_sample_fxn, n_steps=1000, initial_size=100,
-                                                batch_size=1, threshold=0.1, max_samples=1000, return_samples=False):
+                                                batch_size=1, threshold=0.1, max_samples=1000, return_samples=False,
+                                                inner=None):
     """The adaptive outer loop with the OUTER samples sharded over the ranks of torch.distributed (one process per
     GPU; every rank runs its own inner ensembles on its own device).  Rank r starts with its share of
     `initial_size` (parallel.shard_range) and adds `batch_size` samples per round; the stopping rule of
     estimate_kl_div_adaptive_outer_loop (:257-290) is evaluated on the union through one all-reduce of
     (n, sum, sum of squares) of the per-sample estimates per round -- 24 bytes -- so all ranks stop together.
+    `inner` = dict(initial_size, batch_size, threshold, max_samples): collect each rank's share of a round with
+    collect_outer_samples_batched instead of calling `outer_sample_fxn` per sample.
     Returns the global estimate and stdev, the global sample count, and this rank's Ws / samples."""
     import torch
     import torch.distributed as dist
@@ -276,9 +279,12 @@ def estimate_kl_div_adaptive_outer_loop_sharded(noneq_sim, marginal, outer_sampl
     rank, world, _ = parallel.world()
     on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     device = "cuda" if (on and dist.get_backend() == "nccl") else "cpu"
-    collect = lambda: outer_sample_fxn(noneq_sim=noneq_sim, marginal=marginal, n_steps=n_steps)  # noqa: E731
+    if inner is not None:  # this rank's share of a round in one batched collection (collect_outer_samples_batched)
+        collect_n = lambda k: collect_outer_samples_batched(noneq_sim, marginal, k, n_steps, **inner) if k > 0 else []  # noqa: E731
+    else:
+        collect_n = lambda k: [outer_sample_fxn(noneq_sim=noneq_sim, marginal=marginal, n_steps=n_steps) for _ in range(k)]  # noqa: E731
     lo, hi = parallel.shard_range(initial_size, rank, world)
-    outer_samples = [collect() for _ in range(hi - lo)]
+    outer_samples = collect_n(hi - lo)
 
     def global_stats():
         e = np.array([s["estimate"] for s in outer_samples], dtype=np.float64)
@@ -291,8 +297,7 @@ def estimate_kl_div_adaptive_outer_loop_sharded(noneq_sim, marginal, outer_sampl
         return int(n), mean, float(np.sqrt(var) / np.sqrt(n))
     n, mean, sd = global_stats()
     while sd > threshold and n <= max_samples - batch_size * world:
-        for _ in range(batch_size):
-            outer_samples.append(collect())
+        outer_samples.extend(collect_n(batch_size))
         n, mean, sd = global_stats()
     if sd > threshold and rank == 0:
         warnings.warn("stdev_kl_div(outer_samples) > threshold\n({:.3f} > {:.3f})".format(sd, threshold), RuntimeWarning)
