@@ -138,3 +138,8 @@ def test_batched_outer_samples_keep_the_reference_stopping_rule(ib):
     res = nested.estimate_kl_div_adaptive_outer_loop_batched(sim, "full", outer, n_steps=25, initial_size=5, batch_size=4,
                                                              threshold=0.02, max_samples=13)
     assert np.isfinite(res["new_estimate"]) and 5 <= len(res["Ws"]) <= 13 and (len(res["Ws"]) - 5) % 4 == 0
+    # the rank-sharded loop (a single rank here) with the batched inner loops
+    res = nested.estimate_kl_div_adaptive_outer_loop_sharded(sim, "full", None, n_steps=25, initial_size=5, batch_size=4, threshold=0.02,
+                                                             max_samples=13, inner=dict(initial_size=40, batch_size=3, threshold=0.05,
+                                                                                        max_samples=500))
+    assert np.isfinite(res["new_estimate"]) and res["n_outer_samples"] == len(res["Ws"]) and 5 <= len(res["Ws"]) <= 13
