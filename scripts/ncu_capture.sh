@@ -13,4 +13,4 @@ ncu -i /tmp/${tag}.ncu-rep --page source --print-source sass --csv > gpurun_out/
 ncu -i /tmp/${tag}.ncu-rep --page details > gpurun_out/${tag}_details.txt 2>/dev/null
 ls -la /tmp/${tag}.ncu-rep gpurun_out/${tag}_*
 sz=$(stat -c %s /tmp/${tag}.ncu-rep 2>/dev/null || echo 0)
-if [ "$sz" -lt 20000000 ]; then cp /tmp/${tag}.ncu-rep gpurun_out/; fi
+if [ "$sz" -lt 4000000 ]; then cp /tmp/${tag}.ncu-rep gpurun_out/; fi
