@@ -340,3 +340,18 @@ def test_fastmath_accuracy(ib):
     assert ulps(run(11, pos), np.sqrt(pos)).max() <= 2.0
     d0, d1 = run(9, words, two=True)  # table-driven minus library normals
     assert np.abs(d0).max() < 2e-14 and np.abs(d1).max() < 2e-14
+
+
+def test_one_step_ghmc_acceptance_matches_the_published_value(ib):
+    """notebooks/"1D figures, updated.ipynb" cells 65-67: acceptance ratios min(1, exp(-W_shad)) of ONE step of VRORV at
+    dt = 0.6, gamma = 10 from equilibrium of the double well: mean 0.84828 +/- 0.00071, std 0.22585 (1e5 samples there,
+    4e6 here)."""
+    from integrator_benchmark_b200.integrators import baoab_factory
+    from integrator_benchmark_b200.testsystems import double_well
+    ib.set_seed(314)
+    scheme = baoab_factory(double_well.potential, double_well.force, double_well.velocity_scale, double_well.mass)
+    res = scheme.ensemble(4000000, 2, 10.0, 0.6, n_legs=1, x_cache=double_well.x_samples_device())
+    ratios = ib.engine.torch().exp(-res["W"][0]).clamp(max=1.0)
+    mean, std = ratios.mean().item(), ratios.std().item()
+    assert abs(mean - 0.84827685) < 3 * 0.00071420 + 3 * std / 2000.0, mean
+    assert std == pytest.approx(0.22585, abs=0.003)
