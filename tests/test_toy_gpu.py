@@ -355,3 +355,26 @@ def test_one_step_ghmc_acceptance_matches_the_published_value(ib):
     mean, std = ratios.mean().item(), ratios.std().item()
     assert abs(mean - 0.84827685) < 3 * 0.00071420 + 3 * std / 2000.0, mean
     assert std == pytest.approx(0.22585, abs=0.003)
+
+
+def test_quartic_steady_state_histogram_matches_the_published_ground_truth(ib):
+    """notes/note_on_dF_neq_approximation.tex:349-380: quartic, m = 10, beta = 1, gamma = 100, dt = 1.1; histogram
+    D_KL(rho_x || pi_x) of the steady state: VVVR (OVRVO) ~ 0.01309, BAOAB (VRORV) ~ 0.00013 (scripts/validate_quartic_histogram.py)"""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("vqh", os.path.join(root, "scripts", "validate_quartic_histogram.py"))
+    vqh = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vqh)
+    from integrator_benchmark_b200.integrators import baoab_factory, vvvr_factory
+    from integrator_benchmark_b200.testsystems import quartic
+    ib.set_seed(99)
+    edges = np.linspace(-2.5, 2.5, 101)
+    got = {}
+    for name, factory in (("VRORV", baoab_factory), ("OVRVO", vvvr_factory)):
+        scheme = factory(quartic.potential, quartic.force, quartic.velocity_scale, quartic.mass)
+        res = scheme.ensemble(1 << 22, 301, 100.0, 1.1, n_legs=1, x_cache=quartic.x_samples_device(), want_final=True)
+        x = res["x_final"].cpu().numpy()
+        got[name] = vqh.histogram_kl(x[np.isfinite(x) & (np.abs(x) < 2.5)], edges)
+    assert got["OVRVO"] == pytest.approx(0.01309, rel=0.03), got
+    assert 0.00007 < got["VRORV"] < 0.00019, got
