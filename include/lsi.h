@@ -17,9 +17,10 @@
  *     thread-local message for the last failure on the calling thread
  *   - handles are opaque, owned by the caller, freed with the matching
  *     *_destroy; one handle must not be used from two threads at once
- *   - no call synchronises the stream or the device unless stated (lsi_run_protocol synchronises the stream once
- *     when the program has more than 96 substeps (particle systems) / 160 (scalar systems): long multi-timestep
- *     strings are staged in device memory)
+ *   - no call synchronises the stream or the device unless stated.  Programs of more than 96 substeps (particle
+ *     systems) / 160 (scalar systems) do not fit the kernel parameters: their tables are copied to device memory
+ *     (one blocking copy) the FIRST time lsi_run_protocol sees them on a device and are cached on the lsi_program
+ *     handle; later launches of the same program make no allocation, copy or synchronisation
  *   - there is NO CPU fallback: compute calls fail with LSI_ERR_CUDA when no
  *     device is usable
  *   - units are OpenMM's: nm, ps, amu, kJ/mol, K, e   (toy systems: reduced units)
@@ -33,7 +34,7 @@
 extern "C" {
 #endif
 
-#define LSI_ABI_VERSION 1
+#define LSI_ABI_VERSION 2
 
 /* error codes; the Python shim maps them to the exception types the reference raises */
 #define LSI_OK 0
@@ -118,8 +119,8 @@ int lsi_system_create_scalar(int potential_kind, const double params[4], double 
 /* Particle systems.  The description mirrors the OpenMM System objects the reference builds in
  * benchmark/testsystems/{watercluster.py:10-84, waterbox.py:36-48, alanine_dipeptide.py:12-21}:
  * NonbondedForce (Lennard-Jones, Lorentz-Berthelot combination, Coulomb constant 138.935456;
- * NoCutoff, or CutoffPeriodic = minimum image + reaction field with `rf_dielectric`, plain LJ
- * truncation), its exclusions and 1-4 exceptions, HarmonicBondForce 1/2 k (r - r0)^2,
+ * NoCutoff, or CutoffPeriodic = minimum image + reaction field with `rf_dielectric`, LJ truncated or
+ * switched off over [switch_distance, cutoff]), its exclusions and 1-4 exceptions, HarmonicBondForce 1/2 k (r - r0)^2,
  * HarmonicAngleForce 1/2 k (theta - theta0)^2, PeriodicTorsionForce k (1 + cos(n phi - phase)),
  * the restraint (K/2) |x|^2 on every atom (watercluster.py:70-80), force-group ids per force
  * class ("Nonbonded -> 0, else -> 1", experiments/submission_scripts/4_mts_integrator_splittings.py:36-42),
@@ -162,6 +163,12 @@ typedef struct lsi_particles_desc {
     const int32_t* constraint_atoms; /* [n][2] */
     const double* constraint_dist;   /* [n] nm */
     double constraint_tolerance;
+    /* Lennard-Jones switching function of NonbondedForce (setUseSwitchingFunction / setSwitchingDistance, which
+     * openmmtools' WaterBox -- the reference's tiny_waterbox, benchmark/testsystems/waterbox.py:36-48 -- turns on with
+     * switch_width = 1.5 A): for switch_distance < r < cutoff the LJ energy is multiplied by
+     * S(x) = 1 - 6 x^5 + 15 x^4 - 10 x^3, x = (r - switch_distance) / (cutoff - switch_distance), so that energy and
+     * force go to zero continuously at the cutoff.  <= 0: plain truncation.  CutoffPeriodic only. */
+    double switch_distance;
 } lsi_particles_desc;
 
 int lsi_system_create_particles(const lsi_particles_desc* desc, lsi_system** out);
@@ -183,7 +190,9 @@ int lsi_system_num_dof(const lsi_system* s);
  * Per replica r (global id replica0 + r, which alone keys its RNG streams):
  *   leg 0: x0 = x0[r] if given, else x_cache[index drawn from TAG_X0];
  *          v0 = v0[r] if given, else sqrt(kT/m) * N(0,1) from TAG_V0
- *   leg l>0: x continues; v is redrawn from TAG_VMID (configuration) or kept (full)
+ *   leg l>0: x continues; v is redrawn (configuration) or kept (full).  Particle systems redraw from TAG_VMID
+ *          (draw l - 1, unit = atom); scalar systems take normal number l of the replica's TAG_V0 scalar stream, so
+ *          the start and the midpoint velocity of a two-leg protocol are the two halves of one Box-Muller pair
  *   each leg applies the program n_steps times and yields
  *          W = ((E_end - E_start) - (heat_end - heat_start)) / kT
  * Particle systems: states are [replica][atom][3] (x_cache [n_cache][atom][3]); before each leg

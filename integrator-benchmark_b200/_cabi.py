@@ -60,7 +60,7 @@ class ParticlesDesc(ctypes.Structure):
         ("n_settle", ctypes.c_int32), ("settle_atoms", c_int32_pp), ("settle_oh", ctypes.c_double),
         ("settle_hh", ctypes.c_double),
         ("n_constraints", ctypes.c_int32), ("constraint_atoms", c_int32_pp), ("constraint_dist", c_double_p),
-        ("constraint_tolerance", ctypes.c_double),
+        ("constraint_tolerance", ctypes.c_double), ("switch_distance", ctypes.c_double),
     ]
 
 

@@ -1,6 +1,8 @@
 // C-ABI glue: system handles and protocol dispatch (include/lsi.h).
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "lsi_internal.h"
 
 LSI_EXPORT int lsi_device_count(void)
@@ -49,4 +51,41 @@ LSI_EXPORT int lsi_run_protocol(const lsi_system* sys, const lsi_program* prog, 
         return lsi_set_error(LSI_ERR_CUDA, "no CUDA device: liblsi has no CPU fallback");
     if (sys->kind == LSI_SYS_SCALAR) return lsi_toy_run_protocol(sys, prog, args, stream);
     return lsi_particles_run_protocol(sys, prog, args, stream);
+}
+
+int lsi_program_stage(const lsi_program* prog, const void* bytes, size_t n_bytes, void** dev_out)
+{
+    int dev = 0;
+    LSI_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(prog->mu);
+    for (const lsi_staged_program& e : prog->staged)
+        if (e.device == dev && e.host.size() == n_bytes && std::memcmp(e.host.data(), bytes, n_bytes) == 0) {
+            *dev_out = e.dev;
+            return LSI_OK;
+        }
+    if (prog->staged.size() >= 16) {  // setStepSize sweeps: drop the oldest copy (cudaFree waits for its users)
+        cudaFree(prog->staged.front().dev);
+        prog->staged.erase(prog->staged.begin());
+    }
+    void* d = nullptr;
+    LSI_CUDA_CHECK(cudaMalloc(&d, n_bytes));
+    const cudaError_t err = cudaMemcpy(d, bytes, n_bytes, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+        cudaFree(d);
+        return lsi_set_error(LSI_ERR_CUDA, "staging the program failed: %s", cudaGetErrorString(err));
+    }
+    lsi_staged_program e;
+    e.device = dev;
+    e.host.assign((const unsigned char*)bytes, (const unsigned char*)bytes + n_bytes);
+    e.dev = d;
+    prog->staged.push_back(e);
+    *dev_out = d;
+    return LSI_OK;
+}
+
+void lsi_program_free_staged(lsi_program* prog)
+{
+    std::lock_guard<std::mutex> lock(prog->mu);
+    for (lsi_staged_program& e : prog->staged) cudaFree(e.dev);
+    prog->staged.clear();
 }

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,6 +18,15 @@ struct lsi_op {
     double a, b;      // O coefficients (baked at compile time)
 };
 
+// device copy of a long program's substep tables (more substeps than fit the kernel parameters), cached on the
+// program handle: the next launch of the same tables on the same device finds it and needs no allocation, no copy
+// and no host synchronisation
+struct lsi_staged_program {
+    int device;
+    std::vector<unsigned char> host;  // the staged bytes (the key)
+    void* dev;
+};
+
 struct lsi_program {
     std::vector<lsi_op> ops;
     double dt;
@@ -25,6 +35,8 @@ struct lsi_program {
     bool measure_shadow_work;
     bool measure_heat;
     int n_O;
+    mutable std::mutex mu;
+    mutable std::vector<lsi_staged_program> staged;
 };
 
 enum lsi_system_kind { LSI_SYS_SCALAR = 0, LSI_SYS_PARTICLES = 1 };
@@ -51,6 +63,10 @@ int lsi_set_error(int code, const char* fmt, ...);
                                  cudaGetErrorString(err__), __FILE__, __LINE__);                  \
     } while (0)
 
+// api.cu: device pointer of `bytes` staged for the current device (cached on the program; the first call for a given
+// content copies synchronously, later calls return at once)
+int lsi_program_stage(const lsi_program* prog, const void* bytes, size_t n_bytes, void** dev_out);
+void lsi_program_free_staged(lsi_program* prog);
 // toy.cu
 int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const lsi_protocol_args* args,
                          void* stream);

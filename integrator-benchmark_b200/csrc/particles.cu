@@ -44,6 +44,7 @@ struct lsi_particles {
     int nb_method = 0;
     double cutoff = 0, box[3] = {0, 0, 0}, rf_dielectric = 78.3;
     double restraint_k = 0;
+    double switch_distance = 0;
     int g_nb = 0, g_bond = 0, g_angle = 0, g_tors = 0, g_restr = 0;
     double oh = 0, hh = 0, tol = 1e-8;
     double settle_c[8] = {0}, settle_m[9] = {0};
@@ -154,6 +155,9 @@ void fill_system_params(const lsi_particles* p, const DevTables* t, bool mixed, 
     P.krf = periodic ? (1.0 / (rc * rc * rc)) * (er - 1.0) / (2.0 * er + 1.0) : 0.0;
     P.crf = periodic ? (1.0 / rc) * (3.0 * er) / (2.0 * er + 1.0) : 0.0;
     P.restraint_k = p->restraint_k;
+    const bool sw = periodic && p->switch_distance > 0.0 && p->switch_distance < rc;
+    P.switch_r = sw ? p->switch_distance : 0.0;
+    P.inv_switch_w = sw ? 1.0 / (rc - p->switch_distance) : 0.0;
     P.g_nb = p->g_nb; P.g_restr = p->g_restr;
     P.oh = p->oh; P.hh = p->hh; P.tol = p->tol;
     for (int k = 0; k < 8; ++k) P.settle_c[k] = p->settle_c[k];
@@ -259,6 +263,9 @@ LSI_EXPORT int lsi_system_create_particles(const lsi_particles_desc* d, lsi_syst
                 return lsi_set_error(LSI_ERR_ARG, "periodic box edge must be at least twice the cutoff");
     p->rf_dielectric = d->rf_dielectric > 0 ? d->rf_dielectric : 78.3;
     p->restraint_k = d->restraint_k;
+    p->switch_distance = d->switch_distance;
+    if (p->switch_distance > 0.0 && !(p->nb_method == LSI_NB_CUTOFF_PERIODIC && p->switch_distance < p->cutoff))
+        return lsi_set_error(LSI_ERR_ARG, "switch_distance needs CutoffPeriodic and must be below the cutoff");
     p->g_nb = d->group_nonbonded; p->g_bond = d->group_bonds; p->g_angle = d->group_angles;
     p->g_tors = d->group_torsions; p->g_restr = d->group_restraint;
     p->oh = d->settle_oh; p->hh = d->settle_hh;
@@ -548,19 +555,22 @@ int lsi_particles_run_protocol(const lsi_system* sys, const lsi_program* prog, c
     if (n_ops <= kMaxInlineOps) {
         for (int i = 0; i < n_ops; ++i) { P.op_kind[i] = kinds[i]; P.op_slot[i] = slots[i]; P.op_c0[i] = c0[i]; P.op_c1[i] = c1[i]; }
     } else {
-        // long multi-timestep strings: stage the program in device memory (stream-ordered; the one host
-        // synchronisation of this call, because the host vectors die at return)
+        // long multi-timestep strings: the tables live in device memory, cached on the program handle
+        // (lsi_program_stage: no allocation, copy or synchronisation after the first launch)
         const size_t nb = (size_t)n_ops * (2 * sizeof(double)) + 2 * (size_t)n_ops;
-        LSI_CUDA_CHECK(cudaMallocAsync((void**)&dprog, nb, st));
+        std::vector<unsigned char> bytes(nb);
+        std::memcpy(bytes.data(), c0.data(), n_ops * sizeof(double));
+        std::memcpy(bytes.data() + n_ops * sizeof(double), c1.data(), n_ops * sizeof(double));
+        std::memcpy(bytes.data() + 2 * n_ops * sizeof(double), kinds.data(), n_ops);
+        std::memcpy(bytes.data() + 2 * n_ops * sizeof(double) + n_ops, slots.data(), n_ops);
+        void* ext = nullptr;
+        rc = lsi_program_stage(prog, bytes.data(), nb, &ext);
+        if (rc != LSI_OK) return rc;
+        dprog = (unsigned char*)ext;
         double* d0 = (double*)dprog;
         double* d1 = d0 + n_ops;
         unsigned char* dk = (unsigned char*)(d1 + n_ops);
         unsigned char* ds = dk + n_ops;
-        LSI_CUDA_CHECK(cudaMemcpyAsync(d0, c0.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
-        LSI_CUDA_CHECK(cudaMemcpyAsync(d1, c1.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
-        LSI_CUDA_CHECK(cudaMemcpyAsync(dk, kinds.data(), n_ops, cudaMemcpyHostToDevice, st));
-        LSI_CUDA_CHECK(cudaMemcpyAsync(ds, slots.data(), n_ops, cudaMemcpyHostToDevice, st));
-        LSI_CUDA_CHECK(cudaStreamSynchronize(st));
         P.ext_c0 = d0; P.ext_c1 = d1; P.ext_kind = dk; P.ext_slot = ds;
     }
 
@@ -573,7 +583,6 @@ int lsi_particles_run_protocol(const lsi_system* sys, const lsi_program* prog, c
 
     P.team_lanes = L.team_lanes;
     rc = mixed ? lsi_pk_launch_protocol_f32(P, L, stream) : lsi_pk_launch_protocol_f64(P, L, stream);
-    if (dprog) cudaFreeAsync(dprog, st);
     if (rc == LSI_OK && a->moments)  // works are leg-major: W_F = W[0 .. n), W_R = W[n .. 2n)
         rc = lsi_reduce_moments(a->W, a->W + a->n_replicas, a->n_replicas, a->moments, a->workspace, a->workspace_bytes, stream);
     return rc;

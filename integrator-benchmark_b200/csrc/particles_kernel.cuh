@@ -183,7 +183,7 @@ struct TeamCtx {
     const int32_t *perm, *iperm;
     const PKTerm<real>* terms;
     const int32_t *gather_off, *gather_idx;
-    real boxr[3], inv_boxr[3], rc2, krf, krf2, crf, restraint_k;
+    real boxr[3], inv_boxr[3], rc2, krf, krf2, crf, restraint_k, switch_r, inv_switch_w;
 };
 
 template <typename real>
@@ -212,6 +212,7 @@ __device__ __forceinline__ void fill_ctx(TeamCtx<real>* c, const PKParams& P, co
     c->gather_off = P.gather_off; c->gather_idx = P.gather_idx;
     c->rc2 = (real)P.cutoff2; c->krf = (real)P.krf; c->krf2 = (real)(2.0 * P.krf); c->crf = (real)P.crf;
     c->restraint_k = (real)P.restraint_k;
+    c->switch_r = (real)P.switch_r; c->inv_switch_w = (real)P.inv_switch_w;
 }
 
 template <typename real, bool PERIODIC>
@@ -231,7 +232,7 @@ __device__ __forceinline__ void min_image(const TeamCtx<real>& C, real& dx, real
 // the Coulomb-only body, whose sums leave the lane's own charge out of the loop.
 template <typename real, bool PERIODIC, bool ENERGY>
 struct PairBody {
-    real bx, by, bz, ibx, iby, ibz, rc2, krf, krf2, crf;
+    real bx, by, bz, ibx, iby, ibz, rc2, krf, krf2, crf, sw_r, sw_iw;
     // geometry shared by both bodies
     __device__ __forceinline__ bool geom(const typename Vec<real>::r4& pj, real xi, real yi, real zi, uint32_t mw, int jj,
                                          real& dx, real& dy, real& dz, real& r2v, real& inv_r, real& inv_r2) const
@@ -273,7 +274,8 @@ __device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typena
     PairBody<real, PERIODIC, ENERGY> B;
     B.bx = C.boxr[0]; B.by = C.boxr[1]; B.bz = C.boxr[2];
     B.ibx = C.inv_boxr[0]; B.iby = C.inv_boxr[1]; B.ibz = C.inv_boxr[2];
-    B.rc2 = C.rc2; B.krf = C.krf; B.krf2 = C.krf2; B.crf = C.crf;
+    B.rc2 = C.rc2; B.krf = C.krf; B.krf2 = C.krf2; B.crf = C.crf; B.sw_r = C.switch_r; B.sw_iw = C.inv_switch_w;
+    const bool use_switch = PERIODIC && C.inv_switch_w != (real)0;  // team-uniform
     real gx[APL], gy[APL], gz[APL];  // Coulomb sums without the lane's own charge
     double ge[APL];              // energies: fp32 pair terms summed in fp64 (as OpenMM's mixed mode)
 #pragma unroll
@@ -301,11 +303,22 @@ __device__ __forceinline__ void pair_forces(const TeamCtx<real>& C, const typena
                     const real sig = hsi[a] + lj.x;
                     const real s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
                     const real t = sei[a] * lj.y * s6;  // 4 eps s6
-                    fr += t * ((real)12 * s6 - (real)6) * inv_r2;
+                    real f_lj = t * ((real)12 * s6 - (real)6) * inv_r2;
+                    real e_lj = t * (s6 - (real)1);
+                    if (use_switch) {
+                        // OpenMM's switching function S(x) = 1 - 6 x^5 + 15 x^4 - 10 x^3 on [switch_r, cutoff]; x = 0 below
+                        const real xs = fmax((r2v * inv_r - B.sw_r) * B.sw_iw, (real)0);
+                        const real xs2 = xs * xs;
+                        const real sw = (real)1 + xs2 * xs * ((real)-10 + xs * ((real)15 - (real)6 * xs));
+                        const real dsw = xs2 * ((real)-30 + xs * ((real)60 - (real)30 * xs)) * B.sw_iw;
+                        f_lj = f_lj * sw - e_lj * dsw * inv_r;
+                        e_lj *= sw;
+                    }
+                    fr += f_lj;
                     fr = ok ? fr : (real)0;
                     fx[a] -= fr * dx; fy[a] -= fr * dy; fz[a] -= fr * dz;
                     if (ENERGY) {
-                        const real e = (PERIODIC ? qq * (inv_r + B.krf * r2v - B.crf) : qq * inv_r) + t * (s6 - (real)1);
+                        const real e = (PERIODIC ? qq * (inv_r + B.krf * r2v - B.crf) : qq * inv_r) + e_lj;
                         en[a] += ok ? (double)e : 0.0;
                     }
                 } else {

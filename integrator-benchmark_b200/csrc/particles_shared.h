@@ -36,6 +36,7 @@ struct PKParams {
     int N, nb_method, excl_words, n_units, n_generic;
     double box[3], inv_box[3];
     double cutoff2, krf, crf, restraint_k;
+    double switch_r, inv_switch_w;  // LJ switching function over [switch_r, cutoff]; inv_switch_w = 0: none
     int g_nb, g_restr;
     double oh, hh, tol;
     double settle_c[8];       // SETTLE positions: mO/M, mH/M, ra, rb, rc, 1/ra, 1/(2 rc)

@@ -234,4 +234,9 @@ LSI_EXPORT int lsi_program_flags(const lsi_program* p, int* msw, int* mh)
     return LSI_OK;
 }
 
-LSI_EXPORT void lsi_program_destroy(lsi_program* p) { delete p; }
+LSI_EXPORT void lsi_program_destroy(lsi_program* p)
+{
+    if (!p) return;
+    if (!p->staged.empty()) lsi_program_free_staged(p);
+    delete p;
+}

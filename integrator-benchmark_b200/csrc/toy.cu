@@ -21,6 +21,8 @@
 //     warp-uniform indices.
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "lsi_internal.h"
 #include "rng.cuh"
 
@@ -38,7 +40,10 @@
 namespace {
 
 constexpr int kMaxOps = 160;  // fits the 4 KB parameter space; longer programs use the global copy
-constexpr int kThreads = 256;
+#ifndef LSI_TOY_THREADS
+#define LSI_TOY_THREADS 256
+#endif
+constexpr int kThreads = LSI_TOY_THREADS;
 
 struct ToyProgram {
     int n_ops;
@@ -276,6 +281,9 @@ struct FusedStep {
 #ifndef LSI_TOY_MINB
 #define LSI_TOY_MINB 4
 #endif
+#ifndef LSI_TOY_PIPE
+#define LSI_TOY_PIPE 1
+#endif
 template <int POT, uint32_t CODE, int NOPS, bool NOISE32, bool TRACE = false>
 __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const __grid_constant__ ToyParams P)
 {
@@ -301,7 +309,14 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
         bool finite = true;
         const uint64_t rid = P.replica0 + (uint64_t)r;
         double x = P.x0 ? P.x0[r] : P.x_cache[lsi::cache_index(P.seed, rid, P.n_cache)];
-        double v = P.v0 ? P.v0[r] : P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_V0, 0u);
+        // start-of-leg velocities of a scalar system: normal number `leg` of the replica's TAG_V0 stream, so the start
+        // and the midpoint velocity of a two-leg protocol are the two halves of ONE Box-Muller pair
+        double n_start, n_mid;
+        {
+            const lsi::Philox4 q = lsi::philox_block(P.keys, rid, 0u, LSI_TAG_V0, 0u);
+            LSI_BM64(FT, q.x, q.y, 1.0, n_start, n_mid);
+        }
+        double v = P.v0 ? P.v0[r] : P.sigma * n_start;
         double heat = 0.0;
         const double half_m = 0.5 * P.mass;
         double f = code_entry_valid(CODE, NOPS) ? force<POT>(FT, x, P.p0) : 0.0;
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
 
         for (int leg = 0; leg < P.n_legs; ++leg) {
             if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
-                v = P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_VMID, (uint32_t)(leg - 1));
+                v = P.sigma * (leg == 1 ? n_mid : scalar_normal(FT, P.keys, rid, LSI_TAG_V0, (uint32_t)leg));
             const double E0 = pe + half_m * v * v;
             const double Q0 = heat;
             const uint32_t leg_base = (uint32_t)leg << 26;
@@ -322,30 +337,52 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
             if (TRACE) store_trace(P, leg, T, 0, r, x, v, 0.0);
 
             if (ALIGNED) {
-                // one Philox block feeds exactly U steps: every lane index is a constant
-                int s = 0;
-                uint32_t blk = 0;
-                for (; s + U <= P.n_steps; s += U, ++blk) {
-                    double n[4];
-                    normal_block<NOISE32>(FT, P.keys, rid, leg_base | blk, LSI_TAG_O, P.oc, n[0], n[1], n[2], n[3]);
+                // one Philox block feeds exactly U steps: every lane index is a constant.  The block of the NEXT U steps
+                // is generated in the same basic block as the current U steps (LSI_TOY_PIPE): the noise (integer Philox
+                // rounds, then Box-Muller with 2-4 independent fp64 chains) does not depend on x and v, so the scheduler
+                // interleaves it with the strictly sequential dynamics chain and a single warp keeps both the integer
+                // and the fp64 pipe fed.  Every block is still computed exactly once (the last one without a prefetch).
+                const int n_blk = (P.n_steps + U - 1) / U;
+                if (n_blk > 0) {
+                    double cur[4];
+                    normal_block<NOISE32>(FT, P.keys, rid, leg_base, LSI_TAG_O, P.oc, cur[0], cur[1], cur[2], cur[3]);
+                    int s = 0;
+#if LSI_TOY_PIPE
+#pragma unroll 2
+                    for (uint32_t blk = 1; blk < (uint32_t)n_blk; ++blk, s += U) {
+                        double nxt[4];
+                        normal_block<NOISE32>(FT, P.keys, rid, leg_base | blk, LSI_TAG_O, P.oc, nxt[0], nxt[1], nxt[2], nxt[3]);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            double xi[NO > 0 ? NO : 1];
+#pragma unroll
+                            for (int o = 0; o < NO; ++o) xi[o] = cur[u * NO + o];
+                            FusedStep<POT, CODE, NOPS>::run(FT, x, v, f, heat, P, half_m, xi);
+                            if (TRACE) record(s + u + 1);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+                    }
+#else
+                    for (uint32_t blk = 1; blk < (uint32_t)n_blk; ++blk, s += U) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            double xi[NO > 0 ? NO : 1];
+#pragma unroll
+                            for (int o = 0; o < NO; ++o) xi[o] = cur[u * NO + o];
+                            FusedStep<POT, CODE, NOPS>::run(FT, x, v, f, heat, P, half_m, xi);
+                            if (TRACE) record(s + u + 1);
+                        }
+                        normal_block<NOISE32>(FT, P.keys, rid, leg_base | blk, LSI_TAG_O, P.oc, cur[0], cur[1], cur[2], cur[3]);
+                    }
+#endif
+                    // last block: U steps, or fewer when n_steps is not a multiple of U
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        double xi[NO > 0 ? NO : 1];
-#pragma unroll
-                        for (int o = 0; o < NO; ++o) xi[o] = n[u * NO + o];
-                        FusedStep<POT, CODE, NOPS>::run(FT, x, v, f, heat, P, half_m, xi);
-                        if (TRACE) record(s + u + 1);
-                    }
-                }
-                if (s < P.n_steps) {
-                    double n[4];
-                    normal_block<NOISE32>(FT, P.keys, rid, leg_base | blk, LSI_TAG_O, P.oc, n[0], n[1], n[2], n[3]);
-#pragma unroll
-                    for (int u = 0; u < U - 1; ++u) {
                         if (s + u < P.n_steps) {
                             double xi[NO > 0 ? NO : 1];
 #pragma unroll
-                            for (int o = 0; o < NO; ++o) xi[o] = n[u * NO + o];
+                            for (int o = 0; o < NO; ++o) xi[o] = cur[u * NO + o];
                             FusedStep<POT, CODE, NOPS>::run(FT, x, v, f, heat, P, half_m, xi);
                             if (TRACE) record(s + u + 1);
                         }
@@ -418,7 +455,7 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
 
         for (int leg = 0; leg < P.n_legs; ++leg) {
             if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
-                v = P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_VMID, (uint32_t)(leg - 1));
+                v = P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_V0, (uint32_t)leg);
             const double E0 = potential<POT>(FT, x, P.p0) + half_m * v * v;
             const double Q0 = heat;
             const uint32_t leg_base = (uint32_t)leg << 26;
@@ -554,13 +591,10 @@ constexpr int slen(const char* s)
 // grid of the persistent fused kernels: one full wave (resident CTAs per SM x SMs), or fewer when there are fewer chunks
 unsigned fused_grid(int64_t n)
 {
-    static int wave = 0;
-    if (wave == 0) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;
-        wave = sms * LSI_TOY_MINB;
-    }
+    int dev = 0, sms = 0;  // two attribute queries per launch (no cache: devices of one process may differ)
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        sms = 148;
+    const int64_t wave = (int64_t)sms * LSI_TOY_MINB;
     const int64_t chunks = (n + kThreads - 1) / kThreads;
     return (unsigned)(chunks < wave ? chunks : wave);
 }
@@ -718,16 +752,18 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
         if (n_ops <= kMaxOps) {
             for (int i = 0; i < n_ops; ++i) { tp.kind[i] = kinds[i]; tp.c0[i] = c0[i]; tp.c1[i] = c1[i]; }
         } else {
-            // long multi-timestep strings: stage the program in device memory (stream-ordered)
+            // long multi-timestep strings: the tables live in device memory, cached on the program handle
+            // (lsi_program_stage: no allocation, copy or synchronisation after the first launch)
             const size_t nb = (size_t)n_ops * (2 * sizeof(double)) + (size_t)n_ops;
-            LSI_CUDA_CHECK(cudaMallocAsync(&ext, nb, st));
+            std::vector<unsigned char> bytes(nb);
+            std::memcpy(bytes.data(), c0.data(), n_ops * sizeof(double));
+            std::memcpy(bytes.data() + n_ops * sizeof(double), c1.data(), n_ops * sizeof(double));
+            std::memcpy(bytes.data() + 2 * n_ops * sizeof(double), kinds.data(), n_ops);
+            const int src = lsi_program_stage(prog, bytes.data(), nb, &ext);
+            if (src != LSI_OK) return src;
             double* d0 = (double*)ext;
             double* d1 = d0 + n_ops;
             unsigned char* dk = (unsigned char*)(d1 + n_ops);
-            LSI_CUDA_CHECK(cudaMemcpyAsync(d0, c0.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
-            LSI_CUDA_CHECK(cudaMemcpyAsync(d1, c1.data(), n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
-            LSI_CUDA_CHECK(cudaMemcpyAsync(dk, kinds.data(), n_ops, cudaMemcpyHostToDevice, st));
-            LSI_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors die at return
             tp.ext_c0 = d0; tp.ext_c1 = d1; tp.ext_kind = dk;
         }
         switch (sys->potential) {
@@ -738,7 +774,6 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
         }
     }
     if (err != cudaSuccess) return lsi_set_error(LSI_ERR_CUDA, "toy kernel launch failed: %s", cudaGetErrorString(err));
-    if (ext) LSI_CUDA_CHECK(cudaFreeAsync(ext, st));
     if (a->moments) return lsi_finalize_moments(P.partials, launched ? (int)fused_grid(a->n_replicas) : (int)grid, a->moments, stream);
     return LSI_OK;
 }

@@ -114,7 +114,7 @@ class ParticleSystem:
     """Particle system (lsi_system*, LSI_SYS_PARTICLES) built from a plain description dict:
 
         n_atoms, mass, charge, sigma, epsilon,
-        nonbonded_method ("NoCutoff" | "CutoffPeriodic"), cutoff, box, rf_dielectric,
+        nonbonded_method ("NoCutoff" | "CutoffPeriodic"), cutoff, box, rf_dielectric, switch_distance,
         exclusions (n,2), exception_atoms (n,2), exception_params (n,3: chargeProd, sigma, epsilon),
         bond_atoms (n,2), bond_params (n,2: r0, k), angle_atoms (n,3), angle_params (n,2: theta0, k),
         torsion_atoms (n,4), torsion_params (n,3: periodicity, phase, k), restraint_k,
@@ -180,6 +180,7 @@ class ParticleSystem:
         b, d.constraint_dist = dbl("constraint_dist")
         assert len(a) == len(b)
         d.constraint_tolerance = float(desc.get("constraint_tolerance", 1e-8))
+        d.switch_distance = float(desc.get("switch_distance", 0.0) or 0.0)
         h = ctypes.c_void_p()
         check(lib.lsi_system_create_particles(ctypes.byref(d), ctypes.byref(h)))
         self._h = h

@@ -80,10 +80,12 @@ def load_system_xml(source, pme_as_reaction_field=False, ignore_unknown_forces=F
                 method = "CutoffPeriodic"
             if method not in ("NoCutoff", "CutoffPeriodic"):
                 raise NotImplementedError("NonbondedForce method %s is not built" % method)
-            if force.get("useSwitchingFunction", "0") not in ("0", "false") and not pme_as_reaction_field:
-                raise NotImplementedError("switching functions are not built")
             desc["nonbonded_method"] = method
             desc["cutoff"] = _f(force, "cutoff", 0.0)
+            if force.get("useSwitchingFunction", "0") not in ("0", "false"):
+                if method != "CutoffPeriodic":
+                    raise NotImplementedError("a switching function needs a cutoff method")
+                desc["switch_distance"] = _f(force, "switchingDistance", 0.0)
             desc["rf_dielectric"] = _f(force, "rfDielectric", 78.3)
             parts = list(force.find("Particles"))
             if len(parts) != n:
@@ -187,10 +189,12 @@ def system_to_xml(desc, openmm_version="7.2"):
             ET.SubElement(tors, "Torsion", k=repr(float(k)), p1=str(int(a)), p2=str(int(b)), p3=str(int(c)), p4=str(int(d_)),
                           periodicity=str(int(round(per))), phase=repr(float(ph)))
     method = {"NoCutoff": 0, "CutoffPeriodic": 2}[desc.get("nonbonded_method", "NoCutoff")]
+    sw = float(desc.get("switch_distance", 0.0) or 0.0)
     f = ET.SubElement(forces, "Force", alpha="0", cutoff=repr(float(desc.get("cutoff", 1.0) or 1.0)), dispersionCorrection="0",
                       ewaldTolerance=".0005", forceGroup=str(g.get("nonbonded", 0)), method=str(method), nx="0", ny="0", nz="0",
-                      recipForceGroup="-1", rfDielectric=repr(float(desc.get("rf_dielectric", 78.3))), switchingDistance="-1",
-                      type="NonbondedForce", useSwitchingFunction="0", version="2")
+                      recipForceGroup="-1", rfDielectric=repr(float(desc.get("rf_dielectric", 78.3))),
+                      switchingDistance=repr(sw) if sw > 0 else "-1",
+                      type="NonbondedForce", useSwitchingFunction="1" if sw > 0 else "0", version="2")
     nbp = ET.SubElement(f, "Particles")
     q = np.asarray(desc.get("charge", np.zeros(n)), dtype=float)
     sig = np.asarray(desc.get("sigma", np.ones(n)), dtype=float)

@@ -26,8 +26,7 @@ def load_alanine(constrained=True):
 
 
 water_cluster_rigid = _make(systems.water_cluster, "water_cluster_rigid", "Reference", 1.0, 100000, constrained=True)
-water_cluster_flexible = _make(systems.water_cluster, "water_cluster_flexible", "Reference", 0.5, 200000,
-                               thinning_interval=20000, constrained=False)
+water_cluster_flexible = _make(systems.water_cluster, "water_cluster_flexible", "Reference", 1.0, 100000, constrained=False)
 tiny_waterbox = _make(systems.tiny_waterbox, "tiny_waterbox_constrained", "CUDA", 1.0, 100000, constrained=True)
 alanine_constrained = _make(systems.alanine_dipeptide, "alanine_constrained", "Reference", 1.0, 50000, constrained=True)
 alanine_unconstrained = _make(systems.alanine_dipeptide, "alanine_unconstrained", "Reference", 1.0, 50000,

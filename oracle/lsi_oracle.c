@@ -177,8 +177,9 @@ static void normals4_f32(const uint32_t r[4], double n[4])
 /*
  * Runs, for each replica, n_legs legs of `n_steps` applications of the
  * splitting program (bookkeepers.py:247-295 / low_dimensional_systems.py:160-184):
- *   leg 0: x0 from cache (or x0_in), v0 ~ MB (or v0_in)
- *   leg 1: x continues; v resampled (marginal 0 = "configuration") or kept (1 = "full")
+ *   leg 0: x0 from cache (or x0_in), v0 ~ MB (or v0_in): normal 0 of the replica's TAG_V0 scalar stream
+ *   leg l: x continues; v resampled (marginal 0 = "configuration": normal l of the same TAG_V0 stream, so the start
+ *          and midpoint velocities of a two-leg protocol share one Box-Muller pair) or kept (1 = "full")
  * W[leg] = ((E_end - E_start) - (Q_end - Q_start)) / kT     (bookkeepers.py:237-243)
  * Optional traces hold, per leg, n_steps+1 entries (entry 0 = leg start) of
  * x, v and the cumulative W in kT (numba_integrators.py:56-61).
@@ -210,7 +211,7 @@ ORC_API int orc_toy_protocol(int pot_kind, const double* pot_params, double mass
         double v = v0_in ? v0_in[r] : sigma * scalar_normal(seed, rid, TAG_V0, 0u);
         double heat = 0.0;
         for (int leg = 0; leg < n_legs; ++leg) {
-            if (leg > 0 && marginal == 0) v = sigma * scalar_normal(seed, rid, TAG_VMID, (uint32_t)(leg - 1));
+            if (leg > 0 && marginal == 0) v = sigma * scalar_normal(seed, rid, TAG_V0, (uint32_t)leg);
             const double E0 = toy_potential(pot_kind, pot_params, x) + 0.5 * mass * v * v;
             const double Q0 = heat;
             double wd = 0.0;
@@ -373,6 +374,7 @@ typedef struct {
     const int32_t* constraint_atoms; /* [n][2] */
     const double* constraint_dist;
     double constraint_tolerance;
+    double switch_distance; /* LJ switching function starts here (<= 0: plain truncation); OpenMM NonbondedForce */
 } OrcParticles;
 
 static inline int in_group(int term_group, int g) { return g < 0 || term_group == g; }
@@ -384,7 +386,7 @@ static void min_image(const OrcParticles* S, double d[3])
 }
 
 /* forces (3N, overwritten) and energy of the force classes selected by group g (-1 = all) */
-static double particles_forces(const OrcParticles* S, const double* x, int g, double* f)
+static double particles_forces_f64(const OrcParticles* S, const double* x, int g, double* f)
 {
     const int N = S->n_atoms;
     double E = 0.0;
@@ -416,9 +418,19 @@ static double particles_forces(const OrcParticles* S, const double* x, int g, do
                 const double eps = sqrt(S->epsilon[i] * S->epsilon[j]);
                 const double sr2 = sig * sig / r2, sr6 = sr2 * sr2 * sr2;
                 const double qq = ONE_4PI_EPS0 * S->charge[i] * S->charge[j];
-                /* dE/dr * (1/r): LJ 4 eps (12 sr12 - 6 sr6)/r^2 ; Coulomb qq (1/r^3 - 2 krf) */
-                const double fr = 4.0 * eps * (12.0 * sr6 * sr6 - 6.0 * sr6) / r2 + qq * (inv_r * inv_r * inv_r - 2.0 * krf);
-                E += 4.0 * eps * (sr6 * sr6 - sr6) + qq * (inv_r + krf * r2 - crf);
+                /* -dE/dr * (1/r): LJ 4 eps (12 sr12 - 6 sr6)/r^2 ; Coulomb qq (1/r^3 - 2 krf) */
+                double e_lj = 4.0 * eps * (sr6 * sr6 - sr6);
+                double f_lj = 4.0 * eps * (12.0 * sr6 * sr6 - 6.0 * sr6) / r2;
+                if (S->nonbonded_method == 1 && S->switch_distance > 0.0 && r > S->switch_distance) {
+                    /* OpenMM's switching function: E S(x), S = 1 - 6 x^5 + 15 x^4 - 10 x^3 */
+                    const double w = rc - S->switch_distance, xs = (r - S->switch_distance) / w;
+                    const double sw = 1.0 + xs * xs * xs * (-10.0 + xs * (15.0 - 6.0 * xs));
+                    const double dsw = xs * xs * (-30.0 + xs * (60.0 - 30.0 * xs)) / w;
+                    f_lj = f_lj * sw - e_lj * dsw * inv_r;
+                    e_lj *= sw;
+                }
+                const double fr = f_lj + qq * (inv_r * inv_r * inv_r - 2.0 * krf);
+                E += e_lj + qq * (inv_r + krf * r2 - crf);
                 for (int c = 0; c < 3; ++c) {
                     f[3 * i + c] -= fr * d[c];
                     f[3 * j + c] += fr * d[c];
@@ -531,7 +543,222 @@ static double particles_forces(const OrcParticles* S, const double* x, int g, do
 
 ORC_API double orc_particles_energy_forces(const OrcParticles* S, const double* x, int group, double* f)
 {
-    return particles_forces(S, x, group, f);
+    return particles_forces_f64(S, x, group, f);
+}
+
+/* ---- "mixed" precision restatement of the same forces (how the reference configures OpenMM's CUDA platform,
+ * benchmark/testsystems/configuration.py:42-45: fp32 pair / bonded arithmetic, fp64 state and accumulation of
+ * energies).  It follows the engine's mixed path (integrator-benchmark_b200/csrc/particles_kernel.cuh) operation
+ * by operation where that matters for rounding: positions wrapped into the box in fp64 and THEN rounded to float,
+ * charges pre-multiplied by sqrt(K), every atom accumulates its own force over a full shell of partners in float,
+ * pair energies are float values summed in double, bonded terms are evaluated once per term in float, the restraint
+ * uses the unwrapped position rounded to float.  It is not bit-identical to the GPU (rsqrt.approx vs 1/sqrtf, order
+ * of the partner loop), which is why tests compare with a tolerance of 1e-5 of the energy scale. */
+static double particles_forces_f32(const OrcParticles* S, const double* x, int g, double* f)
+{
+    const int N = S->n_atoms;
+    const int periodic = S->nonbonded_method == 1;
+    double E = 0.0;
+    float* xs = (float*)malloc(sizeof(float) * 3 * N);
+    float* ff = (float*)calloc((size_t)3 * N, sizeof(float));
+    for (int i = 0; i < N; ++i)
+        for (int c = 0; c < 3; ++c) {
+            double p = x[3 * i + c];
+            if (periodic) p -= S->box[c] * floor(p / S->box[c]);
+            xs[3 * i + c] = (float)p;
+        }
+    const float bx[3] = {(float)S->box[0], (float)S->box[1], (float)S->box[2]};
+    const float ibx[3] = {periodic ? (float)(1.0 / S->box[0]) : 0.f, periodic ? (float)(1.0 / S->box[1]) : 0.f,
+                          periodic ? (float)(1.0 / S->box[2]) : 0.f};
+#define MIN_IMAGE_F(d)                                                         \
+    do {                                                                       \
+        if (periodic)                                                          \
+            for (int c_ = 0; c_ < 3; ++c_) (d)[c_] = (d)[c_] - bx[c_] * rintf((d)[c_] * ibx[c_]); \
+    } while (0)
+    if (in_group(S->group_nonbonded, g)) {
+        unsigned char* ex = (unsigned char*)calloc((size_t)N * N, 1);
+        for (int k = 0; k < S->n_exclusions; ++k) {
+            const int i = S->exclusions[2 * k], j = S->exclusions[2 * k + 1];
+            ex[(size_t)i * N + j] = ex[(size_t)j * N + i] = 1;
+        }
+        for (int k = 0; k < S->n_exceptions; ++k) {
+            const int i = S->exception_atoms[2 * k], j = S->exception_atoms[2 * k + 1];
+            ex[(size_t)i * N + j] = ex[(size_t)j * N + i] = 1;
+        }
+        const double rc = S->cutoff, eps_rf = S->rf_dielectric;
+        const float rc2 = (float)(rc * rc);
+        const double krf_d = periodic ? (1.0 / (rc * rc * rc)) * (eps_rf - 1.0) / (2.0 * eps_rf + 1.0) : 0.0;
+        const float krf = (float)krf_d, krf2 = (float)(2.0 * krf_d);
+        const float crf = periodic ? (float)((1.0 / rc) * (3.0 * eps_rf) / (2.0 * eps_rf + 1.0)) : 0.f;
+        const int use_switch = periodic && S->switch_distance > 0.0 && S->switch_distance < rc;
+        const float sw_r = (float)S->switch_distance, sw_iw = use_switch ? (float)(1.0 / (rc - S->switch_distance)) : 0.f;
+        const double sk = sqrt(ONE_4PI_EPS0);
+        double e_pairs = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const float qi = (float)(S->charge[i] * sk), hsi = (float)(0.5 * S->sigma[i]), sei = (float)(2.0 * sqrt(S->epsilon[i]));
+            float fx = 0.f, fy = 0.f, fz = 0.f;
+            double en = 0.0;
+            for (int j = 0; j < N; ++j) {
+                if (j == i || ex[(size_t)i * N + j]) continue;
+                float d[3] = {xs[3 * j] - xs[3 * i], xs[3 * j + 1] - xs[3 * i + 1], xs[3 * j + 2] - xs[3 * i + 2]};
+                MIN_IMAGE_F(d);
+                const float r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                if (periodic && !(r2 < rc2)) continue;
+                const float inv_r = 1.0f / sqrtf(r2), inv_r2 = inv_r * inv_r;
+                const float qq = qi * (float)(S->charge[j] * sk);
+                float fr = periodic ? qq * (inv_r * inv_r2 - krf2) : qq * inv_r * inv_r2;
+                float e = periodic ? qq * (inv_r + krf * r2 - crf) : qq * inv_r;
+                const float sej = (float)(2.0 * sqrt(S->epsilon[j]));
+                if (sei != 0.f && sej != 0.f) {
+                    const float sig = hsi + (float)(0.5 * S->sigma[j]);
+                    const float s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
+                    const float t = sei * sej * s6; /* 4 eps s6 */
+                    float f_lj = t * (12.0f * s6 - 6.0f) * inv_r2;
+                    float e_lj = t * (s6 - 1.0f);
+                    if (use_switch) {
+                        const float xs_ = fmaxf((r2 * inv_r - sw_r) * sw_iw, 0.f), xs2 = xs_ * xs_;
+                        const float sw = 1.0f + xs2 * xs_ * (-10.0f + xs_ * (15.0f - 6.0f * xs_));
+                        const float dsw = xs2 * (-30.0f + xs_ * (60.0f - 30.0f * xs_)) * sw_iw;
+                        f_lj = f_lj * sw - e_lj * dsw * inv_r;
+                        e_lj *= sw;
+                    }
+                    fr += f_lj;
+                    e += e_lj;
+                }
+                fx -= fr * d[0]; fy -= fr * d[1]; fz -= fr * d[2];
+                en += (double)e;
+            }
+            ff[3 * i] += fx; ff[3 * i + 1] += fy; ff[3 * i + 2] += fz;
+            e_pairs += 0.5 * en; /* every pair is visited from both ends */
+        }
+        E += e_pairs;
+        for (int k = 0; k < S->n_exceptions; ++k) {
+            const int i = S->exception_atoms[2 * k], j = S->exception_atoms[2 * k + 1];
+            const float kqq = (float)(ONE_4PI_EPS0 * S->exception_params[3 * k]), sig = (float)S->exception_params[3 * k + 1],
+                        eps4 = (float)(4.0 * S->exception_params[3 * k + 2]);
+            float d[3] = {xs[3 * j] - xs[3 * i], xs[3 * j + 1] - xs[3 * i + 1], xs[3 * j + 2] - xs[3 * i + 2]};
+            MIN_IMAGE_F(d);
+            const float r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            if (periodic && r2 >= rc2) continue;
+            const float inv_r = 1.0f / sqrtf(r2), inv_r2 = inv_r * inv_r;
+            const float s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
+            const float e = eps4 * (s6 * s6 - s6) + kqq * inv_r;
+            const float fr = eps4 * (12.0f * s6 * s6 - 6.0f * s6) * inv_r2 + kqq * inv_r * inv_r2;
+            E += (double)e;
+            for (int c = 0; c < 3; ++c) {
+                ff[3 * i + c] -= fr * d[c];
+                ff[3 * j + c] += fr * d[c];
+            }
+        }
+        free(ex);
+    }
+    if (in_group(S->group_bonds, g))
+        for (int k = 0; k < S->n_bonds; ++k) {
+            const int i = S->bond_atoms[2 * k], j = S->bond_atoms[2 * k + 1];
+            const float r0 = (float)S->bond_params[2 * k], kb = (float)S->bond_params[2 * k + 1];
+            float d[3] = {xs[3 * j] - xs[3 * i], xs[3 * j + 1] - xs[3 * i + 1], xs[3 * j + 2] - xs[3 * i + 2]};
+            MIN_IMAGE_F(d);
+            const float r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            const float inv_r = 1.0f / sqrtf(r2), dr = r2 * inv_r - r0;
+            E += (double)(0.5f * kb * dr * dr);
+            const float fr = kb * dr * inv_r;
+            for (int c = 0; c < 3; ++c) {
+                ff[3 * i + c] += fr * d[c];
+                ff[3 * j + c] -= fr * d[c];
+            }
+        }
+    if (in_group(S->group_angles, g))
+        for (int k = 0; k < S->n_angles; ++k) {
+            const int i = S->angle_atoms[3 * k], j = S->angle_atoms[3 * k + 1], l = S->angle_atoms[3 * k + 2];
+            const float th0 = (float)S->angle_params[2 * k], ka = (float)S->angle_params[2 * k + 1];
+            float a[3], b[3];
+            for (int c = 0; c < 3; ++c) {
+                a[c] = xs[3 * i + c] - xs[3 * j + c];
+                b[c] = xs[3 * l + c] - xs[3 * j + c];
+            }
+            MIN_IMAGE_F(a);
+            MIN_IMAGE_F(b);
+            const float ira = 1.0f / sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+            const float irb = 1.0f / sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+            float ct = (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) * ira * irb;
+            ct = fminf(fmaxf(ct, -1.0f), 1.0f);
+            const float dth = acosf(ct) - th0;
+            const float st = sqrtf(fmaxf(1.0f - ct * ct, 1e-24f));
+            const float cf = ka * dth / st; /* force = +cf d cos(theta)/d r */
+            const float iab = ira * irb, ia2 = ira * ira, ib2 = irb * irb;
+            E += (double)(0.5f * ka * dth * dth);
+            for (int c = 0; c < 3; ++c) {
+                const float ga = b[c] * iab - ct * a[c] * ia2, gb = a[c] * iab - ct * b[c] * ib2;
+                ff[3 * i + c] += cf * ga;
+                ff[3 * l + c] += cf * gb;
+                ff[3 * j + c] -= cf * (ga + gb);
+            }
+        }
+    if (in_group(S->group_torsions, g))
+        for (int k = 0; k < S->n_torsions; ++k) {
+            const int a1 = S->torsion_atoms[4 * k], a2 = S->torsion_atoms[4 * k + 1], a3 = S->torsion_atoms[4 * k + 2],
+                      a4 = S->torsion_atoms[4 * k + 3];
+            const int nper = (int)floor(S->torsion_params[3 * k] + 0.5);
+            const float cph = (float)cos(S->torsion_params[3 * k + 1]), sph = (float)sin(S->torsion_params[3 * k + 1]);
+            const float kt = (float)S->torsion_params[3 * k + 2];
+            float b1[3], b2[3], b3[3];
+            for (int c = 0; c < 3; ++c) {
+                b1[c] = xs[3 * a2 + c] - xs[3 * a1 + c];
+                b2[c] = xs[3 * a3 + c] - xs[3 * a2 + c];
+                b3[c] = xs[3 * a4 + c] - xs[3 * a3 + c];
+            }
+            MIN_IMAGE_F(b1);
+            MIN_IMAGE_F(b2);
+            MIN_IMAGE_F(b3);
+            const float n1[3] = {b1[1] * b2[2] - b1[2] * b2[1], b1[2] * b2[0] - b1[0] * b2[2], b1[0] * b2[1] - b1[1] * b2[0]};
+            const float n2[3] = {b2[1] * b3[2] - b2[2] * b3[1], b2[2] * b3[0] - b2[0] * b3[2], b2[0] * b3[1] - b2[1] * b3[0]};
+            const float b2sq = b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2];
+            const float ib2 = 1.0f / sqrtf(b2sq), b2n = b2sq * ib2;
+            const float yy = b2n * (b1[0] * n2[0] + b1[1] * n2[1] + b1[2] * n2[2]);
+            const float xx = n1[0] * n2[0] + n1[1] * n2[1] + n1[2] * n2[2];
+            const float n1sq = n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2];
+            const float n2sq = n2[0] * n2[0] + n2[1] * n2[1] + n2[2] * n2[2];
+            /* cos(n phi), sin(n phi) from cos phi, sin phi by the multiple-angle recurrence (as the kernel) */
+            const float inorm = 1.0f / sqrtf(fmaxf(n1sq * n2sq, 1e-36f));
+            const float c1 = xx * inorm, s1 = yy * inorm;
+            float cn = c1, sn = s1;
+            for (int q = 1; q < nper; ++q) {
+                const float c2 = cn * c1 - sn * s1;
+                sn = sn * c1 + cn * s1;
+                cn = c2;
+            }
+            if (nper == 0) { cn = 1.0f; sn = 0.0f; }
+            E += (double)(kt * (1.0f + cn * cph + sn * sph));
+            const float dE = -kt * (float)nper * (sn * cph - cn * sph);
+            const float k1 = -b2n / n1sq, k4 = b2n / n2sq, ib2sq = ib2 * ib2;
+            const float u = (b1[0] * b2[0] + b1[1] * b2[1] + b1[2] * b2[2]) * ib2sq;
+            const float w = (b3[0] * b2[0] + b3[1] * b2[1] + b3[2] * b2[2]) * ib2sq;
+            for (int c = 0; c < 3; ++c) {
+                const float g1 = k1 * n1[c], g4 = k4 * n2[c];
+                ff[3 * a1 + c] += -dE * g1;
+                ff[3 * a2 + c] += -dE * (-g1 - u * g1 + w * g4);
+                ff[3 * a3 + c] += -dE * (-g4 + u * g1 - w * g4);
+                ff[3 * a4 + c] += -dE * g4;
+            }
+        }
+    if (in_group(S->group_restraint, g) && S->restraint_k != 0.0) {
+        const float kr = (float)S->restraint_k;
+        for (int i = 0; i < N; ++i) {
+            const float px = (float)x[3 * i], py = (float)x[3 * i + 1], pz = (float)x[3 * i + 2];
+            ff[3 * i] -= kr * px; ff[3 * i + 1] -= kr * py; ff[3 * i + 2] -= kr * pz;
+            E += (double)(0.5f * kr * (px * px + py * py + pz * pz));
+        }
+    }
+#undef MIN_IMAGE_F
+    for (int i = 0; i < 3 * N; ++i) f[i] = (double)ff[i];
+    free(xs);
+    free(ff);
+    return E;
+}
+
+ORC_API double orc_particles_energy_forces_f32(const OrcParticles* S, const double* x, int group, double* f)
+{
+    return particles_forces_f32(S, x, group, f);
 }
 
 /* ---- constraints ----------------------------------------------------------------------- */
@@ -740,6 +967,7 @@ static void atom_normals(uint64_t seed, uint64_t rid, uint32_t draw, uint32_t ta
 
 /* flags */
 #define ORC_FLAG_ROUND_MIDPOINT_X_FP32 1 /* bookkeepers.py:266,298-305: x passes through a float32 frame */
+#define ORC_FLAG_FORCE_FP32 2            /* forces and potential energies from particles_forces_f32 ("mixed") */
 
 /*
  * Protocol for particle systems (bookkeepers.py:184-295).  x_cache: [n_cache][N][3];
@@ -763,6 +991,8 @@ ORC_API int orc_particles_protocol(const OrcParticles* S, double kT, int n_ops, 
     for (int i = 0; i < n_ops; ++i) n_O += (op_kind[i] == OP_O);
     const int64_t T = (int64_t)n_steps + 1;
     int rc_all = 0;
+    double (*const particles_forces)(const OrcParticles*, const double*, int, double*) =
+        (flags & ORC_FLAG_FORCE_FP32) ? particles_forces_f32 : particles_forces_f64;
 
 #pragma omp parallel for schedule(dynamic, 1)
     for (int64_t r = 0; r < n_replicas; ++r) {
@@ -888,7 +1118,7 @@ ORC_API int orc_particles_hmc(const OrcParticles* S, double kT, int64_t n, int n
         memcpy(x, x_in + r * D, sizeof(double) * D);
         memcpy(xu, x, sizeof(double) * D);
         constrain_positions(S, xu, x);
-        double pe = particles_forces(S, x, -1, f);
+        double pe = particles_forces_f64(S, x, -1, f);
         int n_acc = 0, n_first = 0;
         for (int round = 0; round < n_rounds; ++round) {
             atom_normals(seed, rid, 2u * (uint32_t)round, TAG_EQ, N, 0, xi);
@@ -915,7 +1145,7 @@ ORC_API int orc_particles_hmc(const OrcParticles* S, double kT, int64_t n, int n
                     constrain_positions(S, xu, x);
                     for (int k = 0; k < D; ++k) v[k] = v[k] + (x[k] - xi[k]) / dt;
                     constrain_velocities(S, x, v);
-                    pe_new = particles_forces(S, x, -1, f);
+                    pe_new = particles_forces_f64(S, x, -1, f);
                     for (int k = 0; k < D; ++k) v[k] = v[k] + 0.5 * dt * f[k] / S->mass[k / 3];
                     constrain_velocities(S, x, v);
                 }

@@ -177,7 +177,7 @@ class OrcParticles(ctypes.Structure):
         ("n_settle", ctypes.c_int32), ("settle_atoms", c_int32_pp), ("settle_oh", ctypes.c_double),
         ("settle_hh", ctypes.c_double),
         ("n_constraints", ctypes.c_int32), ("constraint_atoms", c_int32_pp), ("constraint_dist", c_double_p),
-        ("constraint_tolerance", ctypes.c_double),
+        ("constraint_tolerance", ctypes.c_double), ("switch_distance", ctypes.c_double),
     ]
 
 
@@ -207,6 +207,7 @@ def make_particles(desc):
     box = list(desc.get("box", (0.0, 0.0, 0.0)))
     S.box = (ctypes.c_double * 3)(*box)
     S.rf_dielectric = float(desc.get("rf_dielectric", 78.3))
+    S.switch_distance = float(desc.get("switch_distance", 0.0) or 0.0)
 
     def ilist(key, cols):
         a = _i32(desc.get(key), cols)
@@ -240,11 +241,12 @@ def make_particles(desc):
     return S, keep
 
 
-def particles_energy_forces(desc, x, group=-1):
+def particles_energy_forces(desc, x, group=-1, force_fp32=False):
+    """potential energy and forces; force_fp32: the "mixed" restatement (fp32 pair / bonded arithmetic, energies summed in fp64)"""
     S, _keep = make_particles(desc)
     x = _f64(x).reshape(-1)
     f = np.zeros_like(x)
-    fn = lib().orc_particles_energy_forces
+    fn = lib().orc_particles_energy_forces_f32 if force_fp32 else lib().orc_particles_energy_forces
     fn.restype = ctypes.c_double
     e = fn(ctypes.byref(S), _dp(x), int(group), _dp(f))
     return e, f.reshape(-1, 3)
@@ -268,7 +270,10 @@ def constrain_velocities(desc, x, v):
 
 def particles_protocol(desc, splitting, dt, gamma, kT, n_replicas, n_steps, marginal="configuration", seed=0,
                        replica0=0, x_cache=None, x0=None, v0=None, n_legs=2, traces=False, want_direct=False,
-                       noise_fp32=False, round_midpoint=False, program=None):
+                       noise_fp32=False, round_midpoint=False, program=None, force_fp32=False, mixed=False):
+    """mixed=True is the engine's LSI_PRECISION_MIXED: fp32 O noise AND fp32 force / energy arithmetic."""
+    if mixed:
+        noise_fp32 = force_fp32 = True
     prog = program or _sp.compile_splitting(splitting, dt, gamma)
     kind, group, frac, a, b = _ops_arrays(prog)
     S, _keep = make_particles(desc)
@@ -289,7 +294,7 @@ def particles_protocol(desc, splitting, dt, gamma, kT, n_replicas, n_steps, marg
         group.ctypes.data_as(c_int32_p), _dp(frac), _dp(a), _dp(b), ctypes.c_double(dt),
         ctypes.c_uint64(seed), ctypes.c_uint64(replica0), ctypes.c_int64(n),
         _dp(xc), ctypes.c_int64(0 if xc is None else len(xc)), _dp(x0a), _dp(v0a),
-        int(n_steps), MARGINAL[marginal], int(n_legs), int(bool(noise_fp32)), int(bool(round_midpoint)),
+        int(n_steps), MARGINAL[marginal], int(n_legs), int(bool(noise_fp32)), int(bool(round_midpoint)) | (2 if force_fp32 else 0),
         _dp(W), _dp(Q), _dp(wd), _dp(xf), _dp(vf), _dp(tx), _dp(tv), _dp(tpe), _dp(tke), _dp(th), _dp(twd))
     assert rc == 0
     out = {"W": W, "Q": Q, "x_final": xf, "v_final": vf}
