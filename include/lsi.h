@@ -304,7 +304,10 @@ int lsi_bootstrap_nested(const double* w, const int64_t* row_offsets, int64_t n_
  * FMA-pipe microbenchmark (no reference counterpart): blocks x 256 threads, each running
  * iters x 8 independent fused multiply-adds in fp64 (LSI_PRECISION_DOUBLE) or fp32;
  * flops = blocks * 256 * iters * 16.  bench.py times it with CUDA events to obtain the
- * measured non-tensor FMA peak that the FMA-bound kernels are held against. */
+ * measured non-tensor FMA peak that the FMA-bound kernels are held against.
+ * precision = 10 + k (k = 0..4): dispatch test, each iteration runs the 8 DFMAs interleaved with 8 k independent
+ * 32-bit integer multiply-adds; the time against k shows whether integer work hides under fp64 instructions
+ * (scripts/microbench_dispatch.py, profiles/README.md). */
 int lsi_microbench_fma(int precision, int64_t iters, int blocks, void* sink, void* stream);
 
 /* Test hook (no reference counterpart): evaluates the lean fp64 functions the toy kernels use for Box-Muller noise

@@ -21,6 +21,34 @@ __global__ void __launch_bounds__(256) fma_kernel(int64_t iters, T seed, T* __re
     if (s == (T)-1.2345) sink[0] = s;  // never true; keeps the chains alive
 }
 
+// Dispatch test behind the toy kernels' roofline argument: per iteration 8 independent DFMAs interleaved with
+// `N_INT` x 8 independent 32-bit integer multiply-adds (the instruction class of Philox).  If a warp-wide fp64
+// instruction only occupied the 16-lane fp64 pipe for two cycles, the integer work would hide under it (time = the
+// fp64-only time until N_INT > 1); if it holds the sub-partition's dispatch port for both cycles, every integer
+// instruction adds a cycle (time = fp64 time x (1 + N_INT / 2)).
+template <int N_INT>
+__global__ void __launch_bounds__(256) dispatch_mix_kernel(int64_t iters, double seed, double* __restrict__ sink)
+{
+    double a0 = seed + (double)threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    unsigned k[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) k[j] = threadIdx.x * 2654435761u + j;
+    const double m = 0.999993, c = 1.0e-3;
+    for (int64_t i = 0; i < iters; ++i) {
+        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+#pragma unroll
+        for (int r = 0; r < N_INT; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) k[j] = k[j] * 0xD2511F53u + 0x9E3779B9u;
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    unsigned x = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x ^= k[j];
+    if (s == -1.2345 || x == 0x12345u) sink[0] = s + (double)x;  // never true; keeps the chains alive
+}
+
 // test hook: the lean fp64 functions of fastmath64.cuh, element-wise
 __global__ void fastmath_kernel(int which, int64_t n, const double* __restrict__ x, double* __restrict__ out0, double* __restrict__ out1)
 {
@@ -83,7 +111,15 @@ LSI_EXPORT int lsi_test_fastmath(int which, int64_t n, const double* x, double* 
 LSI_EXPORT int lsi_microbench_fma(int precision, int64_t iters, int blocks, void* sink, void* stream)
 {
     if (!sink || iters <= 0 || blocks <= 0) return lsi_set_error(LSI_ERR_ARG, "lsi_microbench_fma: bad argument");
-    if (precision == LSI_PRECISION_DOUBLE)
+    if (precision >= 10 && precision <= 14) {  // dispatch test: 8 DFMA + (precision - 10) x 8 IMAD per iteration
+        switch (precision - 10) {
+        case 0: dispatch_mix_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0, (double*)sink); break;
+        case 1: dispatch_mix_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0, (double*)sink); break;
+        case 2: dispatch_mix_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0, (double*)sink); break;
+        case 3: dispatch_mix_kernel<3><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0, (double*)sink); break;
+        default: dispatch_mix_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0, (double*)sink); break;
+        }
+    } else if (precision == LSI_PRECISION_DOUBLE)
         fma_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0, (double*)sink);
     else
         fma_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0f, (float*)sink);

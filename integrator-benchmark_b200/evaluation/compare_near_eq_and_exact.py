@@ -276,9 +276,20 @@ def estimate_kl_div_adaptive_outer_loop_sharded(noneq_sim, marginal, outer_sampl
     import torch
     import torch.distributed as dist
     from .. import parallel
+    from .. import _rngstate
     rank, world, _ = parallel.world()
     on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     device = "cuda" if (on and dist.get_backend() == "nccl") else "cpu"
+    # Ranks must draw DIFFERENT trajectories, or the union double-counts samples and the stopping rule fires early:
+    # (1) replica ids (Philox streams) come from disjoint per-rank ranges; (2) the numpy generator that picks the outer
+    # configurations must differ between ranks -- if two ranks were seeded alike, each rank reseeds from (state, rank).
+    _rngstate.set_rank(rank)
+    if on:
+        probe = torch.tensor([float(np.random.get_state()[1][0])], dtype=torch.float64, device=device)
+        probes = [torch.zeros_like(probe) for _ in range(world)]
+        dist.all_gather(probes, probe)
+        if len({float(p.item()) for p in probes}) < world:
+            np.random.seed(np.random.SeedSequence([int(probe.item()), rank]).generate_state(4))
     if inner is not None:  # this rank's share of a round in one batched collection (collect_outer_samples_batched)
         collect_n = lambda k: collect_outer_samples_batched(noneq_sim, marginal, k, n_steps, **inner) if k > 0 else []  # noqa: E731
     else:

@@ -22,7 +22,7 @@ def _fs(dt):
 
 
 # ------------------------------------------------------------------------------------------- stability
-def test_stability(test_system, integrator, n_samples, trajectory_length, check_interval=10, precision="mixed",
+def test_stability(test_system, integrator, n_samples, trajectory_length, check_interval=10, precision=None,
                    seed=None):
     """True iff all `n_samples` trajectories of `trajectory_length` steps, started from x ~ cache and v ~ MB, keep a
     potential energy that is neither NaN nor positive at every `check_interval`-th step (thresholds.py:19-35: the
@@ -31,11 +31,8 @@ def test_stability(test_system, integrator, n_samples, trajectory_length, check_
     engine.require_cuda()
     eq = test_system
     n = int(n_samples)
-    tol = integrator.getConstraintTolerance()
-    if abs(eq.constraint_tolerance - tol) > 0:
-        eq.constraint_tolerance = tol
-        eq._engine_system = None
-    system = eq.engine_system()
+    precision = eq.precision if precision is None else precision  # the platform's arithmetic ("Reference" -> double)
+    system = eq.engine_system(integrator.getConstraintTolerance())
     seed = _rngstate.get_seed() if seed is None else int(seed)
     rid = _rngstate.reserve_replicas(n)
     t = engine.torch()
@@ -114,7 +111,6 @@ def get_hmr_stability_threshold_curve(test_system, splitting="V R O R V", traj_l
     try:
         for scale in h_masses:
             test_system.system = repartition_hydrogen_mass_amber(topology, default_system, scale_factor=scale)
-            test_system._engine_system = None
             lsi = LangevinSplittingIntegrator(splitting)
 
             def stability_oracle(dt):
@@ -125,7 +121,6 @@ def get_hmr_stability_threshold_curve(test_system, splitting="V R O R V", traj_l
             thresholds.append(grid[np.argmax(densities[-1])])
     finally:
         test_system.system = default_system
-        test_system._engine_system = None
     return h_masses, thresholds
 
 
@@ -145,7 +140,7 @@ def error_oracle_factory(test_system, error_threshold, scheme="O V R V O", n_pro
 
 # ------------------------------------------------------------------------------------------- acceptance
 def estimate_acceptance_rate(test_system, scheme, dt, n_samples=10000, gamma=1.0 / unit.picosecond,
-                             temperature=298.0 * unit.kelvin, precision="mixed", seed=None):
+                             temperature=298.0 * unit.kelvin, precision=None, seed=None):
     """GHMC acceptance ratios min(1, exp(-W_shad)) of ONE step of `scheme` from equilibrium, for `n_samples`
     draws (notebook cell 4); dt in fs.  One launch of the protocol kernel."""
     from ..testsystems.bookkeepers import NonequilibriumSimulator
@@ -156,7 +151,7 @@ def estimate_acceptance_rate(test_system, scheme, dt, n_samples=10000, gamma=1.0
     n = int(n_samples)
     seed = _rngstate.get_seed() if seed is None else int(seed)
     rid = _rngstate.reserve_replicas(n)
-    res = engine.run_protocol(eq.engine_system(), integrator.program, n, 1, eq.kT_value, n_legs=1, seed=seed,
+    res = engine.run_protocol(sim._system(), integrator.program, n, 1, eq.kT_value, n_legs=1, seed=seed,
                               replica0=rid, x_cache=eq.samples_device(), precision=sim.precision, want_moments=False,
                               out={})
     W = res["W"][0]

@@ -30,8 +30,7 @@ def _apply_hydrogen_mass_factor(eq_sim, factor):
     if missing:
         raise Exception("hydrogen-mass repartitioning needs %s in the system description" % " and ".join(missing))
     desc["mass"] = repartition_hydrogen_mass_amber_masses(desc["elements"], desc["bonds_topology"], desc["mass"], factor)
-    eq_sim.system = desc
-    eq_sim._engine_system = None  # masses are part of the compiled system tables
+    eq_sim.system = desc  # the setter drops the compiled system tables (masses are part of them)
     eq_sim.MODIFIED_H_MASS = True
 
 

@@ -112,17 +112,15 @@ class CustomizableGHMC:
         return self._globals["naccept"] / max(1.0, self._globals["ntrials"])
 
     # ---- the ensemble of chains
-    def run(self, equilibrium_simulator, x, v=None, n_trials=1, seed=None, precision="double"):
+    def run(self, equilibrium_simulator, x, v=None, n_trials=1, seed=None, precision=None):
         """`n_trials` GHMC trials for every chain.  x: (n, n_atoms, 3) nm; v: same shape in nm/ps or None for
         Maxwell-Boltzmann velocities.  Returns (x, v, accept) as device tensors, accept = (n_trials, n) bool.
         naccept / ntrials accumulate over chains and trials."""
         engine.require_cuda()
         t = engine.torch()
         eq = equilibrium_simulator
-        if abs(eq.constraint_tolerance - self._constraint_tolerance) > 0:
-            eq.constraint_tolerance = self._constraint_tolerance
-            eq._engine_system = None
-        system = eq.engine_system()
+        precision = eq.precision if precision is None else precision
+        system = eq.engine_system(self._constraint_tolerance)
         seed = _rngstate.get_seed() if seed is None else int(seed)
         x = t.as_tensor(np.asarray(x, dtype=np.float64) if not t.is_tensor(x) else x).cuda().to(t.float64).contiguous()
         n = x.shape[0]

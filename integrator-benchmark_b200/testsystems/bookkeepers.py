@@ -12,7 +12,9 @@ import os
 
 import numpy as np
 
-from .. import _rngstate, engine, unit
+import warnings
+
+from .. import _rngstate, _staging, engine, unit
 from ..constants import kB
 
 
@@ -36,6 +38,7 @@ class EquilibriumSimulator:
                  thinning_interval, name):
         self.platform = platform
         self.topology = topology
+        self._engine_systems = {}  # constraint tolerance -> engine.ParticleSystem
         self.system = system
         self.positions = np.asarray(positions, dtype=np.float64)
         self.temperature = temperature
@@ -50,7 +53,6 @@ class EquilibriumSimulator:
         self.kT = self.temperature * kB
         self.samples = None
         self._samples_dev = None
-        self._engine_system = None
         # sampler settings (see collect_equilibrium_samples)
         self.extra_chances = 15
         self.equilibration_collision_rate = 5.0  # 1/ps, Langevin mixing stage
@@ -62,15 +64,34 @@ class EquilibriumSimulator:
 
     # ---- engine handles
     @property
+    def system(self):
+        return self._system_desc
+
+    @system.setter
+    def system(self, desc):
+        # a new description (e.g. repartitioned hydrogen masses) invalidates the compiled system tables
+        self._system_desc = desc
+        self._engine_systems = {}
+
+    @property
     def kT_value(self):
         return self.kT.value_in_unit(unit.kilojoule_per_mole) if unit.is_quantity(self.kT) else float(self.kT)
 
-    def engine_system(self):
-        if self._engine_system is None:
+    def engine_system(self, constraint_tolerance=None):
+        """The engine's handle of this system at a constraint tolerance (default: this simulator's own, 1e-8).  Handles
+        are cached per tolerance, so simulators and GHMC probes that share this object never change each other's."""
+        tol = float(self.constraint_tolerance if constraint_tolerance is None else constraint_tolerance)
+        if tol not in self._engine_systems:
             desc = dict(self.system)
-            desc["constraint_tolerance"] = self.constraint_tolerance
-            self._engine_system = engine.ParticleSystem(desc)
-        return self._engine_system
+            desc["constraint_tolerance"] = tol
+            self._engine_systems[tol] = engine.ParticleSystem(desc)
+        return self._engine_systems[tol]
+
+    @property
+    def precision(self):
+        """arithmetic the platform this simulator was built on stands for: "Reference" -> "double", CUDA / OpenCL ->
+        "mixed" (benchmark/testsystems/configuration.py:36-45)"""
+        return getattr(self.platform, "precision", "mixed")
 
     # ---- equilibrium cache
     def collect_equilibrium_samples(self, seed=None):
@@ -105,12 +126,64 @@ class EquilibriumSimulator:
                                                         seed=seed, replica0=0, precision=self.sampler_precision)
         self.acceptance = acc.mean(dim=0).cpu().numpy()  # (rounds accepted, accepted at the first chance)
         ok = t.isfinite(x).all(dim=(1, 2))
-        if not bool(ok.all()):
+        self.n_dropped = int((~ok).sum().item())
+        if self.n_dropped:
+            warnings.warn("%s: %d of %d equilibration chains ended in a non-finite state and were dropped from the cache"
+                          % (self.name, self.n_dropped, n))
             x = x[ok]
         self._samples_dev = x.contiguous()
         self.samples = self._samples_dev.cpu().numpy()
         self.cached = True
         return self.samples
+
+    def collect_equilibrium_samples_single_chain(self, n_chains=1, thinning_interval=None, seed=None, quench_steps=20000,
+                                                 progress=None):
+        """Equilibrium caches built THE REFERENCE'S WAY (reference :89-113): one extra-chance-HMC chain per cache
+        (steps_per_hmc = 10, 15 extra chances, `timestep`), started from the energy-minimised `positions`, burnt in for
+        `burn_in_length` rounds, then `n_samples` configurations taken every `thinning_interval` rounds (default: this
+        simulator's, the reference's 10 000).  `n_chains` independent chains run side by side (one warp or CTA each) and
+        cost the same wall time as one; returns (n_chains, n_samples, n_atoms, 3) in nm, float64, on the host.  The
+        minimisation is a quench: Langevin dynamics at 1 K (the reference calls OpenMM's L-BFGS minimiser).
+        A lone chain is latency-bound (about 0.2 ms per round for the 20-water cluster), which is why
+        collect_equilibrium_samples() -- many independent chains -- is the default."""
+        engine.require_cuda()
+        t = engine.torch()
+        system = self.engine_system()
+        n = int(n_chains)
+        thin = int(self.thinning_interval if thinning_interval is None else thinning_interval)
+        seed = _rngstate.get_seed() if seed is None else int(seed)
+        dt = self.timestep.value_in_unit(unit.picosecond) if unit.is_quantity(self.timestep) else float(self.timestep)
+        x = t.as_tensor(np.ascontiguousarray(self.positions))[None].expand(n, -1, -1).contiguous().cuda()
+        # energy "minimisation": relax at small step, then quench at 1 K (each chain gets its own noise)
+        for k, (h, gamma, kT, n_steps) in enumerate([(0.1 * dt, 100.0, self.kT_value, 500), (0.5 * dt, 20.0, self.kT_value, 2000),
+                                                     (dt, 10.0, self.kT_value / 298.0, int(quench_steps))]):
+            res = engine.run_protocol(system, engine.Program("V R O R V", h, gamma), n, n_steps, kT, n_legs=1,
+                                      seed=seed + 104729 * (k + 1), replica0=0, x0=x, want_final=True, want_moments=False,
+                                      precision="double", out={})
+            x = res["x_final"]
+        call = [0]
+
+        def rounds(x_in, n_rounds):
+            call[0] += 1  # a fresh seed per launch: every launch counts its rounds from zero
+            x_out, _, acc = engine.sample_equilibrium_particles(system, x_in, self.kT_value, int(n_rounds), self.steps_per_hmc,
+                                                                self.extra_chances, dt, seed=seed + 15485863 * call[0], replica0=0,
+                                                                precision=self.sampler_precision)
+            return x_out, acc
+        x, acc = rounds(x, self.burn_in_length)
+        burn_acc = acc.mean(dim=0).cpu().numpy()
+        out = np.empty((n, int(self.n_samples)) + tuple(self.positions.shape), dtype=np.float64)
+        acc_sum = t.zeros(2, dtype=t.float64, device=x.device)
+        for i in range(int(self.n_samples)):
+            x, acc = rounds(x, thin)
+            acc_sum += acc.mean(dim=0)
+            out[:, i] = x.cpu().numpy()
+            if progress is not None and (i + 1) % 100 == 0:
+                progress(i + 1)
+        self.acceptance = (acc_sum / max(1, int(self.n_samples))).cpu().numpy()
+        self.burn_in_acceptance = burn_acc
+        if not np.isfinite(out).all():
+            warnings.warn("%s: a single-chain cache contains non-finite configurations" % self.name)
+        return out
 
     def get_acceptance_rate(self):
         """fraction of HMC rounds accepted (reference :80-83)"""
@@ -194,7 +267,7 @@ class EquilibriumSimulator:
 
 
 def _sample_v(eq, x, tol, seed=None):
-    system = eq.engine_system()
+    system = eq.engine_system(tol)
     prog = engine.Program("V R O R V", 0.001, 1.0)
     seed = _rngstate.get_seed() if seed is None else int(seed)
     rid = _rngstate.reserve_replicas(1)
@@ -207,20 +280,22 @@ class NonequilibriumSimulator:
     """Nonequilibrium simulator, supporting shadow_work accumulation, and drawing x, v, from
     equilibrium (reference :159-295)."""
 
-    def __init__(self, equilibrium_simulator, integrator, precision="mixed", round_midpoint=True):
+    def __init__(self, equilibrium_simulator, integrator, precision=None, round_midpoint=True):
         self.equilibrium_simulator, self.integrator = equilibrium_simulator, integrator
         self.constraint_tolerance = self.integrator.getConstraintTolerance()
-        # "mixed" mirrors how the reference configures OpenMM's CUDA platform
-        # (testsystems/configuration.py:42-45); "double" mirrors the Reference platform
-        self.precision = precision
+        # the arithmetic follows the platform the equilibrium simulator was built on, as the reference's Simulation does
+        # (bookkeepers.py:142-156): "Reference" -> "double", CUDA -> "mixed" (how the reference configures OpenMM's CUDA
+        # platform, testsystems/configuration.py:42-45); an explicit `precision` overrides it
+        self.precision = equilibrium_simulator.precision if precision is None else precision
+        if self.precision not in ("double", "mixed"):
+            raise ValueError("precision must be 'double' or 'mixed'")
         # positions pass through a float32 frame between the legs, as in the reference (:266,298-305)
         self.round_midpoint = round_midpoint
         self._buffers = {}
         self._last = None  # final (x, v) of the most recent single-trajectory call
-        eq = self.equilibrium_simulator
-        if abs(eq.constraint_tolerance - self.constraint_tolerance) > 0 or eq._engine_system is None:
-            eq.constraint_tolerance = self.constraint_tolerance
-            eq._engine_system = None
+
+    def _system(self):
+        return self.equilibrium_simulator.engine_system(self.constraint_tolerance)
 
     # ---- sampling
     def sample_x_from_equilibrium(self):
@@ -248,7 +323,7 @@ class NonequilibriumSimulator:
         traces = bool(store_potential_energy or store_W_shad_trace)
         rid = _rngstate.reserve_replicas(1)
         direct = self.integrator._measure_shadow_work
-        res = engine.run_protocol(eq.engine_system(), self.integrator.program, 1, int(n_steps), self._kT(), n_legs=1,
+        res = engine.run_protocol(self._system(), self.integrator.program, 1, int(n_steps), self._kT(), n_legs=1,
                                   seed=_rngstate.get_seed(), replica0=rid, x0=x0[None], v0=v0[None],
                                   precision=self.precision, want_heat=True, want_direct=direct, want_final=True,
                                   traces=traces, want_moments=False, out={})
@@ -258,7 +333,7 @@ class NonequilibriumSimulator:
         self._last = (res["x_final"][0].cpu().numpy(), res["v_final"][0].cpu().numpy())
         if store_potential_energy:
             frames = res["trace_x"][0, :, 0]
-            pe, _ = eq.engine_system().energy_forces(frames, precision=self.precision, want_forces=False)
+            pe, _ = self._system().energy_forces(frames, precision=self.precision, want_forces=False)
             result["potential_energies"] = pe.cpu().numpy() * unit.kilojoule_per_mole
         if store_W_shad_trace:
             result["W_shad_trace"] = np.diff(res["trace_w"][0, :, 0].cpu().numpy())
@@ -283,7 +358,7 @@ class NonequilibriumSimulator:
             v0 = np.asarray(v_0.value_in_unit(unit.nanometer / unit.picosecond) if unit.is_quantity(v_0) else v_0, dtype=np.float64)
             v0 = np.broadcast_to(v0, x0.shape)
         rid = _rngstate.reserve_replicas(n)
-        res = engine.run_protocol(eq.engine_system(), self.integrator.program, n, int(n_steps), self._kT(), n_legs=1,
+        res = engine.run_protocol(self._system(), self.integrator.program, n, int(n_steps), self._kT(), n_legs=1,
                                   seed=_rngstate.get_seed() if seed is None else int(seed), replica0=rid,
                                   x0=np.array(x0, dtype=np.float64, order="C"), v0=None if v0 is None else np.array(v0, dtype=np.float64, order="C"),
                                   precision=self.precision, want_heat=True, want_final=want_final, want_moments=False, out={})
@@ -308,23 +383,29 @@ class NonequilibriumSimulator:
         traces = bool(store_potential_energy_traces or store_W_shad_traces)
         seed = _rngstate.get_seed() if seed is None else int(seed)
         rid = _rngstate.reserve_replicas(n)
-        res = engine.run_protocol(eq.engine_system(), self.integrator.program, n, int(protocol_length), self._kT(),
+        res = engine.run_protocol(self._system(), self.integrator.program, n, int(protocol_length), self._kT(),
                                   marginal=marginal, n_legs=2, seed=seed, replica0=rid, x_cache=eq.samples_device(),
                                   precision=self.precision, want_heat=True, traces=traces, out=self._buffers,
                                   round_midpoint=self.round_midpoint)
         self.last_moments = res.get("moments")
         W = res["W"]
         self.integrator._accumulate(heat=res["heat"].nan_to_num(0.0).sum().item())
-        conv = (lambda a: a.cpu().numpy()) if as_numpy else (lambda a: a)
-        result = {"W_shads_F": conv(W[0]), "W_shads_R": conv(W[1])}
+        inc = pe = None
         if store_W_shad_traces:
             tw = res["trace_w"]  # (leg, step, replica), cumulative
             inc = (tw[:, 1:] - tw[:, :-1]).permute(2, 0, 1)  # (replica, leg, step)
-            inc = conv(inc)
-            result["W_shad_traces"] = [(inc[i, 0], inc[i, 1]) for i in range(n)]
         if store_potential_energy_traces:
-            frames = res["trace_x"][1].reshape(-1, eq.engine_system().n_atoms, 3)
-            pe, _ = eq.engine_system().energy_forces(frames, precision=self.precision, want_forces=False)
-            pe = conv(pe.reshape(int(protocol_length) + 1, n).transpose(0, 1))
+            frames = res["trace_x"][1].reshape(-1, self._system().n_atoms, 3)
+            pe, _ = self._system().energy_forces(frames, precision=self.precision, want_forces=False)
+            pe = pe.reshape(int(protocol_length) + 1, n).transpose(0, 1)
+        if as_numpy:
+            # asynchronous copies into pinned host memory, one synchronisation (_staging.to_host); the arrays own their memory
+            wF, wR, inc, pe = _staging.to_host([W[0], W[1], inc, pe])
+        else:
+            wF, wR = W[0], W[1]  # views of this simulator's output buffer: overwritten by its next call
+        result = {"W_shads_F": wF, "W_shads_R": wR}
+        if inc is not None:
+            result["W_shad_traces"] = [(inc[i, 0], inc[i, 1]) for i in range(n)]
+        if pe is not None:
             result["potential_energies"] = [pe[i] for i in range(n)]
         return result

@@ -10,7 +10,7 @@ import functools
 
 import numpy as np
 
-from .. import _cabi, _rngstate, engine
+from .. import _cabi, _rngstate, _staging, engine
 from ..integrators.numba_integrators import ToyIntegrator, identify_potential
 
 
@@ -114,7 +114,8 @@ class NumbaNonequilibriumSimulator:
         shape (n, protocol_length) and (x, v) traces of shape (n, protocol_length, 2).
         With traces=False only the final works are produced: W arrays have shape (n, 1) (so the
         caller's `W[:, -1]` still works) and xv_* are None -- use this for large ensembles.
-        as_numpy=False leaves the results on the GPU as torch tensors."""
+        as_numpy=False leaves the results on the GPU as torch tensors; those are VIEWS of this simulator's output
+        buffers and are overwritten by its next call (clone them to keep them).  numpy results own their memory."""
         if marginal not in ("configuration", "full"):
             raise NotImplementedError("`marginal` must be either 'configuration' or 'full'")
         integ, gamma, dt = self._unwrap()
@@ -134,6 +135,6 @@ class NumbaNonequilibriumSimulator:
             W_F, W_R = res["W"][0].unsqueeze(1) * integ.kT, res["W"][1].unsqueeze(1) * integ.kT
             xv_F = xv_R = None
         if as_numpy:
-            conv = lambda a: None if a is None else a.cpu().numpy()  # noqa: E731
-            return conv(W_F), conv(W_R), conv(xv_F), conv(xv_R)
+            # one asynchronous copy per array into pinned host memory, one synchronisation (_staging.to_host)
+            return tuple(_staging.to_host([W_F, W_R, xv_F, xv_R]))
         return W_F, W_R, xv_F, xv_R
