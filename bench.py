@@ -1,57 +1,116 @@
 #!/usr/bin/env python
-"""Headline benchmark: replica-steps/s of the fused Langevin-splitting protocol.
+"""Benchmark of the replica-ensemble / shadow-work path: replica-steps/s per (system, splitting).
 
-Workload (BASELINE.json configs[1]): 1-D double well
-(m = 10, beta = 1, gamma = 10 as in the reference's six-scheme comparison, dt = 0.35), 1 048 576 replicas PER GPU, protocol_length 10
-(the reference's convention: 9 integrator steps per leg, forward + reverse leg), all six
-5-letter symmetric splittings over {O, R, V}; one bench "step" = one pass over the batch =
-6 fused protocol launches + the DeltaF_neq moment reduction (all-reduced over ranks).
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Default (`--workload all`): ONE JSON line whose top level is the headline, BASELINE.json configs[1] (C2: 1-D double well,
+1 048 576 replicas per GPU, protocol_length 10, the six 5-letter symmetric splittings over {O, R, V}), and whose
+`per_workload` key holds the same record (value / e2e / roofline / cpu_baseline) for the other four configs, each on a
+short fixed number of steps: C1 quartic (the reference's vvvr / baoab closures), C3 rigid water cluster, C4 alanine
+dipeptide (VRORV + an MTS string), C5 tiny water box.  `--workload NAME` measures one of them alone as the top level.
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events, max over
-ranks); `e2e` goes through the public API with pinned HOST buffers (H2D of the equilibrium
-cache, D2H of the works, every step); `roofline` holds the dominant kernel against the FP64
-FMA peak measured in the same run; `cpu_baseline` is the CPU oracle port on the host cores.
+One bench "step" = one pass over the batch = one fused protocol launch per splitting (forward leg, midpoint velocity
+redraw, reverse leg) + the DeltaF_neq moment reduction, all-reduced over ranks.
+  value     device-resident throughput: inputs in HBM, CUDA events around every step, L2 flushed (untimed) between steps,
+            max over ranks.  The moment all-reduce of step s is started inside the timed interval of step s + 1 and
+            overlaps its kernels (moments are additive; nothing downstream needs them earlier); the last ones are
+            drained inside the timed region.
+  e2e       the same work through the reference-facing drop-in call with DEFAULT arguments, as a reference caller makes it
+            (NumbaNonequilibriumSimulator.collect_protocol_samples / NonequilibriumSimulator.collect_protocol_samples):
+            host-side equilibrium cache uploaded every call, numpy results on the host (the toy call returns the full
+            work and (x, v) traces, as the reference does).  Sub-keys give the same call with `traces=False` (final works
+            only) and `as_numpy=False` (estimate only).
+  roofline  dominant kernel alone (events around each launch) against the FMA peak measured in the same run.
+  cpu_baseline / --impl reference: the reference's own numba closures (oracle/_ref, installed by oracle/make_ref.sh)
+            under the restated collect_protocol_samples loop on all host cores for C1 / C2; the restated C oracle
+            (OpenMP) for C3-C5, where the reference needs OpenMM.
 """
 import argparse
+import ctypes
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
+from functools import partial
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SPLITTINGS = {"OVRVO": "O V R V O", "ORVRO": "O R V R O", "RVOVR": "R V O V R",
-              "ROVOR": "R O V O R", "VRORV": "V R O R V", "VOROV": "V O R O V"}
-SYSTEM, MASS, BETA, GAMMA, DT = "double_well", 10.0, 1.0, 10.0, 0.35
-N_CACHE = 1_000_000
-METRIC, UNIT = "replica-steps/sec (double well, six 5-letter splittings, F+R protocol)", "replica-steps/s"
+UNIT = "replica-steps/s"
+KT_298 = 8.31446261815324e-3 * 298.0
+FIVE_LETTER = {"OVRVO": "O V R V O", "ORVRO": "O R V R O", "RVOVR": "R V O V R",
+               "ROVOR": "R O V O R", "VRORV": "V R O R V", "VOROV": "V O R O V"}
+# the four closures of the reference's numba file and the substeps they perform (integrators/numba_integrators.py)
+REF_SCHEMES = {"OVRVO": "vvvr", "ORVRO": "orvro", "VRORV": "baoab", "RVOVR": "aboba"}
 
-# Algorithmic flops per replica-step (DESIGN.md "flop convention"): FMA = 2, add/mul = 1,
-# transcendental = 1; Philox/Box-Muller work is NOT counted.  O: 9/DOF, V: 2/DOF, R: 2/DOF,
-# one force evaluation (10 flops: x^5, sin, 2 FMA) per distinct position visited.
-F_FORCE_DW = 10
+WORKLOADS = {
+    # toy workloads: protocol_length counts recorded states (reference convention): protocol_length - 1 steps per leg
+    "double_well": dict(
+        config="C2", kind="toy", system="double_well", mass=10.0, kT=1.0, gamma=10.0, dt=0.35, replicas=1 << 20, protocol_length=10,
+        splittings=FIVE_LETTER, f_force=10, n_cache=1_000_000, e2e_replicas=1 << 20, ref_replicas=1 << 16, precision="double",
+        label="C2 double well (BASELINE configs[1]), six 5-letter symmetric splittings"),
+    "quartic": dict(
+        config="C1", kind="toy", system="quartic", mass=10.0, kT=1.0, gamma=100.0, dt=1.1, replicas=1 << 20, protocol_length=100,
+        splittings={"OVRVO": "O V R R V O", "VRORV": "V R O O R V"}, closures={"OVRVO": "vvvr", "VRORV": "baoab"}, f_force=3,
+        n_cache=1_000_000, e2e_replicas=1 << 17, ref_replicas=1 << 13, precision="double",
+        label="C1 1-D quartic (BASELINE configs[0]), OVRVO vs VRORV as the reference's vvvr / baoab closures perform them"),
+    # particle workloads: protocol_length = steps per leg (NonequilibriumSimulator.collect_protocol_samples)
+    "water_cluster": dict(
+        config="C3", kind="particles", replicas=47360, protocol_length=200, dt=0.002, gamma=1.0, kT=KT_298,
+        splittings={"OVRVO": "O V R V O", "VRORV": "V R O R V"}, flops={"OVRVO": 56200, "VRORV": 57400}, precision="mixed",
+        ref_replicas=256, cpu_replicas=512, e2e_replicas=47360,
+        label="C3 rigid TIP3P water cluster, 20 waters, no cutoff, restraint K=1, SETTLE (BASELINE configs[2])"),
+    "alanine": dict(
+        config="C4", kind="particles", replicas=59200, protocol_length=200, dt=0.002, gamma=1.0, kT=KT_298,
+        splittings={"VRORV": "V R O R V", "MTS": "V0 V1 R O R V1 V1 R O R V1 V0"}, flops={"VRORV": 29000, "MTS": 59000},
+        precision="mixed", ref_replicas=1024, cpu_replicas=2048, e2e_replicas=59200,
+        label="C4 alanine dipeptide vacuum, H-bonds constrained, MTS V0/V1 (BASELINE configs[3])"),
+    "waterbox": dict(
+        config="C5", kind="particles", replicas=8192, protocol_length=200, dt=0.002, gamma=1.0, kT=KT_298,
+        splittings={"OVRVO": "O V R V O", "VRORV": "V R O R V"}, flops={"OVRVO": 1.20e6, "VRORV": 1.20e6}, precision="mixed",
+        ref_replicas=32, cpu_replicas=48, e2e_replicas=8192, hbm_bytes_per_step_streaming=19584.0,
+        label="C5 tiny water box, 102 TIP3P waters, 1.5 nm, cutoff 0.6 nm + reaction field, switched LJ, SETTLE (BASELINE configs[4])"),
+}
+ORDER = ["double_well", "quartic", "water_cluster", "alanine", "waterbox"]
 
 
-def flops_per_step(splitting):
+def flops_per_step(splitting, f_force):
+    """Algorithmic flops per replica-step of a 1-DOF system (DESIGN.md flop convention): FMA = 2, add/mul = 1,
+    transcendental = 1; Philox / Box-Muller work is NOT counted.  O: 9, V: 2, R: 2, one force evaluation per distinct
+    position visited (steady state)."""
     toks = splitting.split()
-    n_evals = 0
-    valid = False  # force known at current position? steady state: last op of previous step
-    seq = toks + toks  # second pass sees the steady-state validity
-    for i, t in enumerate(seq):
+    n_evals, valid = 0, False
+    for i, t in enumerate(toks + toks):  # the second pass sees the steady-state validity
         if t == "R":
             valid = False
         elif t == "V":
             if not valid and i >= len(toks):
                 n_evals += 1
             valid = True
-    return 9 * toks.count("O") + 2 * toks.count("V") + 2 * toks.count("R") + F_FORCE_DW * n_evals
+    return 9 * toks.count("O") + 2 * toks.count("V") + 2 * toks.count("R") + f_force * n_evals
+
+
+def metric_name(name, W):
+    return "replica-steps/sec (%s, %s, F+R protocol)" % (name, "+".join(W["splittings"]))
+
+
+def steps_per_leg(W, plen=None):
+    plen = plen or W["protocol_length"]
+    return plen - 1 if W["kind"] == "toy" else plen
+
+
+def workload_config(name, W, n, plen):
+    cfg = {"workload": "%s: %d replicas/GPU x protocol_length %d (%d steps/leg, 2 legs) x %d splittings"
+                       % (W["label"], n, plen, steps_per_leg(W, plen), len(W["splittings"])),
+           "system": name, "gamma": W["gamma"], "dt": W["dt"], "kT": W["kT"], "marginal": "configuration",
+           "splittings": list(W["splittings"].values()), "replicas_per_gpu": n, "protocol_length": plen, "precision": W["precision"],
+           "l2": "flushed between timed steps (256 MiB memset, untimed)",
+           "parallelism": "replica shards, no data-path collective; moment all-reduce per step, overlapped with the next step"}
+    if W["kind"] == "toy":
+        cfg["mass"], cfg["equilibrium_cache"] = W["mass"], W["n_cache"]
+    return cfg
 
 
 class ClockSampler:
@@ -109,81 +168,10 @@ class ClockSampler:
         return out
 
 
-def cpu_port_throughput(n_replicas, protocol_length, repeats=1):
-    """CPU oracle port (OpenMP over replicas, all host cores) on the same workload."""
-    from oracle import oracle
-    oracle.set_threads()
-    cache = oracle.sample_equilibrium_scalar(SYSTEM, 20000, 100, seed=1)
-    steps = protocol_length - 1
-    t0 = time.perf_counter()
-    total = 0
-    for _ in range(repeats):
-        for name, s in SPLITTINGS.items():
-            oracle.toy_protocol(SYSTEM, s, DT, GAMMA, n_replicas, steps, mass=MASS, kT=1.0 / BETA, seed=1, x_cache=cache)
-            total += n_replicas * 2 * steps
-    dt = time.perf_counter() - t0
-    return total / dt, dt
-
-
-def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure
-    Python (numba closures / OpenMM) and cannot travel to the GPU box, so this arm times the CPU
-    oracle port (oracle/lsi_oracle.c, pinned to the reference's closures by tests/golden) with all
-    host threads, each step a bounded sample of the workload."""
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
-        return
-    n_sample = args.ref_replicas
-    cores = os.cpu_count()
-    for _ in range(args.warmup):
-        cpu_port_throughput(max(n_sample // 8, 1024), args.protocol_length)
-    t0 = time.perf_counter()
-    total = 0.0
-    for _ in range(args.steps):
-        v, dt = cpu_port_throughput(n_sample, args.protocol_length)
-        total += v * dt
-    wall = time.perf_counter() - t0
-    value = total / wall
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": workload_config(args, args.replicas),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d replicas x 6 splittings x 2 legs x %d steps per bench step" %
-                                   (n_sample, args.protocol_length - 1)},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
-
-
-def workload_config(args, n_per_gpu):
-    return {"workload": "C2 double well (BASELINE configs[1]): %d replicas/GPU x protocol_length %d "
-                        "(%d steps/leg, 2 legs) x 6 splittings" % (n_per_gpu, args.protocol_length,
-                                                                    args.protocol_length - 1),
-            "system": SYSTEM, "mass": MASS, "beta": BETA, "gamma": GAMMA, "dt": DT, "marginal": "configuration",
-            "splittings": list(SPLITTINGS), "replicas_per_gpu": n_per_gpu, "protocol_length": args.protocol_length,
-            "equilibrium_cache": N_CACHE, "l2": "flushed between timed steps (256 MiB memset, untimed)",
-            "parallelism": "replica shards, no data-path collective; 48-double moment all-reduce per step"}
-
-
 # ------------------------------------------------------------------------------------------------
-# configs[2..4]: water cluster, alanine dipeptide, tiny water box (SURVEY 8d rows C3-C5)
-KT_298 = 8.31446261815324e-3 * 298.0
-PARTICLE_WORKLOADS = {
-    # name: (config label, replicas/GPU, protocol_length, dt ps, splittings, algorithmic flops per replica-step)
-    "water_cluster": ("C3 rigid TIP3P water cluster, 20 waters, no cutoff, restraint K=1, SETTLE (BASELINE configs[2])",
-                      47360, 200, 0.002, {"OVRVO": "O V R V O", "VRORV": "V R O R V"}, {"OVRVO": 56200, "VRORV": 57400}),
-    "alanine": ("C4 alanine dipeptide vacuum, H-bonds constrained, MTS V0/V1 (BASELINE configs[3])",
-                59200, 200, 0.002, {"VRORV": "V R O R V", "MTS": "V0 V1 R O R V1 V1 R O R V1 V0"}, {"VRORV": 29000, "MTS": 59000}),
-    "waterbox": ("C5 tiny water box, 102 TIP3P waters, 1.5 nm, cutoff 0.6 nm + reaction field, SETTLE (BASELINE configs[4])",
-                 8192, 200, 0.002, {"OVRVO": "O V R V O", "VRORV": "V R O R V"}, {"OVRVO": 1.20e6, "VRORV": 1.20e6}),
-}
-HBM_BYTES_PER_STEP_STREAMING = {"waterbox": 19584.0}  # SURVEY 8d: 2 x 306 x 32 B if the state were streamed every step
-
-
-def particle_system(name):
+# inputs
+def particle_description(name):
+    """(system description, start geometry or frames) of a particle workload"""
     from integrator_benchmark_b200.testsystems import systems as ts
     if name == "water_cluster":
         return ts.water_cluster(20, constrained=True, seed=1)
@@ -194,498 +182,493 @@ def particle_system(name):
     return desc, frames
 
 
-def particles_cpu_port(name, cache, n_replicas, steps_per_leg, dt, splittings, seed=1):
-    """CPU oracle port (fp64, OpenMP over replicas, all host cores) on a bounded sample of the workload."""
+def particle_simulator(name):
+    """the reference-facing EquilibriumSimulator of a particle workload (testsystems/molecular.py)"""
+    from integrator_benchmark_b200 import testsystems
+    return {"water_cluster": testsystems.water_cluster_rigid, "alanine": testsystems.alanine_constrained,
+            "waterbox": testsystems.tiny_waterbox}[name]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (test infrastructure: the only places bench.py touches oracle/)
+def cpu_reference_toy(name, W, n_per_scheme, x_cache, repeats=1):
+    """The reference's own numba closures (oracle/_ref) under the restated collect_protocol_samples loop, all host cores.
+    Only the schemes the reference's file implements are run.  Returns (replica-steps/s, seconds, description) or None."""
+    from oracle import ref_toy
+    ok, why = ref_toy.available()
+    if not ok:
+        return None, why
+    schemes = [k for k in W["splittings"] if k in REF_SCHEMES]
+    cores = os.cpu_count() or 1
+    plen = W["protocol_length"]
+    ref_toy.collect_parallel(name, schemes, x_cache, max(cores * 16, 64), plen, "configuration", W["gamma"], W["dt"], processes=cores)
+    secs = 0.0
+    for r in range(repeats):
+        _, s = ref_toy.collect_parallel(name, schemes, x_cache, n_per_scheme, plen, "configuration", W["gamma"], W["dt"],
+                                        processes=cores, seed=17 * r)
+        secs += s
+    total = repeats * len(schemes) * n_per_scheme * 2 * (plen - 1)
+    return (total / secs, secs, "%d protocols x %d schemes (%s) x 2 legs x %d steps x %d passes, %d worker processes: the reference's "
+            "numba_integrators.py closures (oracle/_ref) under the restated low_dimensional_systems.py:160-184 loop, traces "
+            "collected as the reference does" % (n_per_scheme, len(schemes), "/".join(schemes), plen - 1, repeats, cores)), ""
+
+
+def cpu_port_toy(name, W, n, x_cache, repeats=1):
+    """restated C oracle (OpenMP over replicas) on the same workload: (replica-steps/s, seconds)"""
     from oracle import oracle
     oracle.set_threads()
-    desc, _ = particle_system(name)
+    steps = W["protocol_length"] - 1
+    oracle.toy_protocol(name, "V R O R V", W["dt"], W["gamma"], 4096, steps, mass=W["mass"], kT=W["kT"], seed=1, x_cache=x_cache)
     t0 = time.perf_counter()
-    total = 0
-    for s in splittings.values():
-        oracle.particles_protocol(desc, s, dt, 1.0, KT_298, n_replicas, steps_per_leg, seed=seed, x_cache=cache)
-        total += n_replicas * 2 * steps_per_leg
+    for _ in range(repeats):
+        for s in W["splittings"].values():
+            oracle.toy_protocol(name, s, W["dt"], W["gamma"], n, steps, mass=W["mass"], kT=W["kT"], seed=1, x_cache=x_cache)
     secs = time.perf_counter() - t0
-    return total / secs, secs
+    return repeats * len(W["splittings"]) * n * 2 * steps / secs, secs
 
 
-def run_particles(args):
-    name = args.workload
-    label, n_default, plen_default, dt, splittings, flops = PARTICLE_WORKLOADS[name]
-    n = args.replicas or n_default
-    steps_per_leg = args.protocol_length or plen_default
-    metric = "replica-steps/sec (%s, %s, F+R protocol)" % (name, "+".join(splittings))
-    precision = args.precision or "mixed"
-    cfg = {"workload": "%s: %d replicas/GPU x protocol_length %d (2 legs) x %d splittings" % (label, n, steps_per_leg, len(splittings)),
-           "system": name, "temperature_K": 298.0, "collision_rate_per_ps": 1.0, "dt_ps": dt, "marginal": "configuration",
-           "splittings": list(splittings), "replicas_per_gpu": n, "protocol_length": steps_per_leg, "precision": precision,
-           "l2": "flushed between timed steps (256 MiB memset, untimed); state is shared-memory resident",
-           "parallelism": "replica shards, no data-path collective; moment all-reduce per step"}
-    rank = int(os.environ.get("RANK", 0))
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        desc, x = particle_system(name)
-        cache = x if x.ndim == 3 else x[None]
-        n_ref = args.ref_replicas or {"water_cluster": 256, "alanine": 1024, "waterbox": 32}[name]
-        steps_ref = min(steps_per_leg, 50)
-        for _ in range(args.warmup):
-            particles_cpu_port(name, cache, max(n_ref // 8, 8), 5, dt, splittings)
-        t0 = time.perf_counter()
-        tot = 0.0
-        for _ in range(args.steps):
-            v, secs = particles_cpu_port(name, cache, n_ref, steps_ref, dt, splittings)
-            tot += v * secs
-        wall = time.perf_counter() - t0
-        value = tot / wall
-        print(json.dumps({"metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference", "config": cfg,
-                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                           "sample": "%d replicas x %d splittings x 2 legs x %d steps per bench step (restated CPU "
-                                                     "oracle, OpenMP; not OpenMM)" % (n_ref, len(splittings), steps_ref)},
-                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+def cpu_port_particles(name, W, n, steps, cache):
+    from oracle import oracle
+    oracle.set_threads()
+    desc, _ = particle_description(name)
+    oracle.particles_protocol(desc, "V R O R V", W["dt"], W["gamma"], W["kT"], max(os.cpu_count() or 1, 8), 2, seed=1, x_cache=cache)
+    t0 = time.perf_counter()
+    for s in W["splittings"].values():
+        oracle.particles_protocol(desc, s, W["dt"], W["gamma"], W["kT"], n, steps, seed=1, x_cache=cache)
+    secs = time.perf_counter() - t0
+    return len(W["splittings"]) * n * 2 * steps / secs, secs
+
+
+def toy_cache_cpu(name, n=20000):
+    from oracle import oracle
+    oracle.set_threads()
+    return oracle.sample_equilibrium_scalar(name, n, 100, seed=1)
+
+
+def particle_cache_cpu(name, n=16):
+    """a few start configurations for the CPU leg: the committed water-box frames, or the start geometry relaxed by a
+    short oracle run (the CPU leg measures throughput; it does not need an equilibrium ensemble)"""
+    desc, x = particle_description(name)
+    if x.ndim == 3:
+        return x
+    return x[None]
+
+
+def cpu_baseline(name, W, target_s=10.0):
+    """cpu_baseline object of one workload: about `target_s` seconds of CPU work on all host cores"""
+    cores = os.cpu_count() or 1
+    if W["kind"] == "toy":
+        x_cache = toy_cache_cpu(name)
+        n = W["ref_replicas"]
+        out, why = cpu_reference_toy(name, W, n, x_cache)
+        port_v, _ = cpu_port_toy(name, W, 1 << 17, x_cache)
+        if out is not None:
+            v, secs, _ = out
+            repeats = int(min(32, max(1, round(target_s / max(secs, 1e-3)))))
+            (v, secs, what), _ = cpu_reference_toy(name, W, n, x_cache, repeats=repeats)
+            return {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": what + " (%.1f s)" % secs,
+                    "port_value": port_v, "port_note": "restated C oracle (oracle/lsi_oracle.c, OpenMP over replicas, final works only)"}
+        return {"value": port_v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "131072 replicas x %d splittings (restated C oracle; reference closures unavailable: %s)" % (len(W["splittings"]), why)}
+    steps = min(W["protocol_length"], 50)
+    v, secs = cpu_port_particles(name, W, W["cpu_replicas"], steps, particle_cache_cpu(name))
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d replicas x %d splittings x 2 legs x %d steps (%.1f s; restated fp64 C oracle, OpenMP over replicas; not OpenMM -- "
+                      "the reference's own figure is 1.28e4 replica-steps/s on the OpenMM Reference platform for alanine dipeptide, "
+                      "BASELINE.md)" % (W["cpu_replicas"], len(W["splittings"]), steps, secs)}
+
+
+def reference_record(name, W, steps, warmup, n_gpus):
+    """--impl reference: the reference's CPU implementation of the path on the host cores; each step a bounded sample"""
+    cores = os.cpu_count() or 1
+    plen = W["protocol_length"]
+    if W["kind"] == "toy":
+        x_cache = toy_cache_cpu(name)
+        n = W["ref_replicas"]
+        out, why = cpu_reference_toy(name, W, max(n // 8, 256), x_cache, repeats=max(1, warmup))  # compiles, forks, warms
+        if out is not None:
+            total_s, units = 0.0, 0.0
+            for _ in range(steps):
+                (v, secs, what), _ = cpu_reference_toy(name, W, n, x_cache)
+                total_s += secs
+                units += v * secs
+            kind = "reference"
+        else:
+            total_s, units, what, kind = 0.0, 0.0, "restated C oracle (reference closures unavailable: %s)" % why, "port"
+            for _ in range(steps):
+                v, secs = cpu_port_toy(name, W, 1 << 17, x_cache)
+                total_s += secs
+                units += v * secs
+    else:
+        cache = particle_cache_cpu(name)
+        nsteps = min(plen, 50)
+        for _ in range(max(1, warmup)):
+            cpu_port_particles(name, W, max(W["ref_replicas"] // 8, 8), 5, cache)
+        total_s, units, kind = 0.0, 0.0, "port"
+        for _ in range(steps):
+            v, secs = cpu_port_particles(name, W, W["ref_replicas"], nsteps, cache)
+            total_s += secs
+            units += v * secs
+        what = "%d replicas x %d splittings x 2 legs x %d steps per bench step (restated fp64 C oracle, OpenMP; not OpenMM)" % (
+            W["ref_replicas"], len(W["splittings"]), nsteps)
+    value = units / total_s
+    return {"metric": metric_name(name, W), "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 * total_s / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference", "config": workload_config(name, W, W["replicas"], plen),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": what},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", 0)) != 0:
         return
+    names = ORDER if args.workload == "all" else [args.workload]
+    head = reference_record(names[0], WORKLOADS[names[0]], args.steps, args.warmup, args.gpus)
+    if len(names) > 1:
+        head["per_workload"] = {}
+        for nm in names[1:]:
+            rec = reference_record(nm, WORKLOADS[nm], 2, 1, args.gpus)
+            head["per_workload"]["%s %s" % (WORKLOADS[nm]["config"], nm)] = {k: rec[k] for k in ("metric", "value", "unit", "ms_per_step", "steps",
+                                                                                                "config", "cpu_baseline", "e2e")}
+    print(json.dumps(head))
 
-    import ctypes
-    import torch
-    import torch.distributed as dist
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+class Context:
+    """process-wide state of the GPU arm: ranks, device, L2-flush buffer, FMA peaks measured once"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from integrator_benchmark_b200 import engine, parallel
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local_rank = parallel.init_process_group()
+        engine.require_cuda()
+        self.dev = torch.device("cuda", self.local_rank)
+        torch.cuda.set_device(self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self._peaks = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def peaks(self):
+        """FP64 / FP32 FMA peaks of this GPU, TFLOP/s (lsi_microbench_fma, burst = best of 6)"""
+        if self._peaks is None:
+            torch = self.torch
+            from integrator_benchmark_b200 import _cabi, engine
+            sink = torch.zeros(8, dtype=torch.float64, device=self.dev)
+            self._peaks = {}
+            for prec, name in [(0, "fp64"), (1, "fp32")]:
+                blocks, iters = 148 * 8, 20000 if prec == 0 else 40000
+                best = 1e30
+                for _ in range(6):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    _cabi.check(_cabi.lib.lsi_microbench_fma(prec, iters, blocks, ctypes.c_void_p(sink.data_ptr()),
+                                                             engine.current_stream_ptr()))
+                    b.record()
+                    b.synchronize()
+                    best = min(best, a.elapsed_time(b))
+                self._peaks[name] = blocks * 256 * iters * 16 / (best * 1e-3) / 1e12
+        return self._peaks
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "MEASURED_PEAKS.json"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
+    """Measures one workload on the GPU arm; returns the JSON record (rank 0) or None (other ranks)."""
+    torch = ctx.torch
     import integrator_benchmark_b200 as ib
-    from integrator_benchmark_b200 import _cabi, engine, parallel
-    rank, world, local_rank = parallel.init_process_group()
-    engine.require_cuda()
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    seed = 0x5EED0003
-    replica0 = rank * n
-    desc, x = particle_system(name)
-    system = engine.ParticleSystem(desc)
-    # equilibrium cache (input of the path): the reference's own frames for the box; otherwise 1024
-    # configurations equilibrated on the GPU from the start geometry (same on every rank)
-    # (the box: the reference's 4 fixture frames tiled, then equilibrated for the reaction-field potential)
-    n_eq = 1024 if x.ndim == 2 else 256
-    if True:
+    from integrator_benchmark_b200 import engine, parallel
+    from integrator_benchmark_b200.integrators import LangevinSplittingIntegrator, numba_integrators
+    from integrator_benchmark_b200.testsystems import (NonequilibriumSimulator, NumbaBookkeepingSimulator,
+                                                       NumbaNonequilibriumSimulator)
+    from integrator_benchmark_b200 import unit
+
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    toy = W["kind"] == "toy"
+    nsl = steps_per_leg(W, plen)
+    seed = 0x5EED0000 + ORDER.index(name) + 1
+    replica0 = rank * n  # global replica ids: rank r owns [r n, (r + 1) n)
+    S = len(W["splittings"])
+    precision = W["precision"]
+
+    # ---- system, programs, equilibrium cache (the path's input; generated once on the GPU, same on every rank)
+    if toy:
+        system = engine.ScalarSystem(W["system"], W["mass"])
+        eq = NumbaBookkeepingSimulator(mass=W["mass"], beta=1.0 / W["kT"], name=name,
+                                       **({} if name == "quartic" else {"potential": ib.testsystems.double_well.potential,
+                                                                        "force": ib.testsystems.double_well.force}))
+        eq.set_x_samples(eq.collect_equilibrium_samples(W["n_cache"], n_burn=300, seed=seed))
+        cache = eq.x_samples_device()
+    else:
+        eq = particle_simulator(name)
+        system = eq.engine_system()
+        desc, x = particle_description(name)
+        n_eq = 1024 if x.ndim == 2 else 256
         x0 = torch.as_tensor(np.ascontiguousarray(x if x.ndim == 3 else x[None]))
         x0 = x0[torch.arange(n_eq) % x0.shape[0]].contiguous().to(dev)
         for k, (h, gamma, ns) in enumerate([(0.0002, 100.0, 500), (0.001, 20.0, 500), (0.002, 5.0, 2000)]):
-            res = engine.run_protocol(system, engine.Program("V R O R V", h, gamma), n_eq, ns, KT_298, n_legs=1, seed=seed + k,
+            res = engine.run_protocol(system, engine.Program("V R O R V", h, gamma), n_eq, ns, W["kT"], n_legs=1, seed=seed + 100 + k,
                                       x0=x0, want_final=True, want_moments=False, out={})
             x0 = res["x_final"]
-        cache_host = x0.cpu()
-    cache_host = cache_host.pin_memory()
-    cache = cache_host.to(dev)
-    programs = {k: engine.Program(s, dt, 1.0) for k, s in splittings.items()}
-    bufs = {k: {} for k in splittings}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    moments_all = torch.zeros(len(splittings), 8, dtype=torch.float64, device=dev)
+        eq.set_samples(x0.cpu().numpy())
+        cache = eq.samples_device()
+    programs = {k: engine.Program(s, W["dt"], W["gamma"]) for k, s in W["splittings"].items()}
+    bufs = {k: {} for k in programs}
+    mom = [torch.zeros(S, 8, dtype=torch.float64, device=dev) for _ in range(2)]
+    pending = [None, None]
 
-    def one_pass(cache_dev):
+    def launch(k, prog, x_cache_dev, want_moments=True):
+        return engine.run_protocol(system, prog, n, nsl, W["kT"], marginal="configuration", seed=seed, replica0=replica0,
+                                   x_cache=x_cache_dev, out=bufs[k], precision=precision, want_moments=want_moments)
+
+    def one_pass(i):
+        """bench step i: the all-reduce of step i - 1 starts now (NCCL's stream) and overlaps this step's kernels; this
+        step's moment buffer is free again once the all-reduce of step i - 2 has finished (stream-ordered wait)"""
+        b = i & 1
+        if i > 0:
+            pending[b ^ 1] = parallel.all_reduce_moments_async(mom[b ^ 1])
+        if pending[b] is not None:
+            pending[b].wait()
+            pending[b] = None
         for j, (k, prog) in enumerate(programs.items()):
-            res = engine.run_protocol(system, prog, n, steps_per_leg, KT_298, marginal="configuration", seed=seed, replica0=replica0,
-                                      x_cache=cache_dev, precision=precision, out=bufs[k])
-            moments_all[j].copy_(res["moments"], non_blocking=True)
-        parallel.all_reduce_moments(moments_all)
+            res = launch(k, prog, cache)
+            mom[b][j].copy_(res["moments"], non_blocking=True)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def drain(i_last):
+        b = i_last & 1
+        pending[b] = parallel.all_reduce_moments_async(mom[b])
+        for q in (0, 1):
+            if pending[q] is not None:
+                pending[q].wait()
+                pending[q] = None
+
+    for i in range(warmup):
+        one_pass(i)
+    drain(warmup - 1)
+    ctx.barrier()
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < min_warm_s:  # short steps: keep warming until clocks and allocator have settled
+        for i in range(20):
+            one_pass(i)
+        drain(19)
         torch.cuda.synchronize()
+    ctx.barrier()
 
-    for _ in range(args.warmup):
-        one_pass(cache)
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    # ---- device-resident timing
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx.barrier()
     if sampler:
         sampler.mark()
-    for s_ in range(args.steps):
-        flush.zero_()
-        ev[s_][0].record()
-        one_pass(cache)
-        ev[s_][1].record()
-    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(steps):
+        ctx.flush.zero_()
+        ev[s][0].record()
+        one_pass(s)
+        if s == steps - 1:
+            drain(s)
+        ev[s][1].record()
+    ctx.barrier()
+    t_wall = time.perf_counter() - t_wall0
     if sampler:
         sampler.mark()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     clocks = sampler.stop() if sampler else None
-    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_ms = float(tmax.item())
-    steps_per_pass = len(splittings) * n * 2 * steps_per_leg
-    value = world * steps_per_pass * args.steps / (dev_ms * 1e-3)
+    dev_ms = ctx.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    units_per_pass = S * n * 2 * nsl  # replica-steps per rank per bench step
+    value = world * units_per_pass * steps / (dev_ms * 1e-3)
 
-    # dominant kernel alone
-    k_ms = {k: 0.0 for k in splittings}
-    for _ in range(max(1, args.steps // 2)):
+    # ---- dominant kernel alone: events around each protocol launch, L2 flushed before each; enqueue all, sync once
+    k_reps = max(2, min(steps, 50))
+    kev = {k: [] for k in programs}
+    for _ in range(k_reps):
         for k, prog in programs.items():
-            flush.zero_()
+            ctx.flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            engine.run_protocol(system, prog, n, steps_per_leg, KT_298, seed=seed, replica0=replica0, x_cache=cache,
-                                precision=precision, out=bufs[k], want_moments=False)
+            launch(k, prog, cache)
             b.record()
-            b.synchronize()
-            k_ms[k] += a.elapsed_time(b)
-    kernel_ms = {k: v / max(1, args.steps // 2) for k, v in k_ms.items()}
+            kev[k].append((a, b))
+    torch.cuda.synchronize()
+    kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / k_reps for k, v in kev.items()}
+    estimates_dev = [ib.evaluation.estimate_from_moments(mom[(steps - 1) & 1][j].cpu().numpy()) for j in range(S)]
 
-    sink = torch.zeros(8, dtype=torch.float64, device=dev)
-    peaks = {}
-    for prec, pname in [(0, "fp64"), (1, "fp32")]:
-        blocks, iters = 148 * 8, 20000 if prec == 0 else 40000
-        best = 1e30
-        for _ in range(6):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            _cabi.check(_cabi.lib.lsi_microbench_fma(prec, iters, blocks, ctypes.c_void_p(sink.data_ptr()), engine.current_stream_ptr()))
-            b.record()
-            b.synchronize()
-            best = min(best, a.elapsed_time(b))
-        peaks[pname] = blocks * 256 * iters * 16 / (best * 1e-3) / 1e12
+    # ---- end to end through the reference-facing call (host cache in, numpy out)
+    n_e2e = min(n, W["e2e_replicas"])
+    if toy:
+        kind_of = W.get("closures")
+        sims = {}
+        for k, s in W["splittings"].items():
+            if kind_of:
+                f = getattr(numba_integrators, kind_of[k] + "_factory")(eq.potential, eq.force, eq.velocity_scale, eq.mass)
+            else:
+                f = numba_integrators.splitting_factory(s, eq.potential, eq.force, eq.velocity_scale, eq.mass)
+            sims[k] = NumbaNonequilibriumSimulator(eq, partial(f, gamma=W["gamma"], dt=W["dt"]))
+        h2d = int(eq.x_samples.nbytes)
 
-    # end to end with host buffers: H2D of the cache, D2H of the works and moments, every step
-    w_host = torch.empty(len(splittings), 2, n, dtype=torch.float64).pin_memory()
-    m_host = torch.empty(len(splittings), 8, dtype=torch.float64).pin_memory()
-    cache2 = torch.empty_like(cache)
+        def call(sim, mode):
+            eq.release_device_cache()  # the host-side cache is uploaded again, as for a caller that owns it on the host
+            if mode == "default":  # the reference's call: full work and (x, v) traces as numpy arrays
+                W_F, W_R, xv_F, xv_R = sim.collect_protocol_samples(n_e2e, plen, "configuration")
+                return ib.evaluation.estimate_nonequilibrium_free_energy(W_F[:, -1], W_R[:, -1]), W_F.nbytes + W_R.nbytes + xv_F.nbytes + xv_R.nbytes
+            if mode == "final_works":
+                W_F, W_R, _, _ = sim.collect_protocol_samples(n_e2e, plen, "configuration", traces=False)
+                return ib.evaluation.estimate_nonequilibrium_free_energy(W_F[:, -1], W_R[:, -1]), W_F.nbytes + W_R.nbytes
+            sim.collect_protocol_samples(n_e2e, plen, "configuration", traces=False, as_numpy=False)
+            return ib.evaluation.estimate_from_moments(sim.last_moments.cpu().numpy()), 64
+        modes = ["default", "final_works", "estimate_only"]
+    else:
+        sims = {}
+        for k, s in W["splittings"].items():
+            integ = LangevinSplittingIntegrator(s, temperature=298.0 * unit.kelvin, collision_rate=W["gamma"] / unit.picoseconds,
+                                                timestep=W["dt"] * unit.picoseconds)
+            sims[k] = NonequilibriumSimulator(eq, integ, precision=precision)
+        h2d = int(eq.samples.nbytes)
 
-    def e2e_pass(copy_works=True):
-        cache2.copy_(cache_host, non_blocking=True)
-        for j, (k, prog) in enumerate(programs.items()):
-            res = engine.run_protocol(system, prog, n, steps_per_leg, KT_298, seed=seed, replica0=replica0, x_cache=cache2,
-                                      precision=precision, out=bufs[k])
-            if copy_works:
-                w_host[j].copy_(res["W"], non_blocking=True)
-            moments_all[j].copy_(res["moments"], non_blocking=True)
-        parallel.all_reduce_moments(moments_all)
-        m_host.copy_(moments_all, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return [ib.evaluation.estimate_from_moments(m_host[j].numpy()) for j in range(len(splittings))]
+        def call(sim, mode):
+            eq.release_device_cache()
+            if mode == "default":  # the reference's call: {"W_shads_F", "W_shads_R"} as numpy arrays
+                r = sim.collect_protocol_samples(n_e2e, plen, "configuration")
+                return ib.evaluation.estimate_nonequilibrium_free_energy(r["W_shads_F"], r["W_shads_R"]), r["W_shads_F"].nbytes + r["W_shads_R"].nbytes
+            sim.collect_protocol_samples(n_e2e, plen, "configuration", as_numpy=False)
+            return ib.evaluation.estimate_from_moments(sim.last_moments.cpu().numpy()), 64
+        modes = ["default", "estimate_only"]
 
-    e2e_pass()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(2, args.steps // 2)
-    for _ in range(e2e_steps):
-        estimates = e2e_pass()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * steps_per_pass * e2e_steps / float(e2e_s.item())
-    # the same call for a caller that keeps the works on the device and reads back only the estimate's moments
-    for _ in range(2):
-        e2e_pass(copy_works=False)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_pass(copy_works=False)
-    barrier()
-    e2e_m = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_m, op=dist.ReduceOp.MAX)
-    e2e_estimate_only = world * steps_per_pass * e2e_steps / float(e2e_m.item())
+    e2e_steps = max(2, min(steps // 2, 10))
+    e2e = {}
+    for mode in modes:
+        d2h = 0
+        for _ in range(2):  # first calls page-lock their staging buffers
+            for sim in sims.values():
+                call(sim, mode)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            d2h = 0
+            ests = []
+            for sim in sims.values():
+                est, nbytes = call(sim, mode)
+                ests.append(est)
+                d2h += nbytes
+        ctx.barrier()
+        secs = ctx.max_over_ranks(time.perf_counter() - t0)
+        e2e[mode] = {"value": world * S * n_e2e * 2 * nsl * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": h2d * S,
+                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "replicas_per_call": n_e2e}
+        if mode == "default":
+            estimates_e2e = ests
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
+    # ---- roofline of the dominant kernel
+    peaks = ctx.peaks()
     kernel_s = sum(kernel_ms.values()) * 1e-3
-    alg = sum(flops[k] * n * 2 * steps_per_leg for k in splittings)
-    achieved = alg / kernel_s / 1e12
-    peak = peaks["fp32"] if precision == "mixed" else peaks["fp64"]
-    roofline = {"bound": "fp32_fma" if precision == "mixed" else "fp64_fma", "kernel": "particles_protocol_kernel<%s>" % name,
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": "lsi_microbench_fma, best of 6, measured in this run (fp32 %.1f, fp64 %.1f TFLOP/s)" % (peaks["fp32"], peaks["fp64"]),
-                "note": "algorithmic flops per replica-step from SURVEY 8d (half-shell pair count; FMA = 2); the kernel runs a "
-                        "full-shell loop (twice the pair evaluations, no atomics) with fp64 constraints and bookkeeping",
-                "replica_steps_per_s_kernel_only": len(splittings) * n * 2 * steps_per_leg / kernel_s,
-                "kernel_ms_per_splitting": kernel_ms, "flops_per_replica_step": flops}
-    if name in HBM_BYTES_PER_STEP_STREAMING:
-        peaks_file = {}
-        try:
-            peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
-        eq = HBM_BYTES_PER_STEP_STREAMING[name] * roofline["replica_steps_per_s_kernel_only"] / 1e9
-        roofline["hbm_equivalent"] = {"achieved": eq, "peak": hbm_peak, "unit": "GB/s", "frac": eq / hbm_peak,
-                                      "note": "bytes a per-step-streaming design would move (19.6 KB per replica-step); this "
-                                              "kernel keeps the state in shared memory and moves 7.4 KB per replica-PROTOCOL",
-                                      "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback"}
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        n_ref = args.ref_replicas or {"water_cluster": 512, "alanine": 2048, "waterbox": 48}[name]
-        v, secs = particles_cpu_port(name, cache_host.numpy(), n_ref, min(steps_per_leg, 50), dt, splittings)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": "%d replicas x %d splittings x 2 legs x %d steps (%.1f s; restated fp64 CPU oracle, OpenMP over replicas; not "
-                         "OpenMM -- the reference's own figure is 1.28e4 replica-steps/s on the OpenMM Reference platform for alanine "
-                         "dipeptide, BASELINE.md)" % (n_ref, len(splittings), min(steps_per_leg, 50), secs)}
-    print(json.dumps({
-        "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 forces / f64 state" if precision == "mixed" else "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cache_host.numel() * 8),
-                "d2h_bytes_per_step": int(w_host.numel() * 8 + m_host.numel() * 8), "steps": e2e_steps,
-                "estimate_only": {"value": e2e_estimate_only, "unit": UNIT, "d2h_bytes_per_step": int(m_host.numel() * 8),
-                                  "note": "works stay on the device (as_numpy=False); only the moments of the estimate are read back"}},
-        "gpu_launches": args.steps * len(splittings) * 3, "roofline": roofline, "cpu_baseline": cpu,
-        "DeltaF_neq": {k: {"estimate": e[0], "stderr": float(np.sqrt(max(e[1], 0.0)))} for k, e in zip(splittings, estimates)}}))
-    if world > 1:
-        dist.destroy_process_group()
+    if toy:
+        fl = {k: flops_per_step(s, W["f_force"]) for k, s in W["splittings"].items()}
+        bound, peak, kname = "fp64_fma", peaks["fp64"], "toy_fused_kernel<%s, splitting>" % name
+        note = ("algorithmic flops exclude the Philox + Box-Muller noise generation that dominates the instruction count "
+                "(n_O Gaussians per replica-step)")
+    else:
+        fl = W["flops"]
+        fp32 = precision == "mixed"
+        bound, peak, kname = ("fp32_fma" if fp32 else "fp64_fma"), (peaks["fp32"] if fp32 else peaks["fp64"]), "particles_protocol_kernel<%s>" % name
+        note = ("algorithmic flops per replica-step from SURVEY 8d (half-shell pair count; FMA = 2); the kernel runs a full-shell "
+                "loop (twice the pair evaluations, no atomics) with fp64 constraints and bookkeeping")
+    achieved = sum(fl[k] * n * 2 * nsl for k in programs) / kernel_s / 1e12
+    hpk, hsrc = hbm_peak()
+    hbm_bytes = S * n * (8 + 16) if toy else S * n * (24 * system.n_atoms + 16)  # per pass: start state in, two works out
+    roofline = {"bound": bound, "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": 8.04e6 if (name == "double_well" and n == (1 << 20)) else None,
+                "peak_source": "lsi_microbench_fma, best of 6, measured in this run (fp64 %.1f, fp32 %.1f TFLOP/s)" % (peaks["fp64"], peaks["fp32"]),
+                "note": note, "replica_steps_per_s_kernel_only": units_per_pass / kernel_s, "kernel_ms_per_splitting": kernel_ms,
+                "flops_per_replica_step": fl,
+                "hbm": {"achieved": hbm_bytes / kernel_s / 1e9, "peak": hpk, "unit": "GB/s", "frac": hbm_bytes / kernel_s / 1e9 / hpk,
+                        "peak_source": hsrc, "note": "algorithmic bytes: start state gathered once, two works written per replica"}}
+    if "hbm_bytes_per_step_streaming" in W:
+        eqv = W["hbm_bytes_per_step_streaming"] * units_per_pass / kernel_s / 1e9
+        roofline["hbm_equivalent"] = {"achieved": eqv, "peak": hpk, "unit": "GB/s", "frac": eqv / hpk, "peak_source": hsrc,
+                                      "note": "bytes a per-step-streaming design would move (19.6 KB per replica-step); this kernel "
+                                              "keeps the state in shared memory and moves 7.4 KB per replica-PROTOCOL"}
+    main = dict(e2e["default"])
+    main["call"] = ("NumbaNonequilibriumSimulator.collect_protocol_samples(n, protocol_length, marginal)" if toy else
+                    "NonequilibriumSimulator.collect_protocol_samples(n, protocol_length, marginal)") + ", default arguments, numpy results"
+    if "final_works" in e2e:
+        main["final_works_only"] = dict(e2e["final_works"], note="same call with traces=False: the two final work arrays only")
+    main["estimate_only"] = dict(e2e["estimate_only"], note="same call with as_numpy=False: works stay on the device, the moments of the estimate are read back")
+    launches_per_protocol = 2 if toy else 3
+    rec = {"metric": metric_name(name, W), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64" if precision == "double" else "f32 forces and O noise / f64 state, constraints and accumulators",
+           "data": "synthetic", "config": workload_config(name, W, n, plen), "wall_ms_per_step_incl_flush": 1e3 * t_wall / steps,
+           "clocks": clocks, "e2e": main, "gpu_launches": steps * S * launches_per_protocol, "roofline": roofline,
+           "cpu_baseline": cpu_baseline(name, W) if with_cpu else None,
+           "DeltaF_neq": {k: {"estimate": e[0], "stderr": float(np.sqrt(max(e[1], 0.0)))} for k, e in zip(programs, estimates_dev)},
+           "DeltaF_neq_e2e": {k: {"estimate": float(e[0]), "stderr": float(np.sqrt(max(e[1], 0.0)))} for k, e in zip(programs, estimates_e2e)}}
+    return rec
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=0, help="0 = 200 (double_well) / 4 (particle workloads)")
-    ap.add_argument("--warmup", type=int, default=0, help="0 = 10 (double_well) / 3")
+    ap.add_argument("--steps", type=int, default=0, help="0 = 200 (toy headline) / 4 (particle workloads)")
+    ap.add_argument("--warmup", type=int, default=0, help="0 = 10 (toy headline) / 3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="double_well", choices=["double_well"] + sorted(PARTICLE_WORKLOADS),
-                    help="double_well = BASELINE configs[1] (the headline); the others are configs[2..4]")
+    ap.add_argument("--workload", default="all", choices=["all"] + ORDER,
+                    help="all = C2 headline + per_workload records of the other configs; or one config alone")
     ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (0 = the workload's default)")
     ap.add_argument("--protocol-length", type=int, default=0, help="0 = the workload's default")
-    ap.add_argument("--ref-replicas", type=int, default=0)
+    ap.add_argument("--ref-replicas", type=int, default=0, help="protocols per scheme (toy) / replicas (particles) of one reference-arm step")
     ap.add_argument("--precision", default=None, choices=[None, "double", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "ours" and args.warmup:
-        args.warmup = max(args.warmup, 3)  # timing rule: at least three warm-up steps
-    if args.workload != "double_well":
-        args.steps, args.warmup = args.steps or 4, args.warmup or 3
-        return run_particles(args)
-    args.steps, args.warmup = args.steps or 200, args.warmup or 10
-    args.replicas = args.replicas or (1 << 20)
-    args.protocol_length = args.protocol_length or 10
-    args.ref_replicas = args.ref_replicas or (1 << 17)
-
+    names = ORDER if args.workload == "all" else [args.workload]
+    head = names[0]
+    toy_head = WORKLOADS[head]["kind"] == "toy"
+    if args.ref_replicas:
+        WORKLOADS[head] = dict(WORKLOADS[head], ref_replicas=args.ref_replicas)
     if args.impl == "reference":
+        args.steps, args.warmup = args.steps or 5, args.warmup or 1
         return run_reference(args)
+    args.steps = args.steps or (200 if toy_head else 4)
+    args.warmup = max(args.warmup or (10 if toy_head else 3), 3)  # timing rule: at least three warm-up steps
+    if args.precision:
+        for nm in names:
+            WORKLOADS[nm] = dict(WORKLOADS[nm], precision=args.precision)
 
-    import torch
-    import torch.distributed as dist
-
-    import integrator_benchmark_b200 as ib
-    from integrator_benchmark_b200 import _cabi, engine, parallel
-    import ctypes
-
-    rank, world, local_rank = parallel.init_process_group()
-    engine.require_cuda()
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    n = args.replicas
-    steps_per_leg = args.protocol_length - 1
-    replica0 = rank * n  # global replica ids: rank r owns [r n, (r + 1) n)
-    seed = 0x5EED0002
-
-    from integrator_benchmark_b200.testsystems import double_well
-    system = engine.ScalarSystem(SYSTEM, MASS)
-    programs = {k: engine.Program(s, DT, GAMMA) for k, s in SPLITTINGS.items()}
-    # equilibrium cache (input of the path, generated once on the GPU, same on every rank)
-    x_cache_host = torch.from_numpy(double_well.collect_equilibrium_samples(N_CACHE, n_burn=300, seed=seed)).pin_memory()
-    x_cache = x_cache_host.to(dev)
-    bufs = {k: {} for k in SPLITTINGS}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    moments_all = torch.zeros(len(SPLITTINGS), 8, dtype=torch.float64, device=dev)
-
-    toy_precision = args.precision or "double"
-
-    def one_pass(x_cache_dev):
-        for j, (k, prog) in enumerate(programs.items()):
-            res = engine.run_protocol(system, prog, n, steps_per_leg, 1.0 / BETA, marginal="configuration", seed=seed,
-                                      replica0=replica0, x_cache=x_cache_dev, out=bufs[k], precision=toy_precision)
-            moments_all[j].copy_(res["moments"], non_blocking=True)
-        parallel.all_reduce_moments(moments_all)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        one_pass(x_cache)
-    barrier()
-    # a step is ~1.5 ms: keep warming (untimed) for at least half a second so that clocks and the
-    # allocator have settled on a fresh box before anything is timed
-    t_warm = time.perf_counter()
-    while time.perf_counter() - t_warm < 0.5:
-        for _ in range(20):
-            one_pass(x_cache)
-        torch.cuda.synchronize()
-    barrier()
-
-    # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed (untimed) in between
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    if sampler:
-        sampler.mark()
-    t_wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush.zero_()
-        ev[s][0].record()
-        one_pass(x_cache)
-        ev[s][1].record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    if sampler:
-        sampler.mark()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop() if sampler else None
-    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_ms = float(tmax.item())
-    steps_per_pass = len(SPLITTINGS) * n * 2 * steps_per_leg  # replica-steps per rank per bench step
-    value = world * steps_per_pass * args.steps / (dev_ms * 1e-3)
-
-    # ---- dominant kernel alone: events around each protocol launch (kernel + 1-block finalize), L2 flushed before
-    # each one; everything is enqueued first and synchronised once, so the GPU does not idle between launches
-    kev = {k: [] for k in SPLITTINGS}
-    for s in range(args.steps):
-        for j, (k, prog) in enumerate(programs.items()):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            engine.run_protocol(system, prog, n, steps_per_leg, 1.0 / BETA, marginal="configuration", seed=seed,
-                                replica0=replica0, x_cache=x_cache, out=bufs[k], precision=toy_precision)
-            b.record()
-            kev[k].append((a, b))
-    torch.cuda.synchronize()
-    kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in kev.items()}
-
-    # ---- measured FMA peaks (same run, burst = best of 5)
-    sink = torch.zeros(8, dtype=torch.float64, device=dev)
-    peaks = {}
-    for prec, name in [(0, "fp64"), (1, "fp32")]:
-        blocks, iters = 148 * 8, 20000 if prec == 0 else 40000
-        best = 1e30
-        for _ in range(6):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            _cabi.check(_cabi.lib.lsi_microbench_fma(prec, iters, blocks, ctypes.c_void_p(sink.data_ptr()),
-                                                     engine.current_stream_ptr()))
-            b.record()
-            b.synchronize()
-            best = min(best, a.elapsed_time(b))
-        peaks[name] = blocks * 256 * iters * 16 / (best * 1e-3) / 1e12  # TFLOP/s
-
-    # ---- end to end through the public API with HOST buffers (pinned), every step:
-    #      H2D of the equilibrium cache, 6 launches, D2H of both work arrays per splitting
-    w_host = torch.empty(len(SPLITTINGS), 2, n, dtype=torch.float64).pin_memory()
-    m_host = torch.empty(len(SPLITTINGS), 8, dtype=torch.float64).pin_memory()
-    x_dev = torch.empty_like(x_cache)
-
-    # D2H of the works rides a copy stream so that it overlaps the next splitting's kernel (PCIe, not the SMs,
-    # bounds this loop: 100 MB per step); events order kernel -> copy and copy -> next reuse of the buffer
-    copy_stream = torch.cuda.Stream(device=dev)
-    done_k = [torch.cuda.Event() for _ in SPLITTINGS]
-    done_c = [torch.cuda.Event() for _ in SPLITTINGS]
-    for e in done_c:
-        e.record(copy_stream)
-
-    def e2e_pass(copy_works=True):
-        main = torch.cuda.current_stream()
-        x_dev.copy_(x_cache_host, non_blocking=True)
-        for j, (k, prog) in enumerate(programs.items()):
-            main.wait_event(done_c[j])  # the previous pass's copy of this buffer has left
-            res = engine.run_protocol(system, prog, n, steps_per_leg, 1.0 / BETA, marginal="configuration", seed=seed,
-                                      replica0=replica0, x_cache=x_dev, out=bufs[k], precision=toy_precision)
-            moments_all[j].copy_(res["moments"], non_blocking=True)
-            if copy_works:
-                done_k[j].record(main)
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(done_k[j])
-                    w_host[j].copy_(res["W"], non_blocking=True)
-                    done_c[j].record(copy_stream)
-        parallel.all_reduce_moments(moments_all)
-        m_host.copy_(moments_all, non_blocking=True)
-        main.synchronize()
-        copy_stream.synchronize()
-        return [ib.evaluation.estimate_from_moments(m_host[j].numpy()) for j in range(len(SPLITTINGS))]
-
-    for _ in range(3):
-        e2e_pass()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(3, args.steps // 2)
-    for _ in range(e2e_steps):
-        estimates = e2e_pass()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * steps_per_pass * e2e_steps / float(e2e_s.item())
-    # the same call for a caller that keeps the works on the device and reads back only the estimate's moments
-    for _ in range(2):
-        e2e_pass(copy_works=False)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_pass(copy_works=False)
-    barrier()
-    e2e_m = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_m, op=dist.ReduceOp.MAX)
-    e2e_estimate_only = world * steps_per_pass * e2e_steps / float(e2e_m.item())
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    alg_flops = sum(flops_per_step(s) * n * 2 * steps_per_leg for s in SPLITTINGS.values())
-    kernel_s = sum(kernel_ms.values()) * 1e-3
-    achieved = alg_flops / kernel_s / 1e12
-    hbm_bytes = len(SPLITTINGS) * n * (8 + 16)  # per pass: gather x0 (8 B) + write W_F, W_R (16 B) per replica
-    peaks_file = {}
-    try:
-        peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:  # noqa: BLE001
-        pass
-    hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
-    roofline = {
-        "bound": "fp64_fma", "kernel": "toy_fused_kernel<double_well, splitting>", "achieved": achieved, "peak": peaks["fp64"],
-        "unit": "TFLOP/s", "frac": achieved / peaks["fp64"],
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch of toy_fused_kernel, ncu --set full
-        # (profiles/r1_toy_fused_ncu_details.txt): the 8 MB equilibrium cache is read once, the works stay in L2
-        "traffic": 8.04e6 if n == (1 << 20) else None,
-        "peak_source": "lsi_microbench_fma fp64, best of 6, measured in this run (fp32: %.1f TFLOP/s)" % peaks["fp32"],
-        "note": "algorithmic flops exclude the Philox + Box-Muller noise generation that dominates the instruction count "
-                "(n_O Gaussians per replica-step); ncu (profiles/r1_ncu_summary.json): issue slots busy + FP64 pipe busy / 2 "
-                "= 86-91 % of the dispatch limit of the 16-lane fp64 sub-partitions",
-        "replica_steps_per_s_kernel_only": len(SPLITTINGS) * n * 2 * steps_per_leg / kernel_s,
-        "kernel_ms_per_splitting": kernel_ms,
-        "flops_per_replica_step": {k: flops_per_step(s) for k, s in SPLITTINGS.items()},
-        "hbm": {"achieved": hbm_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback"},
-    }
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        _, warm = cpu_port_throughput(args.ref_replicas * 2, args.protocol_length)        # also warms the thread pool
-        repeats = int(min(64, max(1, round(10.0 / max(warm, 1e-3)))))                     # about 10 s of CPU work
-        v, secs = cpu_port_throughput(args.ref_replicas * 2, args.protocol_length, repeats=repeats)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": "%d replicas x 6 splittings x %d passes (%.1f s, OpenMP over replicas)"
-                         % (args.ref_replicas * 2, repeats, secs)}
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64" if toy_precision == "double" else "f64 state, f32-generated Gaussians", "data": "synthetic",
-        "config": workload_config(args, n),
-        "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_cache_host.numel() * 8),
-                "d2h_bytes_per_step": int(w_host.numel() * 8 + m_host.numel() * 8), "steps": e2e_steps,
-                "estimate_only": {"value": e2e_estimate_only, "unit": UNIT, "d2h_bytes_per_step": int(m_host.numel() * 8),
-                                  "note": "works stay on the device (as_numpy=False); only the moments of the estimate are read back"}},
-        "gpu_launches": args.steps * len(SPLITTINGS) * 2,
-        "roofline": roofline, "cpu_baseline": cpu,
-        "DeltaF_neq": {k: {"estimate": e[0], "stderr": float(np.sqrt(max(e[1], 0.0)))} for k, e in zip(SPLITTINGS, estimates)},
-    }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    ctx = Context()
+    W = WORKLOADS[head]
+    with_cpu = ctx.world == 1 and not args.no_cpu_baseline
+    line = gpu_record(ctx, head, W, args.steps, args.warmup, args.replicas or W["replicas"], args.protocol_length or W["protocol_length"],
+                      with_cpu, min_warm_s=0.5 if toy_head else 0.0)
+    per = {}
+    for nm in names[1:]:
+        Wn = WORKLOADS[nm]
+        k = 20 if Wn["kind"] == "toy" else 4
+        rec = gpu_record(ctx, nm, Wn, k, 3, Wn["replicas"], Wn["protocol_length"], with_cpu, min_warm_s=0.2 if Wn["kind"] == "toy" else 0.0)
+        if rec is not None:
+            per["%s %s" % (Wn["config"], nm)] = rec
+    if ctx.rank == 0:
+        if per:
+            line["per_workload"] = per
+        print(json.dumps(line))
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -246,14 +246,26 @@ class EquilibriumSimulator:
         """Install an externally produced cache, e.g. the frames of the reference's
         data/tiny_waterbox_constrained_samples.h5 (tests/golden/waterbox_frames.npz)."""
         xyz = np.asarray(getattr(samples, "xyz", samples), dtype=np.float64)
-        self.samples = np.ascontiguousarray(xyz[None] if xyz.ndim == 2 else xyz)
+        t = engine.torch()
+        host = t.as_tensor(np.ascontiguousarray(xyz[None] if xyz.ndim == 2 else xyz)).clone()
+        if t.cuda.is_available():
+            host = host.pin_memory()  # uploads of the cache are asynchronous DMAs from page-locked memory
+        self._samples_host = host
+        self.samples = host.numpy()
         self._samples_dev = None
         self.cached = True
+
+    def release_device_cache(self):
+        """Forget the device copy of the cache: the next protocol call uploads `samples` again (host -> device)."""
+        self._samples_dev = None
 
     def samples_device(self):
         self.load_or_simulate_samples()
         if self._samples_dev is None:
-            self._samples_dev = engine.torch().as_tensor(self.samples).cuda()
+            host = getattr(self, "_samples_host", None)
+            if host is None or host.numpy().ctypes.data != np.asarray(self.samples).ctypes.data:
+                host = engine.torch().as_tensor(np.ascontiguousarray(self.samples, dtype=np.float64))
+            self._samples_dev = host.to("cuda", non_blocking=True)
         return self._samples_dev
 
     def sample_x_from_equilibrium(self):

@@ -50,11 +50,30 @@ class NumbaBookkeepingSimulator:
         self.x_samples = self.collect_equilibrium_samples()
         self.cached = True
 
+    def set_x_samples(self, x_samples):
+        """Install a host-side equilibrium cache (what the reference keeps in `x_samples`).  The copy lives in pinned
+        memory so that every upload to the device is an asynchronous DMA from page-locked pages."""
+        t = engine.torch()
+        host = t.as_tensor(np.ascontiguousarray(x_samples, dtype=np.float64)).clone()
+        if t.cuda.is_available():
+            host = host.pin_memory()
+        self._x_samples_host = host
+        self.x_samples = host.numpy()
+        self._x_samples_dev = None
+        self.cached = True
+
+    def release_device_cache(self):
+        """Forget the device copy of the cache: the next protocol call uploads `x_samples` again (host -> device)."""
+        self._x_samples_dev = None
+
     def x_samples_device(self):
         if not self.cached:
             self.load_or_simulate_x_samples()
         if self._x_samples_dev is None:
-            self._x_samples_dev = engine.torch().as_tensor(self.x_samples).cuda()
+            host = getattr(self, "_x_samples_host", None)
+            if host is None or host.numpy().ctypes.data != np.asarray(self.x_samples).ctypes.data:
+                host = engine.torch().as_tensor(np.ascontiguousarray(self.x_samples, dtype=np.float64))
+            self._x_samples_dev = host.to("cuda", non_blocking=True)
         return self._x_samples_dev
 
     def sample_x_from_equilibrium(self):

@@ -110,7 +110,17 @@ def pool(processes):
         if _pool is not None:
             _pool.terminate()
         _pool = mp.get_context("fork").Pool(processes)
+        import atexit
+        atexit.register(close_pool)
     return _pool
+
+
+def close_pool():
+    global _pool
+    if _pool is not None:
+        _pool.terminate()
+        _pool.join()
+        _pool = None
 
 
 def collect_parallel(system_name, schemes, x_samples, n_per_scheme, protocol_length, marginal, gamma, dt, processes=None, seed=0):

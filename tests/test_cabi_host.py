@@ -129,14 +129,17 @@ def test_particle_system_validation_is_host_only_and_loud():
 
 
 def test_bench_reference_arm_runs_without_a_gpu():
-    """`bench.py --impl reference` times the CPU oracle port and prints the contract's JSON line (no CUDA needed)"""
+    """`bench.py --impl reference` times the reference's own numba closures (oracle/_ref, when installed; otherwise the CPU
+    oracle port) on the host cores and prints the contract's JSON line (no CUDA needed)"""
     import json
     import subprocess
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                          "--ref-replicas", "2048"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          "--workload", "double_well", "--ref-replicas", "2048"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "replica-steps/s"
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "numba_integrators.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["value"] == line["value"]
     assert line["higher_is_better"] is True and line["steps"] == 2 and line["gpu_launches"] == 0
+    assert line["config"]["replicas_per_gpu"] == 1 << 20 and "C2 double well" in line["config"]["workload"]
