@@ -9,8 +9,9 @@ Default (`--workload all`): ONE JSON line whose top level is the headline, BASEL
 short fixed number of steps: C1 quartic (the reference's vvvr / baoab closures), C3 rigid water cluster, C4 alanine
 dipeptide (VRORV + an MTS string), C5 tiny water box.  `--workload NAME` measures one of them alone as the top level.
 
-One bench "step" = one pass over the batch = one fused protocol launch per splitting (forward leg, midpoint velocity
-redraw, reverse leg) + the DeltaF_neq moment reduction, all-reduced over ranks.
+One bench "step" = one pass over the batch = the fused protocol (forward leg, midpoint velocity redraw, reverse leg) of
+every splitting -- scalar systems: all splittings in ONE launch (lsi_run_protocol_batch), particle systems: one launch per
+splitting -- + the DeltaF_neq moment reduction, all-reduced over ranks.
   value     device-resident throughput: inputs in HBM, CUDA events around every step, L2 flushed (untimed) between steps,
             max over ranks.  The moment all-reduce of step s is started inside the timed interval of step s + 1 and
             overlaps its kernels (moments are additive; nothing downstream needs them earlier); the last ones are
@@ -434,9 +435,18 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
     mom = [torch.zeros(S, 8, dtype=torch.float64, device=dev) for _ in range(2)]
     pending = [None, None]
 
-    def launch(k, prog, x_cache_dev, want_moments=True):
+    def launch(k, prog, x_cache_dev, moments_out=None):
         return engine.run_protocol(system, prog, n, nsl, W["kT"], marginal="configuration", seed=seed, replica0=replica0,
-                                   x_cache=x_cache_dev, out=bufs[k], precision=precision, want_moments=want_moments)
+                                   x_cache=x_cache_dev, out=bufs[k], precision=precision, moments_out=moments_out)
+
+    def launch_all(moments_out):
+        """all splittings of the step: scalar systems in ONE launch (lsi_run_protocol_batch), particle systems one by one"""
+        if toy:
+            engine.run_protocols(system, list(programs.values()), n, nsl, W["kT"], marginal="configuration", seed=seed,
+                                 replica0=replica0, x_cache=cache, precision=precision, outs=list(bufs.values()), moments_out=moments_out)
+        else:
+            for j, (k, prog) in enumerate(programs.items()):
+                launch(k, prog, cache, moments_out[j])
 
     def one_pass(i):
         """bench step i: the all-reduce of step i - 1 starts now (NCCL's stream) and overlaps this step's kernels; this
@@ -447,9 +457,7 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
         if pending[b] is not None:
             pending[b].wait()
             pending[b] = None
-        for j, (k, prog) in enumerate(programs.items()):
-            res = launch(k, prog, cache)
-            mom[b][j].copy_(res["moments"], non_blocking=True)
+        launch_all(mom[b])
 
     def drain(i_last):
         b = i_last & 1
@@ -505,8 +513,18 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
             launch(k, prog, cache)
             b.record()
             kev[k].append((a, b))
+    bev = []
+    scratch_mom = torch.zeros(S, 8, dtype=torch.float64, device=dev)
+    for _ in range(k_reps if toy else 0):  # the step's launch as the bench issues it (one batch launch + one finalize)
+        ctx.flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        launch_all(scratch_mom)
+        b.record()
+        bev.append((a, b))
     torch.cuda.synchronize()
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / k_reps for k, v in kev.items()}
+    batch_ms = sum(a.elapsed_time(b) for a, b in bev) / k_reps if bev else None
     estimates_dev = [ib.evaluation.estimate_from_moments(mom[(steps - 1) & 1][j].cpu().numpy()) for j in range(S)]
 
     # ---- end to end through the reference-facing call (host cache in, numpy out)
@@ -578,10 +596,10 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
 
     # ---- roofline of the dominant kernel
     peaks = ctx.peaks()
-    kernel_s = sum(kernel_ms.values()) * 1e-3
+    kernel_s = (batch_ms if batch_ms is not None else sum(kernel_ms.values())) * 1e-3
     if toy:
         fl = {k: flops_per_step(s, W["f_force"]) for k, s in W["splittings"].items()}
-        bound, peak, kname = "fp64_fma", peaks["fp64"], "toy_fused_kernel<%s, splitting>" % name
+        bound, peak, kname = "fp64_fma", peaks["fp64"], "toy_fused2_batch_kernel<%s, %d splittings in one launch>" % (name, S)
         note = ("algorithmic flops exclude the Philox + Box-Muller noise generation that dominates the instruction count "
                 "(n_O Gaussians per replica-step)")
     else:
@@ -597,6 +615,7 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
                 "traffic": 8.04e6 if (name == "double_well" and n == (1 << 20)) else None,
                 "peak_source": "lsi_microbench_fma, best of 6, measured in this run (fp64 %.1f, fp32 %.1f TFLOP/s)" % (peaks["fp64"], peaks["fp32"]),
                 "note": note, "replica_steps_per_s_kernel_only": units_per_pass / kernel_s, "kernel_ms_per_splitting": kernel_ms,
+                "kernel_ms_batch_launch": batch_ms,
                 "flops_per_replica_step": fl,
                 "hbm": {"achieved": hbm_bytes / kernel_s / 1e9, "peak": hpk, "unit": "GB/s", "frac": hbm_bytes / kernel_s / 1e9 / hpk,
                         "peak_source": hsrc, "note": "algorithmic bytes: start state gathered once, two works written per replica"}}
@@ -611,12 +630,12 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
     if "final_works" in e2e:
         main["final_works_only"] = dict(e2e["final_works"], note="same call with traces=False: the two final work arrays only")
     main["estimate_only"] = dict(e2e["estimate_only"], note="same call with as_numpy=False: works stay on the device, the moments of the estimate are read back")
-    launches_per_protocol = 2 if toy else 3
+    launches_per_step = 2 if toy else 3 * S  # toy: one batch kernel + one finalize; particles: protocol + partials + finalize each
     rec = {"metric": metric_name(name, W), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
            "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64" if precision == "double" else "f32 forces and O noise / f64 state, constraints and accumulators",
            "data": "synthetic", "config": workload_config(name, W, n, plen), "wall_ms_per_step_incl_flush": 1e3 * t_wall / steps,
-           "clocks": clocks, "e2e": main, "gpu_launches": steps * S * launches_per_protocol, "roofline": roofline,
+           "clocks": clocks, "e2e": main, "gpu_launches": steps * launches_per_step, "roofline": roofline,
            "cpu_baseline": cpu_baseline(name, W) if with_cpu else None,
            "DeltaF_neq": {k: {"estimate": e[0], "stderr": float(np.sqrt(max(e[1], 0.0)))} for k, e in zip(programs, estimates_dev)},
            "DeltaF_neq_e2e": {k: {"estimate": float(e[0]), "stderr": float(np.sqrt(max(e[1], 0.0)))} for k, e in zip(programs, estimates_e2e)}}

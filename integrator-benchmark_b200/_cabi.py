@@ -96,6 +96,7 @@ def _load():
         "lsi_system_num_dof": (i32, [vp]),
         "lsi_protocol_workspace_bytes": (i64, [i64]),
         "lsi_run_protocol": (i32, [vp, vp, ctypes.POINTER(ProtocolArgs), vp]),
+        "lsi_run_protocol_batch": (i32, [vp, ctypes.POINTER(vp), i32, ctypes.POINTER(ProtocolArgs), vp]),
         "lsi_sample_equilibrium_scalar": (i32, [vp, dbl, i64, ctypes.c_int32, u64, u64, vp, vp]),
         "lsi_sample_equilibrium_particles": (i32, [vp, ctypes.c_int32, dbl, i64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, dbl,
                                                    u64, u64, vp, vp, vp, vp, vp]),

@@ -53,6 +53,31 @@ LSI_EXPORT int lsi_run_protocol(const lsi_system* sys, const lsi_program* prog, 
     return lsi_particles_run_protocol(sys, prog, args, stream);
 }
 
+LSI_EXPORT int lsi_run_protocol_batch(const lsi_system* sys, const lsi_program* const* progs, int32_t n_progs,
+                                      const lsi_protocol_args* args, void* stream)
+{
+    if (!sys || !progs || !args || n_progs < 0) return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol_batch: bad argument");
+    for (int p = 0; p < n_progs; ++p)
+        if (!progs[p]) return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol_batch: NULL program");
+    if (sys->kind != LSI_SYS_SCALAR) {
+        for (int p = 0; p < n_progs; ++p) {
+            const int rc = lsi_run_protocol(sys, progs[p], &args[p], stream);
+            if (rc != LSI_OK) return rc;
+        }
+        return LSI_OK;
+    }
+    for (int p = 0; p < n_progs; ++p) {
+        const lsi_protocol_args* a = &args[p];
+        if (a->n_replicas < 0 || a->n_steps < 0 || a->n_legs < 1) return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol_batch: negative size");
+        if (a->marginal != LSI_MARGINAL_CONFIGURATION && a->marginal != LSI_MARGINAL_FULL)
+            return lsi_set_error(LSI_ERR_UNSUPPORTED, "`marginal` must be either 'configuration' or 'full'");
+        if (!(a->kT > 0.0)) return lsi_set_error(LSI_ERR_ARG, "kT must be positive");
+        if (progs[p]->ops.empty()) return lsi_set_error(LSI_ERR_ARG, "empty program");
+    }
+    if (lsi_device_count() <= 0) return lsi_set_error(LSI_ERR_CUDA, "no CUDA device: liblsi has no CPU fallback");
+    return lsi_toy_run_protocol_batch(sys, progs, n_progs, args, stream);
+}
+
 int lsi_program_stage(const lsi_program* prog, const void* bytes, size_t n_bytes, void** dev_out)
 {
     int dev = 0;

@@ -161,7 +161,46 @@ __device__ __forceinline__ double sin_medium(double x)
 struct Tables {
     double2 lg[128];    // {1 / c_i, -2 log c_i}
     double2 tr[1024];   // {sin, cos}(2 pi j / 1024)
+    static constexpr int kTrigBits = 10;
+    __device__ __forceinline__ double2 log_entry(int i) const { return lg[i]; }
+    __device__ __forceinline__ double2 trig_entry(unsigned j) const { return tr[j]; }
 };
+
+// The same tables laid out so that a random gather never has a bank conflict: a 16-byte shared-memory load is served one
+// quarter-warp at a time (8 lanes x 16 B = the 128-byte width of the 32 banks), so every table is stored 8 times,
+// interleaved -- entry i, copy c at index 8 i + c -- and lane l reads only copy l & 7: the 8 lanes of a quarter-warp
+// always fall into 8 different 16-byte bank groups, whatever their indices.  (With one copy a random gather of the 1024-entry
+// table averaged 9.3 wavefronts per request instead of 4, and the shared-memory pipe was 60 % busy: profiles/README.md.)
+// The trig table keeps every second angle (512 entries, |delta| <= pi / 512: cos delta - 1 truncated after delta^4 is off
+// by at most 7.4e-17), 64 KB; the log table 16 KB.  A TabView is a thread's pair of base pointers (copy l & 7 selected).
+struct TabView {
+    const double2* lg;
+    const double2* tr;
+    static constexpr int kTrigBits = 9;
+    static constexpr int kCopies = 8;
+    static constexpr int kBytes = (128 + 512) * 8 * (int)sizeof(double2);
+    __device__ __forceinline__ double2 log_entry(int i) const { return lg[i * kCopies]; }
+    __device__ __forceinline__ double2 trig_entry(unsigned j) const { return tr[j * kCopies]; }
+};
+
+// stage the replicated tables into `smem` (kBytes, 16-byte aligned) and return this thread's view.  Two phases: the 640
+// distinct entries are read once from global memory (coalesced 16-byte loads) into `scratch` (>= 10 KB of shared memory the
+// caller does not need yet), then every thread writes replicated entries from there (a shared-memory broadcast read, a
+// conflict-free consecutive write).  Ends with a block barrier; `scratch` is free again afterwards.
+__device__ __forceinline__ TabView load_tables_replicated(void* smem, void* scratch)
+{
+    double2* lg = reinterpret_cast<double2*>(smem);
+    double2* tr = lg + 128 * TabView::kCopies;
+    double2* tmp = reinterpret_cast<double2*>(scratch);
+    for (int i = threadIdx.x; i < 128 + 512; i += blockDim.x)
+        tmp[i] = i < 128 ? *reinterpret_cast<const double2*>(kLogTab[i])
+                         : *reinterpret_cast<const double2*>(kTrigTab[2 * (i - 128)]);  // every second angle of the 1024-entry table
+    __syncthreads();
+    for (int i = threadIdx.x; i < (128 + 512) * TabView::kCopies; i += blockDim.x) lg[i] = tmp[i / TabView::kCopies];
+    __syncthreads();
+    const int c = threadIdx.x & (TabView::kCopies - 1);
+    return TabView{lg + c, tr + c};
+}
 
 __device__ __forceinline__ void load_tables(Tables& T)
 {
@@ -179,15 +218,23 @@ static __constant__ double kL2[12] = {
     2.373867385353981485e-13,         // 10 2 pi / 1024 - [9]
     0.0};
 
+// per trig-table size (index = kTrigBits - 9): offset of sincos2pi_u32_tab, N / (2 pi), 2 pi / N (first 33 bits, rest, rounded)
+static __constant__ double kTrigC[2][5] = {
+    {-1.840776872316865512303721e-02, 81.48733086305041191366849, 0x1.921fb54400000p-7, 4.747734770707962695e-13,
+     0.0122718463030851298377447},
+    {-9.203883995854807744728685e-03, 162.974661726100823827337, 0x1.921fb54400000p-8, 2.373867385353981347e-13,
+     0.00613592315154256491887235}};
+
 // -2 log(x) for a positive NORMAL double.  x = 2^k z with z in [0.6855, 1.3711); the interval of z (128 of them,
 // centred on c_i, so that z = 1 is a centre and |r| <= 1/256) gives r = z / c_i - 1 with one rounding.
-__device__ __forceinline__ double neg2log_tab(const Tables& T, double x)
+template <class TAB>
+__device__ __forceinline__ double neg2log_tab(const TAB& T, double x)
 {
     const int hi = __double2hiint(x);
     const int tmp = hi + 0x1000 - 0x3fe60000;
     const int k = tmp >> 20;
     const double z = __hiloint2double(hi - (tmp & (int)0xfff00000), __double2loint(x));
-    const double2 e = T.lg[(tmp >> 13) & 127];
+    const double2 e = T.log_entry((tmp >> 13) & 127);
     const double r = fma(z, e.x, -1.0);
     const double w = fma((double)k, kL2[0], e.y);
     double q = fma(r, kL2[1], kL2[2]);
@@ -206,44 +253,65 @@ __device__ __forceinline__ void sincos_tiny(double d, double& sd, double& cm)
     cm = d2 * fma(d2, kLit[2], -0.5);
 }
 
-// sin and cos of 2 pi (r + 1/2) / 2^32 for a 32-bit word r: the nearest table angle 2 pi j / 1024 comes from the
-// top 10 bits of r + 2^21, the remainder |d| <= pi / 1024 from the low 22 bits
-__device__ __forceinline__ void sincos2pi_u32_tab(const Tables& T, unsigned r, double& s, double& c)
+// sin and cos of 2 pi (r + 1/2) / 2^32 for a 32-bit word r: the nearest table angle 2 pi j / N comes from the
+// top bits of r + 2^(31 - B), the remainder |d| <= pi / N from the low 32 - B bits (N = 2^B table entries)
+template <class TAB>
+__device__ __forceinline__ void sincos2pi_u32_tab(const TAB& T, unsigned r, double& s, double& c)
 {
-    const unsigned rr = r + 0x200000u;  // wraps with the angle
-    const double2 e = T.tr[rr >> 22];
-    const unsigned lowbits = rr & 0x3fffffu;
-    const double X = __hiloint2double((int)(0x41500000u | (lowbits >> 2)), (int)(lowbits << 30));  // 2^22 + low bits
+    constexpr int B = TAB::kTrigBits, E = 32 - B;
+    const unsigned rr = r + (1u << (E - 1));  // wraps with the angle
+    const double2 e = T.trig_entry(rr >> E);
+    const unsigned lowbits = rr & ((1u << E) - 1u);
+    const double X = __hiloint2double((int)(((1023u + E) << 20) | (lowbits >> (E - 20))), (int)(lowbits << (52 - E)));  // 2^E + low bits
     double sd, cm;
-    sincos_tiny(fma(X, kL2[6], kL2[7]), sd, cm);
+    sincos_tiny(fma(X, kL2[6], kTrigC[B - 9][0]), sd, cm);
     s = fma(e.x, cm, fma(e.y, sd, e.x));
     c = fma(e.y, cm, fma(-e.x, sd, e.y));
 }
 
-// sin(x) for |x| < ~1e5 from the same table: n = round(x 1024 / 2 pi), two-term Cody-Waite remainder
-__device__ __forceinline__ double sin_tab(const Tables& T, double x)
+// sin(x) for |x| < ~1e5 from the same table: n = round(x N / 2 pi), two-term Cody-Waite remainder
+template <class TAB>
+__device__ __forceinline__ double sin_tab(const TAB& T, double x)
 {
-    const double t0 = fma(x, kL2[8], kMisc[7]);
-    const double2 e = T.tr[__double2loint(t0) & 1023];
+    constexpr int B = TAB::kTrigBits;
+    const double t0 = fma(x, kTrigC[B - 9][1], kMisc[7]);
+    const double2 e = T.trig_entry((unsigned)__double2loint(t0) & ((1u << B) - 1u));
     const double nd = t0 - kMisc[7];
-    double d = fma(-nd, kL2[9], x);
-    d = fma(-nd, kL2[10], d);
+    double d = fma(-nd, kTrigC[B - 9][2], x);
+    d = fma(-nd, kTrigC[B - 9][3], d);
     double sd, cm;
     sincos_tiny(d, sd, cm);
     return fma(e.x, cm, fma(e.y, sd, e.x));
 }
 
 // cos(x) likewise
-__device__ __forceinline__ double cos_tab(const Tables& T, double x)
+template <class TAB>
+__device__ __forceinline__ double cos_tab(const TAB& T, double x)
 {
-    const double t0 = fma(x, kL2[8], kMisc[7]);
-    const double2 e = T.tr[__double2loint(t0) & 1023];
+    constexpr int B = TAB::kTrigBits;
+    const double t0 = fma(x, kTrigC[B - 9][1], kMisc[7]);
+    const double2 e = T.trig_entry((unsigned)__double2loint(t0) & ((1u << B) - 1u));
     const double nd = t0 - kMisc[7];
-    double d = fma(-nd, kL2[9], x);
-    d = fma(-nd, kL2[10], d);
+    double d = fma(-nd, kTrigC[B - 9][2], x);
+    d = fma(-nd, kTrigC[B - 9][3], d);
     double sd, cm;
     sincos_tiny(d, sd, cm);
     return fma(e.y, cm, fma(-e.x, sd, e.y));
+}
+
+// sin(x) for |x| < 32 with ONE Cody-Waite term, the full-precision 2 pi / N: its representation error (1.1e-16 relative) times
+// n 2 pi / N ~ |x| stays below 4e-15, a few ulp of the argument x itself (the double well evaluates sin(5 x + 5), whose
+// argument already carries that rounding).  Saves one fp64 instruction per force evaluation.
+template <class TAB>
+__device__ __forceinline__ double sin_tab1(const TAB& T, double x)
+{
+    constexpr int B = TAB::kTrigBits;
+    const double t0 = fma(x, kTrigC[B - 9][1], kMisc[7]);
+    const double2 e = T.trig_entry((unsigned)__double2loint(t0) & ((1u << B) - 1u));
+    const double d = fma(kMisc[7] - t0, kTrigC[B - 9][4], x);
+    double sd, cm;
+    sincos_tiny(d, sd, cm);
+    return fma(e.x, cm, fma(e.y, sd, e.x));
 }
 
 // sqrt of a positive normal number in five instructions: with e = 1 - x y^2 for the hardware seed y (|e| < 2^-22),

@@ -76,3 +76,7 @@ int lsi_particles_run_protocol(const lsi_system* sys, const lsi_program* prog, c
 void lsi_particles_free(lsi_particles* p);
 // reduce.cu
 int lsi_finalize_moments(const double* partials, int n_partials, double* moments, void* stream);
+// n (<= 8) independent finalizations in one launch: partials[i] ([n_partials][8]) -> moments[i] ([8])
+int lsi_finalize_moments_batch(const double* const* partials, int n_partials, double* const* moments, int n, void* stream);
+int lsi_toy_run_protocol_batch(const lsi_system* sys, const lsi_program* const* progs, int n_progs, const lsi_protocol_args* args,
+                               void* stream);

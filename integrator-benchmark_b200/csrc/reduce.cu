@@ -67,6 +67,25 @@ __global__ void __launch_bounds__(kThreads) finalize_moments_kernel(const double
     }
 }
 
+struct FinalizeBatch {
+    const double* partials[8];
+    double* moments[8];
+};
+
+// block b folds partials[b] exactly as finalize_moments_kernel does (same order, same result)
+__global__ void __launch_bounds__(kThreads) finalize_moments_batch_kernel(const __grid_constant__ FinalizeBatch F, int n)
+{
+    __shared__ double sh[kThreads / 32];
+    const double* __restrict__ partials = F.partials[blockIdx.x];
+    double* __restrict__ moments = F.moments[blockIdx.x];
+    for (int j = 0; j < 8; ++j) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n; i += kThreads) s += partials[(int64_t)i * 8 + j];
+        s = block_sum(s, sh);
+        if (threadIdx.x == 0) moments[j] = (j < 7) ? s : 0.0;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) moments_partials_kernel(const double* __restrict__ wF,
                                                                     const double* __restrict__ wR, int64_t n,
                                                                     double* __restrict__ partials)
@@ -165,6 +184,17 @@ __global__ void __launch_bounds__(kThreads) bootstrap_kernel(const double* __res
 int lsi_finalize_moments(const double* partials, int n_partials, double* moments, void* stream)
 {
     finalize_moments_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(partials, n_partials, moments);
+    LSI_CUDA_CHECK(cudaGetLastError());
+    return LSI_OK;
+}
+
+int lsi_finalize_moments_batch(const double* const* partials, int n_partials, double* const* moments, int n, void* stream)
+{
+    if (n <= 0) return LSI_OK;
+    if (n > 8) return lsi_set_error(LSI_ERR_ARG, "lsi_finalize_moments_batch: at most 8 at a time");
+    FinalizeBatch F;
+    for (int i = 0; i < 8; ++i) { F.partials[i] = partials[i < n ? i : 0]; F.moments[i] = moments[i < n ? i : 0]; }
+    finalize_moments_batch_kernel<<<n, kThreads, 0, (cudaStream_t)stream>>>(F, n_partials);
     LSI_CUDA_CHECK(cudaGetLastError());
     return LSI_OK;
 }

@@ -90,7 +90,8 @@ __device__ __forceinline__ void box_muller_lean(uint32_t ra, uint32_t rb, double
 
 // the same pair with the table-driven -2 log and sincos (tables staged in shared memory by the caller)
 // and the five-instruction sqrt; `scale` multiplies both normals
-__device__ __forceinline__ void box_muller_tab(const fm::Tables& T, uint32_t ra, uint32_t rb, double scale, double& n0, double& n1)
+template <class TAB>
+__device__ __forceinline__ void box_muller_tab(const TAB& T, uint32_t ra, uint32_t rb, double scale, double& n0, double& n1)
 {
     const double rad = fm::sqrt_pos_scaled(fm::neg2log_tab(T, fm::uniform_from_u32(ra, false)), scale);
     double s, c;
@@ -123,10 +124,20 @@ __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& n0, 
     n1 = rad * s;
 }
 
+// particle systems: uniform index into the equilibrium cache from lane 0 of the replica's own TAG_X0 block
 __device__ __forceinline__ int64_t cache_index(uint64_t seed, uint64_t replica, int64_t n)
 {
     const Philox4 r = philox_block(seed, replica, 0u, LSI_TAG_X0, 0u);
     return (int64_t)(((uint64_t)r.x * (uint64_t)n) >> 32);
+}
+
+// scalar (toy) systems: ONE start block per replica, (replica, draw 0, TAG_V0, unit 0), feeds everything a two-leg
+// protocol draws outside its O substeps: words 0, 1 -> the Box-Muller pair (start velocity, midpoint velocity),
+// word 2 -> the cache index (w2 * n) >> 32, word 3 spare.  Start velocities of legs >= 2 (rare) are normal leg - 2
+// of the stream that begins at draw 1: block 1 + ((leg - 2) >> 2), lane (leg - 2) & 3.
+__device__ __forceinline__ int64_t index_from_word(uint32_t w, int64_t n)
+{
+    return (int64_t)(((uint64_t)w * (uint64_t)n) >> 32);
 }
 
 }  // namespace lsi

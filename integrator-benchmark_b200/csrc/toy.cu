@@ -89,8 +89,8 @@ __device__ __forceinline__ void store_trace(const ToyParams& P, int leg, int64_t
     }
 }
 
-template <int POT>
-__device__ __forceinline__ double potential(const fm::Tables& T, double x, double p0)
+template <int POT, class TAB>
+__device__ __forceinline__ double potential(const TAB& T, double x, double p0)
 {
     if (POT == LSI_POT_QUARTIC) {
         const double x2 = x * x;
@@ -111,8 +111,8 @@ __device__ __forceinline__ double potential(const fm::Tables& T, double x, doubl
     }
 }
 
-template <int POT>
-__device__ __forceinline__ double force(const fm::Tables& T, double x, double p0)
+template <int POT, class TAB>
+__device__ __forceinline__ double force(const TAB& T, double x, double p0)
 {
     if (POT == LSI_POT_QUARTIC) {
         return -4.0 * x * x * x;
@@ -131,8 +131,8 @@ __device__ __forceinline__ double force(const fm::Tables& T, double x, double p0
 }
 
 // four normals of one block of a replica's scalar stream, each multiplied by `scale`
-template <bool NOISE32>
-__device__ __forceinline__ void normal_block(const fm::Tables& T, const lsi::PhiloxKeys& seed, uint64_t replica, uint32_t draw, uint32_t tag,
+template <bool NOISE32, class TAB>
+__device__ __forceinline__ void normal_block(const TAB& T, const lsi::PhiloxKeys& seed, uint64_t replica, uint32_t draw, uint32_t tag,
                                              double scale, double& n0, double& n1, double& n2, double& n3)
 {
     const lsi::Philox4 r = lsi::philox_block(seed, replica, draw, tag, 0u);
@@ -147,15 +147,27 @@ __device__ __forceinline__ void normal_block(const fm::Tables& T, const lsi::Phi
     }
 }
 
-// normal number k of a (replica, tag) scalar stream: block k >> 2, lane k & 3 (always fp64:
-// start and midpoint velocities are drawn once per leg)
-__device__ __forceinline__ double scalar_normal(const fm::Tables& T, const lsi::PhiloxKeys& seed, uint64_t replica, uint32_t tag, uint32_t k)
+// start-of-leg velocity normal of leg >= 2 (legs 0 and 1 share the pair of the replica's start block, see rng.cuh):
+// normal leg - 2 of the TAG_V0 stream that begins at draw 1
+template <class TAB>
+__device__ __forceinline__ double later_leg_normal(const TAB& T, const lsi::PhiloxKeys& seed, uint64_t replica, uint32_t leg)
 {
-    const lsi::Philox4 q = lsi::philox_block(seed, replica, k >> 2, tag, 0u);
+    const uint32_t k = leg - 2u;
+    const lsi::Philox4 q = lsi::philox_block(seed, replica, 1u + (k >> 2), LSI_TAG_V0, 0u);
     double a, b;
     if ((k & 2u) == 0u) LSI_BM64(T, q.x, q.y, 1.0, a, b);
     else LSI_BM64(T, q.z, q.w, 1.0, a, b);
     return (k & 1u) ? b : a;
+}
+
+// the replica's start block: start / midpoint velocity normals and the equilibrium-cache index
+template <class TAB>
+__device__ __forceinline__ void start_block(const TAB& T, const lsi::PhiloxKeys& seed, uint64_t replica, int64_t n_cache,
+                                            double& n_start, double& n_mid, int64_t& index)
+{
+    const lsi::Philox4 q = lsi::philox_block(seed, replica, 0u, LSI_TAG_V0, 0u);
+    LSI_BM64(T, q.x, q.y, 1.0, n_start, n_mid);
+    index = lsi::index_from_word(q.z, n_cache);
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -308,14 +320,10 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
         double wF = 0.0, wR = 0.0;
         bool finite = true;
         const uint64_t rid = P.replica0 + (uint64_t)r;
-        double x = P.x0 ? P.x0[r] : P.x_cache[lsi::cache_index(P.seed, rid, P.n_cache)];
-        // start-of-leg velocities of a scalar system: normal number `leg` of the replica's TAG_V0 stream, so the start
-        // and the midpoint velocity of a two-leg protocol are the two halves of ONE Box-Muller pair
         double n_start, n_mid;
-        {
-            const lsi::Philox4 q = lsi::philox_block(P.keys, rid, 0u, LSI_TAG_V0, 0u);
-            LSI_BM64(FT, q.x, q.y, 1.0, n_start, n_mid);
-        }
+        int64_t idx0;
+        start_block(FT, P.keys, rid, P.n_cache, n_start, n_mid, idx0);
+        double x = P.x0 ? P.x0[r] : P.x_cache[idx0];
         double v = P.v0 ? P.v0[r] : P.sigma * n_start;
         double heat = 0.0;
         const double half_m = 0.5 * P.mass;
@@ -324,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
 
         for (int leg = 0; leg < P.n_legs; ++leg) {
             if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
-                v = P.sigma * (leg == 1 ? n_mid : scalar_normal(FT, P.keys, rid, LSI_TAG_V0, (uint32_t)leg));
+                v = P.sigma * (leg == 1 ? n_mid : later_leg_normal(FT, P.keys, rid, (uint32_t)leg));
             const double E0 = pe + half_m * v * v;
             const double Q0 = heat;
             const uint32_t leg_base = (uint32_t)leg << 26;
@@ -423,6 +431,295 @@ __global__ void __launch_bounds__(kThreads, LSI_TOY_MINB) toy_fused_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------
+// K1 (production path, no traces): the same protocol with
+//   * conflict-free replicated tables in dynamic shared memory (fm::TabView: 80 KB per CTA);
+//   * forces kept as g with F = c g (double well: g = sin(5 x + 5) - 0.6 x^5, c = 10; quartic: g = x^3, c = -4), the
+//     constant folded into the kick length;
+//   * the heat of a leg accumulated as h = sum over O substeps of (v_after^2 - v_before^2), multiplied by m / 2 once;
+//     two O substeps with nothing between them (the end of one step and the start of the next in "O V R V O", the
+//     "O O" of the reference's baoab closure) share their middle term, which cancels and is never computed;
+//   * the last noise block of a leg generating only the Box-Muller pair the remaining steps consume;
+//   * ILP replicas per thread, their chains interleaved by the compiler.
+// Arithmetic differs from the plain formulas only in rounding (1e-16 relative per operation).
+#ifndef LSI_TOY2_THREADS
+#define LSI_TOY2_THREADS 1024
+#endif
+#ifndef LSI_TOY2_MINB
+#define LSI_TOY2_MINB 1
+#endif
+#ifndef LSI_TOY2_ILP
+#define LSI_TOY2_ILP 1
+#endif
+#ifndef LSI_TOY2_UNROLL
+#define LSI_TOY2_UNROLL 2
+#endif
+constexpr int kF2Threads = LSI_TOY2_THREADS;
+constexpr int kF2Unroll = LSI_TOY2_UNROLL;
+constexpr size_t kF2Smem = (size_t)fm::TabView::kBytes + 7u * kF2Threads * sizeof(double);
+static_assert(7u * kF2Threads * sizeof(double) >= (128 + 512) * sizeof(double2), "the accumulator region doubles as the table staging scratch");
+
+template <int POT>
+__device__ __forceinline__ double force_scale(double p0)
+{
+    return POT == LSI_POT_QUARTIC ? -4.0 : (POT == LSI_POT_DOUBLE_WELL ? 10.0 : -p0);
+}
+
+template <int POT, class TAB>
+__device__ __forceinline__ double force_g(const TAB& T, double x)
+{
+    if (POT == LSI_POT_QUARTIC) {
+        return x * x * x;
+    } else if (POT == LSI_POT_DOUBLE_WELL) {
+        const double x2 = x * x;
+        return fma(-0.6, x2 * x2 * x, fm::sin_tab1(T, fma(5.0, x, 5.0)));
+    } else {
+        return x;
+    }
+}
+
+constexpr bool code_is_O(uint32_t code, int nops, int i) { return code_op(code, ((i % nops) + nops) % nops) == LSI_OP_O; }
+
+// two normals (first pair) or four of one O-stream block, each multiplied by `scale`
+template <bool NOISE32, class TAB>
+__device__ __forceinline__ void normal_block_part(const TAB& T, const lsi::PhiloxKeys& seed, uint64_t replica, uint32_t draw,
+                                                  double scale, bool second_pair, double (&n)[4])
+{
+    const lsi::Philox4 r = lsi::philox_block(seed, replica, draw, LSI_TAG_O, 0u);
+    if (NOISE32) {
+        float a, b;
+        lsi::box_muller(r.x, r.y, a, b);
+        n[0] = scale * (double)a; n[1] = scale * (double)b;
+        if (second_pair) {
+            lsi::box_muller(r.z, r.w, a, b);
+            n[2] = scale * (double)a; n[3] = scale * (double)b;
+        }
+    } else {
+        LSI_BM64(T, r.x, r.y, scale, n[0], n[1]);
+        if (second_pair) LSI_BM64(T, r.z, r.w, scale, n[2], n[3]);
+    }
+}
+
+template <int POT, uint32_t CODE, int NOPS, int ILP>
+struct FusedStep2 {
+    // one application of the splitting to ILP replicas; xi[j][] are replica j's normals of this step in substep order,
+    // already multiplied by b sigma; hVs = V length / m * force_scale
+    template <int NO>
+    static __device__ __forceinline__ void run(const fm::TabView& FT, double (&x)[ILP], double (&v)[ILP], double (&g)[ILP],
+                                               double (&h)[ILP], double hR, double hVs, double oa, const double (&xi)[ILP][NO])
+    {
+        bool valid = code_entry_valid(CODE, NOPS);  // folded at compile time after unrolling
+        int o = 0;
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i) {
+            constexpr uint32_t code = CODE;
+            const int kind = (int)((code >> (2 * i)) & 3u);
+            if (kind == LSI_OP_R) {
+#pragma unroll
+                for (int j = 0; j < ILP; ++j) x[j] = fma(hR, v[j], x[j]);
+                valid = false;
+            } else if (kind == LSI_OP_V) {
+                if (!valid) {
+#pragma unroll
+                    for (int j = 0; j < ILP; ++j) g[j] = force_g<POT>(FT, x[j]);
+                }
+                valid = true;
+#pragma unroll
+                for (int j = 0; j < ILP; ++j) v[j] = fma(hVs, g[j], v[j]);
+            } else {
+                const bool sub = !code_is_O(CODE, NOPS, i - 1), add = !code_is_O(CODE, NOPS, i + 1);
+#pragma unroll
+                for (int j = 0; j < ILP; ++j) {
+                    if (sub) h[j] = fma(-v[j], v[j], h[j]);
+                    v[j] = fma(oa, v[j], xi[j][o]);
+                    if (add) h[j] = fma(v[j], v[j], h[j]);
+                }
+                ++o;
+            }
+        }
+    }
+};
+
+// the protocol of ONE program over this CTA's chunks; `acc` is the thread's column of the [7][kF2Threads] moment accumulator
+template <int POT, uint32_t CODE, int NOPS, bool NOISE32, int ILP>
+__device__ __forceinline__ void fused2_run(const fm::TabView& FT, double* acc, const ToyParams& P)
+{
+    constexpr int NO = code_count(CODE, NOPS, LSI_OP_O);  // normals per step: 1 or 2 for every instantiated string
+    static_assert(NO == 1 || NO == 2, "the fused kernel expects one or two O substeps per step");
+    constexpr int U = 4 / NO;                              // steps fed by one Philox block
+    constexpr bool CYC_OO = code_is_O(CODE, NOPS, 0) && code_is_O(CODE, NOPS, NOPS - 1);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) acc[j * kF2Threads] = 0.0;
+
+    const double half_m = 0.5 * P.mass;
+    const double hVs = P.hV * force_scale<POT>(P.p0);
+    const int n_blk = (P.n_steps + U - 1) / U;
+    const int rem = P.n_steps - (n_blk - 1) * U;       // steps fed by the last block (1..U)
+    const bool last_needs_second = rem * NO > 2;
+    // persistent CTAs: CTA b takes the (ILP x kF2Threads)-replica chunks b, b + gridDim.x, ...
+    const int64_t per = (int64_t)kF2Threads * ILP;
+    const int64_t n_chunks = (P.n + per - 1) / per;
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        int64_t r[ILP];
+        bool act[ILP];
+        uint64_t rid[ILP];
+        double x[ILP], v[ILP], g[ILP], h[ILP], pe[ILP], n_mid[ILP], wF[ILP], wR[ILP];
+        bool finite[ILP];
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            r[j] = chunk * per + (int64_t)j * kF2Threads + threadIdx.x;
+            act[j] = r[j] < P.n;
+            if (!act[j]) r[j] = P.n - 1;  // computed like a live replica, never stored
+            rid[j] = P.replica0 + (uint64_t)r[j];
+            double n_start;
+            int64_t idx0;
+            start_block(FT, P.keys, rid[j], P.n_cache, n_start, n_mid[j], idx0);
+            x[j] = P.x0 ? P.x0[r[j]] : P.x_cache[idx0];
+            v[j] = P.v0 ? P.v0[r[j]] : P.sigma * n_start;
+            wF[j] = wR[j] = 0.0;
+            finite[j] = true;
+        }
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            g[j] = code_entry_valid(CODE, NOPS) ? force_g<POT>(FT, x[j]) : 0.0;
+            pe[j] = potential<POT>(FT, x[j], P.p0);  // x does not move between the legs: one evaluation per leg boundary
+        }
+
+        for (int leg = 0; leg < P.n_legs; ++leg) {
+            double E0[ILP];
+#pragma unroll
+            for (int j = 0; j < ILP; ++j) {
+                if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
+                    v[j] = P.sigma * (leg == 1 ? n_mid[j] : later_leg_normal(FT, P.keys, rid[j], (uint32_t)leg));
+                const double v2 = v[j] * v[j];
+                E0[j] = fma(half_m, v2, pe[j]);
+                h[j] = CYC_OO ? -v2 : 0.0;  // the first O of the leg has no O before it
+            }
+            const uint32_t leg_base = (uint32_t)leg << 26;
+            if (n_blk > 0) {
+                double cur[ILP][4];
+#pragma unroll
+                for (int j = 0; j < ILP; ++j)
+                    normal_block_part<NOISE32>(FT, P.keys, rid[j], leg_base, P.oc, n_blk > 1 || last_needs_second, cur[j]);
+                auto steps = [&](int count) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (u < count) {
+                            double xi[ILP][NO];
+#pragma unroll
+                            for (int j = 0; j < ILP; ++j)
+#pragma unroll
+                                for (int o = 0; o < NO; ++o) xi[j][o] = cur[j][u * NO + o];
+                            FusedStep2<POT, CODE, NOPS, ILP>::run(FT, x, v, g, h, P.hR, hVs, P.oa, xi);
+                        }
+                    }
+                };
+                // the block of the NEXT U steps is generated in the same basic block as the current U steps: the noise
+                // (integer Philox rounds, then Box-Muller) does not depend on x and v and interleaves with the dynamics chain
+#pragma unroll kF2Unroll
+                for (int blk = 1; blk < n_blk - 1; ++blk) {
+                    double nxt[ILP][4];
+#pragma unroll
+                    for (int j = 0; j < ILP; ++j) normal_block_part<NOISE32>(FT, P.keys, rid[j], leg_base | (uint32_t)blk, P.oc, true, nxt[j]);
+                    steps(U);
+#pragma unroll
+                    for (int j = 0; j < ILP; ++j)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) cur[j][k] = nxt[j][k];
+                }
+                if (n_blk > 1) {
+                    double nxt[ILP][4];
+#pragma unroll
+                    for (int j = 0; j < ILP; ++j)
+                        normal_block_part<NOISE32>(FT, P.keys, rid[j], leg_base | (uint32_t)(n_blk - 1), P.oc, last_needs_second, nxt[j]);
+                    steps(U);
+#pragma unroll
+                    for (int j = 0; j < ILP; ++j)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) cur[j][k] = nxt[j][k];
+                }
+                steps(rem);
+            }
+#pragma unroll
+            for (int j = 0; j < ILP; ++j) {
+                pe[j] = potential<POT>(FT, x[j], P.p0);
+                const double v2 = v[j] * v[j];
+                const double E1 = fma(half_m, v2, pe[j]);
+                const double heat = half_m * (CYC_OO ? h[j] + v2 : h[j]);  // the last O of the leg has no O after it
+                const double w = ((E1 - E0[j]) - heat) * P.inv_kT;
+                if (act[j]) {
+                    P.W[(int64_t)leg * P.n + r[j]] = w;
+                    if (P.heat) P.heat[(int64_t)leg * P.n + r[j]] = heat;
+                }
+                if (leg == 0) wF[j] = w;
+                if (leg == 1) wR[j] = w;
+                finite[j] = finite[j] && isfinite(w);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            if (!act[j]) continue;
+            if (P.x_final) P.x_final[r[j]] = x[j];
+            if (P.v_final) P.v_final[r[j]] = v[j];
+            if (P.partials) {
+                if (finite[j]) {
+                    acc[0] += 1.0; acc[kF2Threads] += wF[j]; acc[2 * kF2Threads] += wR[j];
+                    acc[3 * kF2Threads] += wF[j] * wF[j]; acc[4 * kF2Threads] += wR[j] * wR[j]; acc[5 * kF2Threads] += wF[j] * wR[j];
+                } else {
+                    acc[6 * kF2Threads] += 1.0;
+                }
+            }
+        }
+    }
+    if (P.partials) {
+        __shared__ double sh[kF2Threads / 32][7];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        __syncthreads();  // a previous program's flush (batch kernel) has been read
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const double s = warp_sum(acc[j * kF2Threads]);
+            if (lane == 0) sh[warp][j] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            double s = 0.0;
+            if (threadIdx.x < 7)
+                for (int w = 0; w < kF2Threads / 32; ++w) s += sh[w][threadIdx.x];
+            P.partials[(int64_t)blockIdx.x * 8 + threadIdx.x] = s;
+        }
+    }
+}
+
+template <int POT, uint32_t CODE, int NOPS, bool NOISE32, int ILP>
+__global__ void __launch_bounds__(kF2Threads, LSI_TOY2_MINB) toy_fused2_kernel(const __grid_constant__ ToyParams P)
+{
+    extern __shared__ __align__(16) unsigned char toy2_smem[];
+    // the moment accumulators' region doubles as the staging scratch of the tables
+    const fm::TabView FT = fm::load_tables_replicated(toy2_smem, toy2_smem + fm::TabView::kBytes);
+    double* acc = reinterpret_cast<double*>(toy2_smem + fm::TabView::kBytes) + threadIdx.x;  // column of [7][kF2Threads]
+    fused2_run<POT, CODE, NOPS, NOISE32, ILP>(FT, acc, P);
+}
+
+// Several programs of one FAMILY (a compile-time list of splitting strings) over the same ensemble in ONE launch: slot i
+// of the family runs when bit i of `enabled` is set, with its own lengths, coefficients and output pointers in P[i].
+// Tables are staged once, the CTAs never drain between programs, and a CTA that finishes a program early starts the next.
+constexpr int kBatchMax = 6;
+struct ToyBatchParams {
+    unsigned enabled;
+    ToyParams P[kBatchMax];
+};
+
+template <int POT, bool NOISE32, int ILP, int NOPS, uint32_t... CODES>
+__global__ void __launch_bounds__(kF2Threads, LSI_TOY2_MINB) toy_fused2_batch_kernel(const __grid_constant__ ToyBatchParams B)
+{
+    extern __shared__ __align__(16) unsigned char toy2_smem[];
+    const fm::TabView FT = fm::load_tables_replicated(toy2_smem, toy2_smem + fm::TabView::kBytes);
+    double* acc = reinterpret_cast<double*>(toy2_smem + fm::TabView::kBytes) + threadIdx.x;
+    int slot = 0;
+    // a fold over the family: every body is inlined with its slot's parameters at constant offsets of the parameter bank
+    ((((B.enabled >> slot) & 1u) ? fused2_run<POT, CODES, NOPS, NOISE32, ILP>(FT, acc, B.P[slot]) : (void)0, ++slot), ...);
+}
+
+// ------------------------------------------------------------------------------------------
 // interpreter
 template <bool EXT>
 struct ProgRead {
@@ -447,15 +744,18 @@ __global__ void __launch_bounds__(kThreads) toy_protocol_kernel(const __grid_con
 
     if (active) {
         const uint64_t rid = P.replica0 + (uint64_t)r;
-        double x = P.x0 ? P.x0[r] : P.x_cache[lsi::cache_index(P.seed, rid, P.n_cache)];
-        double v = P.v0 ? P.v0[r] : P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_V0, 0u);
+        double n_start, n_mid;
+        int64_t idx0;
+        start_block(FT, P.keys, rid, P.n_cache, n_start, n_mid, idx0);
+        double x = P.x0 ? P.x0[r] : P.x_cache[idx0];
+        double v = P.v0 ? P.v0[r] : P.sigma * n_start;
         double heat = 0.0;
         const double half_m = 0.5 * P.mass;
         const int64_t T = (int64_t)P.n_steps + 1;
 
         for (int leg = 0; leg < P.n_legs; ++leg) {
             if (leg > 0 && P.marginal == LSI_MARGINAL_CONFIGURATION)
-                v = P.sigma * scalar_normal(FT, P.keys, rid, LSI_TAG_V0, (uint32_t)leg);
+                v = P.sigma * (leg == 1 ? n_mid : later_leg_normal(FT, P.keys, rid, (uint32_t)leg));
             const double E0 = potential<POT>(FT, x, P.p0) + half_m * v * v;
             const double Q0 = heat;
             const uint32_t leg_base = (uint32_t)leg << 26;
@@ -589,26 +889,42 @@ constexpr int slen(const char* s)
     X("OVRRVO") X("VROORV") X("RVOOVR") X("RVO") X("ROV") X("VRRORRV") X("VRRRORRRV")
 
 // grid of the persistent fused kernels: one full wave (resident CTAs per SM x SMs), or fewer when there are fewer chunks
-unsigned fused_grid(int64_t n)
+unsigned persistent_grid(int64_t n, int64_t per_chunk, int ctas_per_sm)
 {
     int dev = 0, sms = 0;  // two attribute queries per launch (no cache: devices of one process may differ)
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
         sms = 148;
-    const int64_t wave = (int64_t)sms * LSI_TOY_MINB;
-    const int64_t chunks = (n + kThreads - 1) / kThreads;
+    const int64_t wave = (int64_t)sms * ctas_per_sm;
+    const int64_t chunks = (n + per_chunk - 1) / per_chunk;
     return (unsigned)(chunks < wave ? chunks : wave);
+}
+unsigned fused_grid(int64_t n) { return persistent_grid(n, kThreads, LSI_TOY_MINB); }
+unsigned fused2_grid(int64_t n) { return persistent_grid(n, (int64_t)kF2Threads * LSI_TOY2_ILP, LSI_TOY2_MINB); }
+
+template <class K>
+cudaError_t launch_fused2_kernel(K kernel, unsigned grid, const ToyParams& P, cudaStream_t st)
+{
+    // more than 48 KB of dynamic shared memory is an opt-in per function (and per device): cheap, so set on every launch
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2Smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kF2Threads, kF2Smem, st>>>(P);
+    return cudaGetLastError();
 }
 
 template <int POT, bool NOISE32>
-bool launch_fused2(uint32_t code, int nops, bool trace, const ToyParams& P, cudaStream_t st, cudaError_t* err)
+bool launch_fused2(uint32_t code, int nops, bool trace, const ToyParams& P, cudaStream_t st, cudaError_t* err, unsigned* grid_out)
 {
-    const unsigned grid = fused_grid(P.n);
     if (trace && NOISE32) return false;  // traced mixed-precision runs go through the interpreter
 #define X(S)                                                                                       \
     if (nops == slen(S) && code == pack(S)) {                                                      \
-        if (trace) toy_fused_kernel<POT, pack(S), slen(S), false, true><<<grid, kThreads, 0, st>>>(P);  \
-        else toy_fused_kernel<POT, pack(S), slen(S), NOISE32><<<grid, kThreads, 0, st>>>(P);       \
-        *err = cudaGetLastError();                                                                 \
+        if (trace) {                                                                               \
+            *grid_out = fused_grid(P.n);                                                           \
+            toy_fused_kernel<POT, pack(S), slen(S), false, true><<<*grid_out, kThreads, 0, st>>>(P);  \
+            *err = cudaGetLastError();                                                             \
+        } else {                                                                                   \
+            *grid_out = fused2_grid(P.n);                                                          \
+            *err = launch_fused2_kernel(toy_fused2_kernel<POT, pack(S), slen(S), NOISE32, LSI_TOY2_ILP>, *grid_out, P, st);  \
+        }                                                                                          \
         return true;                                                                               \
     }
     LSI_FUSED_STRINGS(X)
@@ -617,18 +933,18 @@ bool launch_fused2(uint32_t code, int nops, bool trace, const ToyParams& P, cuda
 }
 
 bool launch_fused(int pot, bool noise32, uint32_t code, int nops, bool trace, const ToyParams& P, cudaStream_t st,
-                  cudaError_t* err)
+                  cudaError_t* err, unsigned* grid_out)
 {
     switch (pot) {
     case LSI_POT_QUARTIC:
-        return noise32 ? launch_fused2<LSI_POT_QUARTIC, true>(code, nops, trace, P, st, err)
-                       : launch_fused2<LSI_POT_QUARTIC, false>(code, nops, trace, P, st, err);
+        return noise32 ? launch_fused2<LSI_POT_QUARTIC, true>(code, nops, trace, P, st, err, grid_out)
+                       : launch_fused2<LSI_POT_QUARTIC, false>(code, nops, trace, P, st, err, grid_out);
     case LSI_POT_DOUBLE_WELL:
-        return noise32 ? launch_fused2<LSI_POT_DOUBLE_WELL, true>(code, nops, trace, P, st, err)
-                       : launch_fused2<LSI_POT_DOUBLE_WELL, false>(code, nops, trace, P, st, err);
+        return noise32 ? launch_fused2<LSI_POT_DOUBLE_WELL, true>(code, nops, trace, P, st, err, grid_out)
+                       : launch_fused2<LSI_POT_DOUBLE_WELL, false>(code, nops, trace, P, st, err, grid_out);
     default:
-        return noise32 ? launch_fused2<LSI_POT_HARMONIC, true>(code, nops, trace, P, st, err)
-                       : launch_fused2<LSI_POT_HARMONIC, false>(code, nops, trace, P, st, err);
+        return noise32 ? launch_fused2<LSI_POT_HARMONIC, true>(code, nops, trace, P, st, err, grid_out)
+                       : launch_fused2<LSI_POT_HARMONIC, false>(code, nops, trace, P, st, err, grid_out);
     }
 }
 
@@ -664,10 +980,11 @@ LSI_EXPORT int lsi_sample_equilibrium_scalar(const lsi_system* sys, double kT, i
     return LSI_OK;
 }
 
-int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const lsi_protocol_args* a, void* stream)
+// validation + kernel parameters of one (system, program, args); `fusable`: every substep of a kind has the same length
+// (true for lsi_compile output) and the string is short enough for a compile-time code
+static int toy_prepare(const lsi_system* sys, const lsi_program* prog, const lsi_protocol_args* a, ToyParams& P, bool& fusable,
+                       uint32_t& code, int& n_ops_out)
 {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (a->n_replicas == 0) return LSI_OK;
     if (!a->W) return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol: W output is required");
     if (!a->x0 && !(a->x_cache && a->n_cache > 0))
         return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol: need x0 or a non-empty x_cache");
@@ -681,12 +998,11 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
             return lsi_set_error(LSI_ERR_UNSUPPORTED, "scalar systems have a single force group; got V%d", op.group);
 
     const int n_ops = (int)prog->ops.size();
+    n_ops_out = n_ops;
     const double sigma = sqrt(a->kT / sys->mass);
-    const bool noise32 = a->precision == LSI_PRECISION_MIXED;
     if ((int64_t)a->n_steps * (int64_t)(prog->n_O > 0 ? prog->n_O : 1) >= ((int64_t)1 << 28))
         return lsi_set_error(LSI_ERR_ARG, "n_steps * n_O exceeds the 2^28 draws a leg's noise stream holds");
 
-    ToyParams P;
     P.seed = a->seed; P.replica0 = a->replica0; P.n = a->n_replicas;
     P.keys = lsi::philox_round_keys(a->seed);
     P.n_steps = a->n_steps; P.n_legs = a->n_legs; P.marginal = a->marginal;
@@ -698,7 +1014,6 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
     P.trace_rm = (a->flags & LSI_FLAG_TRACE_REPLICA_MAJOR) ? 1 : ((a->flags & LSI_FLAG_TRACE_XV_PAIRS) ? 2 : 0);
     if (P.trace_rm && a->trace_v) return lsi_set_error(LSI_ERR_ARG, "these trace layouts keep (x, v) pairs in trace_x; trace_v must be NULL");
     P.partials = nullptr;
-    const int64_t grid = (a->n_replicas + kThreads - 1) / kThreads;
     if (a->moments) {
         if (a->n_legs != 2) return lsi_set_error(LSI_ERR_ARG, "moments need n_legs == 2");
         if (!a->workspace || a->workspace_bytes < lsi_protocol_workspace_bytes(a->n_replicas))
@@ -706,14 +1021,9 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
                                  (long long)lsi_protocol_workspace_bytes(a->n_replicas));
         P.partials = (double*)a->workspace;
     }
-    const bool direct = a->W_direct != nullptr;
-    const bool trace = a->trace_x || a->trace_v || a->trace_w;
-
-    // ---- fused path: every substep of a kind has the same length (true for lsi_compile output)
-    bool launched = false;
-    cudaError_t err = cudaSuccess;
-    if (!direct && n_ops <= 16) {
-        uint32_t code = 0;
+    fusable = false;
+    code = 0;
+    if (!a->W_direct && n_ops <= 16) {
         bool uniform = true;
         double fr[3] = {-1, -1, -1}, oa = 0, ob = 0;
         for (int i = 0; i < n_ops && uniform; ++i) {
@@ -730,9 +1040,130 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
             P.hR = prog->dt * (fr[LSI_OP_R] > 0 ? fr[LSI_OP_R] : 0.0);
             P.hV = prog->dt * (fr[LSI_OP_V] > 0 ? fr[LSI_OP_V] : 0.0) / sys->mass;
             P.oa = oa; P.oc = ob * sigma;
-            launched = launch_fused(sys->potential, noise32, code, n_ops, trace, P, st, &err);
+            fusable = true;
         }
     }
+    return LSI_OK;
+}
+
+// families of the batch kernel (toy_fused2_batch_kernel): slot order is the order of the strings
+#define LSI_FAMILY_FIVE(X) X("OVRVO") X("ORVRO") X("RVOVR") X("ROVOR") X("VRORV") X("VOROV")
+#define LSI_FAMILY_SIX(X) X("OVRRVO") X("VROORV") X("RVOOVR")
+
+static int family_slot(int family, uint32_t code, int nops)
+{
+    int slot = 0;
+#define X(S)                                                \
+    if (nops == slen(S) && code == pack(S)) return slot;   \
+    ++slot;
+    if (family == 0) { LSI_FAMILY_FIVE(X) } else { LSI_FAMILY_SIX(X) }
+#undef X
+    return -1;
+}
+
+template <int POT, bool NOISE32>
+static cudaError_t launch_batch2(int family, unsigned grid, const ToyBatchParams& B, cudaStream_t st)
+{
+#define X(S) , pack(S)
+    if (family == 0) {
+        auto k = toy_fused2_batch_kernel<POT, NOISE32, LSI_TOY2_ILP, 5 LSI_FAMILY_FIVE(X)>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2Smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, kF2Threads, kF2Smem, st>>>(B);
+    } else {
+        auto k = toy_fused2_batch_kernel<POT, NOISE32, LSI_TOY2_ILP, 6 LSI_FAMILY_SIX(X)>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2Smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, kF2Threads, kF2Smem, st>>>(B);
+    }
+#undef X
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_batch(int pot, bool noise32, int family, unsigned grid, const ToyBatchParams& B, cudaStream_t st)
+{
+    switch (pot) {
+    case LSI_POT_QUARTIC:
+        return noise32 ? launch_batch2<LSI_POT_QUARTIC, true>(family, grid, B, st) : launch_batch2<LSI_POT_QUARTIC, false>(family, grid, B, st);
+    case LSI_POT_DOUBLE_WELL:
+        return noise32 ? launch_batch2<LSI_POT_DOUBLE_WELL, true>(family, grid, B, st) : launch_batch2<LSI_POT_DOUBLE_WELL, false>(family, grid, B, st);
+    default:
+        return noise32 ? launch_batch2<LSI_POT_HARMONIC, true>(family, grid, B, st) : launch_batch2<LSI_POT_HARMONIC, false>(family, grid, B, st);
+    }
+}
+
+// lsi_run_protocol_batch for scalar systems: ONE launch when the programs are distinct members of one family and share
+// the ensemble (replicas, seed, start states, lengths, precision); otherwise one launch per program.  Same results either way.
+int lsi_toy_run_protocol_batch(const lsi_system* sys, const lsi_program* const* progs, int n_progs, const lsi_protocol_args* args,
+                               void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    bool one_launch = n_progs >= 2 && n_progs <= kBatchMax && args[0].n_replicas > 0;
+    ToyBatchParams B;
+    B.enabled = 0;
+    int family = -1;
+    const lsi_protocol_args& a0 = args[0];
+    for (int p = 0; p < n_progs && one_launch; ++p) {
+        const lsi_protocol_args& a = args[p];
+        ToyParams P;
+        bool fusable = false;
+        uint32_t code = 0;
+        int nops = 0;
+        const int rc = toy_prepare(sys, progs[p], &a, P, fusable, code, nops);
+        if (rc != LSI_OK) return rc;
+        const bool same = a.n_replicas == a0.n_replicas && a.n_steps == a0.n_steps && a.n_legs == a0.n_legs && a.marginal == a0.marginal &&
+                          a.precision == a0.precision && a.kT == a0.kT && a.seed == a0.seed && a.replica0 == a0.replica0 &&
+                          a.x_cache == a0.x_cache && a.n_cache == a0.n_cache && a.x0 == a0.x0 && a.v0 == a0.v0;
+        const bool plain = !a.trace_x && !a.trace_v && !a.trace_w && !a.W_direct;
+        if (!same || !plain || !fusable) { one_launch = false; break; }
+        int slot = family_slot(0, code, nops), fam = 0;
+        if (slot < 0) { slot = family_slot(1, code, nops); fam = 1; }
+        if (slot < 0 || (family >= 0 && fam != family) || ((B.enabled >> slot) & 1u)) { one_launch = false; break; }
+        family = fam;
+        B.enabled |= 1u << slot;
+        B.P[slot] = P;
+    }
+    if (!one_launch) {
+        for (int p = 0; p < n_progs; ++p) {
+            const int rc = lsi_toy_run_protocol(sys, progs[p], &args[p], stream);
+            if (rc != LSI_OK) return rc;
+        }
+        return LSI_OK;
+    }
+    const unsigned grid = fused2_grid(a0.n_replicas);
+    const cudaError_t err = launch_batch(sys->potential, a0.precision == LSI_PRECISION_MIXED, family, grid, B, st);
+    if (err != cudaSuccess) return lsi_set_error(LSI_ERR_CUDA, "toy batch kernel launch failed: %s", cudaGetErrorString(err));
+    const double* partials[kBatchMax];
+    double* moments[kBatchMax];
+    int n_fin = 0;
+    for (int p = 0; p < n_progs; ++p)
+        if (args[p].moments) { partials[n_fin] = (const double*)args[p].workspace; moments[n_fin] = args[p].moments; ++n_fin; }
+    if (n_fin > 0) return lsi_finalize_moments_batch(partials, (int)grid, moments, n_fin, stream);
+    return LSI_OK;
+}
+
+int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const lsi_protocol_args* a, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->n_replicas == 0) return LSI_OK;
+    ToyParams P;
+    bool fusable = false;
+    uint32_t code = 0;
+    int n_ops = 0;
+    {
+        const int rc = toy_prepare(sys, prog, a, P, fusable, code, n_ops);
+        if (rc != LSI_OK) return rc;
+    }
+    const double sigma = P.sigma;
+    const bool noise32 = a->precision == LSI_PRECISION_MIXED;
+    const int64_t grid = (a->n_replicas + kThreads - 1) / kThreads;
+    const bool direct = a->W_direct != nullptr;
+    const bool trace = a->trace_x || a->trace_v || a->trace_w;
+
+    bool launched = false;
+    unsigned fused_blocks = 0;
+    cudaError_t err = cudaSuccess;
+    if (fusable) launched = launch_fused(sys->potential, noise32, code, n_ops, trace, P, st, &err, &fused_blocks);
 
     void* ext = nullptr;
     if (!launched) {
@@ -774,6 +1205,6 @@ int lsi_toy_run_protocol(const lsi_system* sys, const lsi_program* prog, const l
         }
     }
     if (err != cudaSuccess) return lsi_set_error(LSI_ERR_CUDA, "toy kernel launch failed: %s", cudaGetErrorString(err));
-    if (a->moments) return lsi_finalize_moments(P.partials, launched ? (int)fused_grid(a->n_replicas) : (int)grid, a->moments, stream);
+    if (a->moments) return lsi_finalize_moments(P.partials, launched ? (int)fused_blocks : (int)grid, a->moments, stream);
     return LSI_OK;
 }

@@ -233,23 +233,12 @@ def sample_equilibrium_particles(system, x, kT, n_rounds, steps_per_hmc=10, extr
     return x_out, v_out, acc
 
 
-def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configuration", n_legs=2, seed=0,
-                 replica0=0, x_cache=None, x0=None, v0=None, precision="double", want_heat=False,
-                 want_direct=False, want_final=False, traces=False, want_moments=True, device=None, out=None,
-                 round_midpoint=False):
-    """One launch of the whole protocol for `n_replicas` replicas (lsi_run_protocol).
-
-    Tensors in/out are float64 CUDA tensors; outputs are leg-major: W[leg, replica],
-    traces [leg, step, replica(, dof)].  traces="replica_major" (scalar systems) gives the reference's own layout instead:
-    trace_w_rm [leg, replica, step] and trace_xv_rm [leg, replica, step, 2]; traces="pairs" keeps the coalesced step-major
-    order with (x, v) interleaved, trace_xv [leg, step, replica, 2] (a permuted view of it has the reference's shape).
-    Returns a dict of tensors (no host sync)."""
-    require_cuda()
+def _protocol_args(system, n_replicas, n_steps, kT, marginal, n_legs, seed, replica0, x_cache, x0, v0, precision, want_heat,
+                   want_direct, want_final, traces, want_moments, dev, out, round_midpoint, moments_out=None):
+    """lsi_protocol_args of one launch; output buffers live in (and are reused from) the dict `out`"""
     t = torch()
-    dev = t.device("cuda", t.cuda.current_device()) if device is None else t.device(device)
     n = int(n_replicas)
     dof = system.n_dof
-    out = {} if out is None else out
 
     def buf(name, *shape):
         cur = out.get(name)
@@ -258,14 +247,6 @@ def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configurati
             out[name] = cur
         return cur
 
-    def as_dev(a):
-        if a is None:
-            return None
-        if not t.is_tensor(a):
-            a = t.as_tensor(np.ascontiguousarray(a, dtype=np.float64))
-        return a.to(device=dev, dtype=t.float64).contiguous()
-
-    x_cache, x0, v0 = as_dev(x_cache), as_dev(x0), as_dev(v0)
     scalar = isinstance(system, ScalarSystem)
     state_shape = (n,) if scalar else (n, dof // 3, 3)
     a = _cabi.ProtocolArgs()
@@ -304,7 +285,11 @@ def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configurati
         a.trace_v = _ptr(buf("trace_v", *tshape))
         a.trace_w = _ptr(buf("trace_w", n_legs, n_steps + 1, n))
     if want_moments and n_legs == 2 and n > 0:
-        a.moments = _ptr(buf("moments", 8))
+        if moments_out is not None:
+            if not (moments_out.is_cuda and moments_out.dtype == t.float64 and moments_out.numel() == 8 and moments_out.is_contiguous()):
+                raise ValueError("moments_out must be a contiguous float64 CUDA tensor of 8 elements")
+            out["moments"] = moments_out
+        a.moments = _ptr(moments_out if moments_out is not None else buf("moments", 8))
         nbytes = lib.lsi_protocol_workspace_bytes(n)
         ws = out.get("_workspace")
         if ws is None or ws.numel() * 8 < nbytes or ws.device != dev:
@@ -312,9 +297,66 @@ def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configurati
             out["_workspace"] = ws
         a.workspace, a.workspace_bytes = _ptr(ws), ws.numel() * 8
     out["_keepalive"] = (x_cache, x0, v0)
+    return a
+
+
+def _as_dev(a, dev):
+    t = torch()
+    if a is None:
+        return None
+    if not t.is_tensor(a):
+        a = t.as_tensor(np.ascontiguousarray(a, dtype=np.float64))
+    return a.to(device=dev, dtype=t.float64).contiguous()
+
+
+def run_protocol(system, program, n_replicas, n_steps, kT, marginal="configuration", n_legs=2, seed=0,
+                 replica0=0, x_cache=None, x0=None, v0=None, precision="double", want_heat=False,
+                 want_direct=False, want_final=False, traces=False, want_moments=True, device=None, out=None,
+                 round_midpoint=False, moments_out=None):
+    """One launch of the whole protocol for `n_replicas` replicas (lsi_run_protocol).
+
+    Tensors in/out are float64 CUDA tensors; outputs are leg-major: W[leg, replica],
+    traces [leg, step, replica(, dof)].  traces="replica_major" (scalar systems) gives the reference's own layout instead:
+    trace_w_rm [leg, replica, step] and trace_xv_rm [leg, replica, step, 2]; traces="pairs" keeps the coalesced step-major
+    order with (x, v) interleaved, trace_xv [leg, step, replica, 2] (a permuted view of it has the reference's shape).
+    `moments_out` (8 float64 on the device) receives the moment vector instead of a buffer of `out`.
+    Returns a dict of tensors (no host sync)."""
+    require_cuda()
+    t = torch()
+    dev = t.device("cuda", t.cuda.current_device()) if device is None else t.device(device)
+    out = {} if out is None else out
+    x_cache, x0, v0 = _as_dev(x_cache, dev), _as_dev(x0, dev), _as_dev(v0, dev)
+    a = _protocol_args(system, n_replicas, n_steps, kT, marginal, n_legs, seed, replica0, x_cache, x0, v0, precision, want_heat,
+                       want_direct, want_final, traces, want_moments, dev, out, round_midpoint, moments_out)
     with t.cuda.device(dev):
         check(lib.lsi_run_protocol(system.handle, program.handle, ctypes.byref(a), current_stream_ptr()))
     return out
+
+
+def run_protocols(system, programs, n_replicas, n_steps, kT, marginal="configuration", n_legs=2, seed=0, replica0=0,
+                  x_cache=None, x0=None, v0=None, precision="double", want_heat=False, want_final=False, want_moments=True,
+                  device=None, outs=None, moments_out=None):
+    """Several programs over the SAME ensemble (lsi_run_protocol_batch): the results equal run_protocol(system, p, ...) for
+    every p, bit for bit; scalar systems run the six 5-letter palindromes (or the reference's three 6-letter closure
+    strings) as ONE kernel launch.  `outs`: one buffer dict per program (reused between calls); `moments_out`: a
+    (len(programs), 8) float64 CUDA tensor receiving the moment vectors.  Returns the list of dicts (no host sync)."""
+    require_cuda()
+    t = torch()
+    dev = t.device("cuda", t.cuda.current_device()) if device is None else t.device(device)
+    programs = list(programs)
+    outs = [{} for _ in programs] if outs is None else outs
+    if len(outs) != len(programs):
+        raise ValueError("one output dict per program")
+    x_cache, x0, v0 = _as_dev(x_cache, dev), _as_dev(x0, dev), _as_dev(v0, dev)
+    arr = (_cabi.ProtocolArgs * len(programs))()
+    for i, out in enumerate(outs):
+        arr[i] = _protocol_args(system, n_replicas, n_steps, kT, marginal, n_legs, seed, replica0, x_cache, x0, v0, precision,
+                                want_heat, False, want_final, False, want_moments, dev, out, False,
+                                None if moments_out is None else moments_out[i])
+    handles = (ctypes.c_void_p * len(programs))(*[p.handle for p in programs])
+    with t.cuda.device(dev):
+        check(lib.lsi_run_protocol_batch(system.handle, handles, len(programs), arr, current_stream_ptr()))
+    return outs
 
 
 def reduce_moments(W_F, W_R):

@@ -191,8 +191,8 @@ class EquilibriumSimulator:
 
     def load_or_simulate_samples(self):
         """If equilibrium samples were collected and stored before, load them, else collect and store them
-        (reference :66-76).  The cache is `{name}_samples.npz` in DATA_PATH; a `{name}_samples.h5` written by the
-        reference (an mdtraj HDF5 trajectory, e.g. data/tiny_waterbox_constrained_samples.h5) is read too.
+        (reference :66-76).  The cache is `{name}_samples.h5` in DATA_PATH, an mdtraj HDF5 trajectory as the reference
+        writes it (its own files, e.g. data/tiny_waterbox_constrained_samples.h5, load directly).
         Off by default (collecting a cache takes seconds here, not hours): set `use_disk_cache = True`."""
         if self.cached:
             return
@@ -204,13 +204,13 @@ class EquilibriumSimulator:
             self.save_samples()
 
     def get_path_to_samples(self):
-        """Samples are {name}_samples.npz in DATA_PATH (reference :115-118 uses .h5)"""
+        """Samples are {name}_samples.h5 in DATA_PATH (reference :115-118): an mdtraj HDF5 trajectory"""
         from .. import DATA_PATH
-        return os.path.join(DATA_PATH, "{}_samples.npz".format(self.name))
+        return os.path.join(DATA_PATH, "{}_samples.h5".format(self.name))
 
     def _candidate_paths(self):
-        npz = self.get_path_to_samples()
-        return [npz, npz[:-4] + ".h5"]
+        h5 = self.get_path_to_samples()
+        return [h5, h5[:-3] + ".npz"]  # .npz: caches written by earlier versions of this package
 
     def check_for_cached_samples(self):
         """Check if there's a file where we expect to find cached samples (reference :120-125)"""
@@ -232,13 +232,23 @@ class EquilibriumSimulator:
             return xyz
         raise FileNotFoundError(self.get_path_to_samples())
 
-    def save_samples(self, path=None):
-        """Store the cache (float32 nm, like the reference's mdtraj file) next to its acceptance statistics."""
+    def save_samples(self, path=None, potential_energy=None):
+        """Store the cache the way the reference's HDF5Reporter does (:106-113: coordinates, cell, potentialEnergy; float32 nm):
+        an mdtraj HDF5 trajectory that `md.load` opens (serialization/mdtraj_hdf5.py).  Potential energies (kJ/mol) are
+        evaluated on the GPU when one is available and none are given."""
+        from ..serialization.mdtraj_hdf5 import save_mdtraj_hdf5, topology_from_description
         path = self.get_path_to_samples() if path is None else path
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        tmp = path + ".tmp.npz"
-        np.savez_compressed(tmp, xyz=np.asarray(self.samples, dtype=np.float32),
-                            acceptance=np.zeros(0) if self.acceptance is None else np.asarray(self.acceptance))
+        xyz = np.asarray(self.samples, dtype=np.float32)
+        desc = self.system if isinstance(self.system, dict) else {}
+        if potential_energy is None and desc.get("n_atoms") and engine.lib.lsi_device_count() > 0:
+            pe, _ = self.engine_system().energy_forces(np.asarray(self.samples, dtype=np.float64), want_forces=False)
+            potential_energy = pe.cpu().numpy()
+        periodic = desc.get("nonbonded_method") == "CutoffPeriodic"
+        topology = topology_from_description(desc) if desc.get("n_atoms") else None
+        tmp = path + ".tmp"
+        save_mdtraj_hdf5(tmp, xyz, cell_lengths=desc.get("box") if periodic else None, potential_energy=potential_energy,
+                         topology=topology, title=str(self.name))
         os.replace(tmp, path)
         return path
 

@@ -98,14 +98,37 @@ ORC_API void orc_normals4(uint64_t seed, uint64_t replica, uint32_t draw, uint32
     normals4(r, out);
 }
 
-/* scalar-stream normal number k of a (replica, tag): block k>>2, lane k&3 */
-static double scalar_normal(uint64_t seed, uint64_t replica, uint32_t tag, uint32_t k)
+/* Scalar (toy) systems, DESIGN.md "RNG layout": ONE start block per replica, (replica, draw 0, TAG_V0, unit 0), feeds
+ * everything a two-leg protocol draws outside its O substeps: words 0, 1 -> the Box-Muller pair (start velocity normal,
+ * midpoint velocity normal), word 2 -> the equilibrium-cache index (w2 * n) >> 32, word 3 spare. */
+static void toy_start_block(uint64_t seed, uint64_t replica, int64_t n_cache, double* n_start, double* n_mid, int64_t* index)
 {
     uint32_t r[4];
     double n[4];
-    philox_block(seed, replica, k >> 2, tag, 0u, r);
+    philox_block(seed, replica, 0u, TAG_V0, 0u, r);
+    normals4(r, n);
+    *n_start = n[0];
+    *n_mid = n[1];
+    *index = (int64_t)(((uint64_t)r[2] * (uint64_t)n_cache) >> 32);
+}
+
+/* start-of-leg velocity normal of leg >= 2: normal leg - 2 of the TAG_V0 stream that begins at draw 1 */
+static double toy_later_leg_normal(uint64_t seed, uint64_t replica, uint32_t leg)
+{
+    const uint32_t k = leg - 2u;
+    uint32_t r[4];
+    double n[4];
+    philox_block(seed, replica, 1u + (k >> 2), TAG_V0, 0u, r);
     normals4(r, n);
     return n[k & 3u];
+}
+
+ORC_API int64_t orc_toy_cache_index(uint64_t seed, uint64_t replica, int64_t n)
+{
+    double a, b;
+    int64_t idx;
+    toy_start_block(seed, replica, n, &a, &b, &idx);
+    return idx;
 }
 
 /* uniform index in [0, n): (r * n) >> 32, r = lane 0 of block (replica, 0, TAG_X0, 0) */
@@ -177,9 +200,9 @@ static void normals4_f32(const uint32_t r[4], double n[4])
 /*
  * Runs, for each replica, n_legs legs of `n_steps` applications of the
  * splitting program (bookkeepers.py:247-295 / low_dimensional_systems.py:160-184):
- *   leg 0: x0 from cache (or x0_in), v0 ~ MB (or v0_in): normal 0 of the replica's TAG_V0 scalar stream
- *   leg l: x continues; v resampled (marginal 0 = "configuration": normal l of the same TAG_V0 stream, so the start
- *          and midpoint velocities of a two-leg protocol share one Box-Muller pair) or kept (1 = "full")
+ *   leg 0: x0 from cache (or x0_in), v0 ~ MB (or v0_in): index and start normal from the replica's start block
+ *   leg l: x continues; v resampled (marginal 0 = "configuration": leg 1 takes the second normal of the start block's
+ *          Box-Muller pair, later legs the TAG_V0 stream from draw 1) or kept (1 = "full")
  * W[leg] = ((E_end - E_start) - (Q_end - Q_start)) / kT     (bookkeepers.py:237-243)
  * Optional traces hold, per leg, n_steps+1 entries (entry 0 = leg start) of
  * x, v and the cumulative W in kT (numba_integrators.py:56-61).
@@ -207,11 +230,14 @@ ORC_API int orc_toy_protocol(int pot_kind, const double* pot_params, double mass
 #pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < n_replicas; ++r) {
         const uint64_t rid = replica0 + (uint64_t)r;
-        double x = x0_in ? x0_in[r] : x_cache[cache_index(seed, rid, n_cache)];
-        double v = v0_in ? v0_in[r] : sigma * scalar_normal(seed, rid, TAG_V0, 0u);
+        double n_start, n_mid;
+        int64_t idx0;
+        toy_start_block(seed, rid, n_cache > 0 ? n_cache : 1, &n_start, &n_mid, &idx0);
+        double x = x0_in ? x0_in[r] : x_cache[idx0];
+        double v = v0_in ? v0_in[r] : sigma * n_start;
         double heat = 0.0;
         for (int leg = 0; leg < n_legs; ++leg) {
-            if (leg > 0 && marginal == 0) v = sigma * scalar_normal(seed, rid, TAG_V0, (uint32_t)leg);
+            if (leg > 0 && marginal == 0) v = sigma * (leg == 1 ? n_mid : toy_later_leg_normal(seed, rid, (uint32_t)leg));
             const double E0 = toy_potential(pot_kind, pot_params, x) + 0.5 * mass * v * v;
             const double Q0 = heat;
             double wd = 0.0;

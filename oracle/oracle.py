@@ -39,6 +39,7 @@ def lib():
         _lib.orc_toy_potential.restype = ctypes.c_double
         _lib.orc_toy_force.restype = ctypes.c_double
         _lib.orc_cache_index.restype = ctypes.c_int64
+        _lib.orc_toy_cache_index.restype = ctypes.c_int64
     return _lib
 
 
@@ -85,7 +86,13 @@ def normals4(seed, replica, draw, tag, unit):
 
 
 def cache_index(seed, replica, n):
+    """particle systems: lane 0 of the replica's TAG_X0 block"""
     return int(lib().orc_cache_index(ctypes.c_uint64(seed), ctypes.c_uint64(replica), ctypes.c_int64(n)))
+
+
+def toy_cache_index(seed, replica, n):
+    """scalar systems: word 2 of the replica's start block (its words 0, 1 are the start / midpoint velocity pair)"""
+    return int(lib().orc_toy_cache_index(ctypes.c_uint64(seed), ctypes.c_uint64(replica), ctypes.c_int64(n)))
 
 
 def toy_potential(kind, x, params=(0.0,)):

@@ -141,55 +141,133 @@ def test_experiment_pickle_layout(tmp_path):
 
 
 # ------------------------------------------------------------------ equilibrium-sample caches
-def _shuffled_zlib(a):
-    import zlib
-    raw = np.ascontiguousarray(a, "<f4").view(np.uint8).reshape(-1, 4).T.copy().tobytes()
-    return zlib.compress(raw, 6)
-
-
-def test_mdtraj_hdf5_chunks_synthetic(tmp_path):
-    """byte-shuffled zlib chunks between unrelated bytes (some of them 0x78) are found, unshuffled and trimmed"""
-    from importlib import import_module
-    h5 = import_module("integrator-benchmark_b200.serialization.mdtraj_hdf5")
-    rng = np.random.default_rng(5)
-    n_atoms, n_frames, chunk_frames = 7, 5, 8
-    xyz = np.zeros((chunk_frames, n_atoms, 3), np.float32)
-    xyz[:n_frames] = rng.normal(size=(n_frames, n_atoms, 3))
-    lengths = np.zeros((64, 3), np.float32)
-    lengths[:n_frames] = 1.5
-    angles = np.zeros((64, 3), np.float32)
-    angles[:n_frames] = 90.0
-    blob = (b"\x89HDF\r\n\x1a\n" + b"\x78\x9cnot a stream" + bytes(rng.integers(0, 256, 300, dtype=np.uint8))
-            + _shuffled_zlib(lengths) + b"\x00" * 17 + _shuffled_zlib(angles) + b"x\x01x\xda"
-            + _shuffled_zlib(np.arange(50, dtype=np.float32)) + _shuffled_zlib(xyz) + b"tail")
-    path = tmp_path / "fake_samples.h5"
-    path.write_bytes(blob)
-    out = h5.load_mdtraj_hdf5(str(path), n_atoms)
-    assert out["xyz"].shape == (n_frames, n_atoms, 3)
-    np.testing.assert_array_equal(out["xyz"], xyz[:n_frames])
-    np.testing.assert_array_equal(out["cell_lengths"], lengths[:n_frames])
-    np.testing.assert_array_equal(out["cell_angles"], angles[:n_frames])
-    with pytest.raises(ValueError):
-        h5.load_mdtraj_hdf5(str(path), n_atoms + 1000)
-    (tmp_path / "not.h5").write_bytes(b"hello")
-    with pytest.raises(ValueError):
-        h5.load_mdtraj_hdf5(str(tmp_path / "not.h5"), n_atoms)
-
-
 REF_H5 = "/root/reference/data/tiny_waterbox_constrained_samples.h5"
 
 
-@pytest.mark.skipif(not os.path.exists(REF_H5), reason="reference checkout not present")
-def test_mdtraj_hdf5_reference_cache():
-    """the one cache the reference ships decodes to the committed fixture frames"""
+def _h5():
     from importlib import import_module
-    h5 = import_module("integrator-benchmark_b200.serialization.mdtraj_hdf5")
+    return (import_module("integrator-benchmark_b200.serialization.mdtraj_hdf5"),
+            import_module("integrator-benchmark_b200.serialization.hdf5_min"))
+
+
+@pytest.mark.parametrize("n_frames,n_atoms", [(5, 7), (1000, 60), (1, 306), (70, 3)])
+def test_mdtraj_hdf5_round_trip(tmp_path, n_frames, n_atoms):
+    """save_mdtraj_hdf5 -> load_mdtraj_hdf5 returns the same frames, cell, energies and topology; the file has the
+    structures mdtraj / PyTables write (checked field by field against the reference's own cache below)"""
+    h5, hmin = _h5()
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(size=(n_frames, n_atoms, 3)).astype(np.float32)
+    pe = rng.normal(size=n_frames).astype(np.float32)
+    topo = {"chains": [{"index": 0, "residues": [{"index": 0, "name": "MOL", "resSeq": 1,
+                                                 "atoms": [{"index": i, "name": "C%d" % i, "element": "C"} for i in range(n_atoms)]}]}], "bonds": []}
+    path = str(tmp_path / "t_samples.h5")
+    h5.save_mdtraj_hdf5(path, xyz, cell_lengths=(1.5, 1.5, 1.5), potential_energy=pe, topology=topo)
+    out = h5.load_mdtraj_hdf5(path, n_atoms)
+    np.testing.assert_array_equal(out["xyz"], xyz)
+    np.testing.assert_array_equal(out["cell_lengths"], np.full((n_frames, 3), 1.5, np.float32))
+    np.testing.assert_array_equal(out["cell_angles"], np.full((n_frames, 3), 90.0, np.float32))
+    np.testing.assert_array_equal(out["potential_energy"], pe)
+    assert out["topology"] == topo
+    raw = hmin.read(path)
+    assert raw["/"].attrs["conventions"] == "Pande" and raw["/"].attrs["conventionVersion"] == "1.1"
+    assert raw["coordinates"].attrs["units"] == "nanometers" and raw["coordinates"].attrs["CLASS"] == "EARRAY"
+    assert raw["coordinates"].maxshape == (None, n_atoms, 3) and raw["potentialEnergy"].attrs["units"] == "kilojoules_per_mole"
+    with pytest.raises(ValueError):
+        h5.load_mdtraj_hdf5(path, n_atoms + 1)
+    (tmp_path / "not.h5").write_bytes(b"hello")
+    with pytest.raises(ValueError):
+        h5.load_mdtraj_hdf5(str(tmp_path / "not.h5"), n_atoms)
+    # without a cell and without energies (the water cluster, alanine dipeptide)
+    h5.save_mdtraj_hdf5(path, xyz)
+    out = h5.load_mdtraj_hdf5(path)
+    np.testing.assert_array_equal(out["xyz"], xyz)
+    assert out["cell_lengths"] is None and out["potential_energy"] is None
+
+
+def test_mdtraj_hdf5_file_structure(tmp_path):
+    """the bytes follow the HDF5 specification the way libhdf5 lays these files out: fixed-size B-tree nodes, 8-byte alignment,
+    sorted symbol table, end-of-file address, chunk keys (size, mask, offsets) with the closing key"""
+    import struct
+    h5, hmin = _h5()
+    xyz = np.arange(40 * 5 * 3, dtype=np.float32).reshape(40, 5, 3)
+    path = str(tmp_path / "s.h5")
+    h5.save_mdtraj_hdf5(path, xyz, cell_lengths=(2.0, 2.0, 2.0), potential_energy=np.zeros(40))
+    b = open(path, "rb").read()
+    assert b[:8] == b"\x89HDF\r\n\x1a\n" and b[8] == 0 and b[13] == 8 and b[14] == 8
+    assert struct.unpack_from("<HH", b, 16) == (4, 16)                       # group leaf / internal node K
+    assert struct.unpack_from("<Q", b, 40)[0] == len(b)                       # end-of-file address
+    root, = struct.unpack_from("<Q", b, 64)
+    btree, heap = struct.unpack_from("<QQ", b, 80)
+    assert root == 96 and b[btree:btree + 4] == b"TREE" and b[heap:heap + 4] == b"HEAP"
+    assert all(a % 8 == 0 for a in (root, btree, heap))
+    r = hmin._Reader(b)
+    names = [n for n, _ in r.group_entries(btree, heap)]
+    assert names == sorted(names) == ["cell_angles", "cell_lengths", "coordinates", "potentialEnergy"]
+    for name, ohdr in r.group_entries(btree, heap):
+        layout = [body for t, body in r.messages(ohdr) if t == 0x08][0]
+        assert layout[0] == 3 and layout[1] == 2
+        rank = layout[2] - 1
+        tree, = struct.unpack_from("<Q", layout, 3)
+        assert b[tree:tree + 4] == b"TREE" and b[tree + 4] == 1 and tree % 8 == 0
+        chunks = r.chunks_of(tree, rank)
+        cshape = struct.unpack_from("<%dI" % rank, layout, 11)
+        assert [c[0][0] for c in chunks] == list(range(0, 40, cshape[0])) and len(chunks) <= 64
+        # closing key: one chunk past the last offset, the chunk dims and the element size
+        key = 8 + 8 * (rank + 1)
+        p = tree + 24 + len(chunks) * (key + 8)
+        assert struct.unpack_from("<II%dQ" % (rank + 1), b, p) == (0, 0, chunks[-1][0][0] + cshape[0]) + tuple(cshape[1:]) + (4,)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_H5), reason="reference checkout not present")
+def test_mdtraj_hdf5_reference_cache(tmp_path):
+    """the one cache the reference ships is parsed structurally and decodes to the committed fixture frames; a file written
+    here carries, message for message, the same dataset descriptions as the reference's (PyTables / libhdf5-written) file"""
+    h5, hmin = _h5()
     out = h5.load_mdtraj_hdf5(REF_H5, 306)
     gold = np.load(os.path.join(ROOT, "tests", "golden", "waterbox_frames.npz"))
-    assert out["xyz"].shape[1:] == (306, 3) and out["xyz"].shape[0] >= 4
-    np.testing.assert_array_equal(out["xyz"][:4], gold["xyz"])
-    np.testing.assert_allclose(out["cell_lengths"][:4], 1.5)
-    np.testing.assert_allclose(out["cell_angles"][:4], 90.0)
+    assert out["xyz"].shape == (4, 306, 3)
+    np.testing.assert_array_equal(out["xyz"], gold["xyz"])
+    np.testing.assert_allclose(out["cell_lengths"], 1.5)
+    np.testing.assert_allclose(out["cell_angles"], 90.0)
+    np.testing.assert_allclose(out["potential_energy"], [-4136.6406, -4029.0005, -4030.8572, -4068.7595], rtol=1e-6)
+    assert len(out["topology"]["chains"][0]["residues"]) == 102 and out["topology"]["chains"][0]["residues"][0]["name"] == "HOH"
+    # re-write the same content and compare the per-dataset header messages with the reference file's
+    path = str(tmp_path / "rewritten.h5")
+    h5.save_mdtraj_hdf5(path, out["xyz"], cell_lengths=out["cell_lengths"], cell_angles=out["cell_angles"],
+                        potential_energy=out["potential_energy"], topology=out["topology"])
+    ref, new = hmin._Reader(open(REF_H5, "rb").read()), hmin._Reader(open(path, "rb").read())
+
+    def headers(r):
+        sym = [struct_body for t, struct_body in r.messages(r.root_ohdr) if t == 0x11][0]
+        import struct
+        return dict(r.group_entries(*struct.unpack_from("<QQ", sym, 0)))
+    h_ref, h_new = headers(ref), headers(new)
+    assert sorted(h_ref) == sorted(h_new)
+    for name in ("coordinates", "cell_lengths", "cell_angles", "potentialEnergy"):
+        m_ref = {t: body for t, body in ref.messages(h_ref[name]) if t in (0x01, 0x03, 0x05, 0x0B)}
+        m_new = {t: body for t, body in new.messages(h_new[name]) if t in (0x01, 0x03, 0x05, 0x0B)}
+        assert m_ref == m_new, name                                   # dataspace, datatype, fill value, filter pipeline: identical bytes
+        a_ref = {body for t, body in ref.messages(h_ref[name]) if t == 0x0C}
+        a_new = {body for t, body in new.messages(h_new[name]) if t == 0x0C}
+        assert a_ref == a_new, name                                   # CLASS / VERSION / TITLE / EXTDIM / units attributes: identical bytes
+    back = h5.load_mdtraj_hdf5(path, 306)
+    np.testing.assert_array_equal(back["xyz"], out["xyz"])
+    assert back["topology"] == out["topology"]
+
+
+def test_topology_from_description():
+    from importlib import import_module
+    h5, _ = _h5()
+    ts = import_module("integrator-benchmark_b200.testsystems.systems")
+    desc, _ = ts.water_cluster(4, constrained=True)
+    topo = h5.topology_from_description(desc)
+    res = topo["chains"][0]["residues"]
+    assert len(res) == 4 and all(r["name"] == "HOH" and [a["element"] for a in r["atoms"]] == ["O", "H", "H"] for r in res)
+    assert len(topo["bonds"]) == 8
+    desc, _ = ts.alanine_dipeptide(constrained=True, mass_scale=3.0)
+    topo = h5.topology_from_description(desc)
+    els = [a["element"] for r in topo["chains"][0]["residues"] for a in r["atoms"]]
+    assert len(els) == 22 and els.count("H") == 12 and els.count("C") == 6 and els.count("N") == 2 and els.count("O") == 2
 
 
 def test_equilibrium_cache_on_disk(tmp_path, monkeypatch):
@@ -202,7 +280,7 @@ def test_equilibrium_cache_on_disk(tmp_path, monkeypatch):
     eq = bk.EquilibriumSimulator(platform=None, topology=None, system={}, positions=np.zeros((5, 3)), temperature=298.0,
                                  timestep=0.001, burn_in_length=10, n_samples=3, thinning_interval=1, name="five_atoms")
     eq.use_disk_cache = True
-    assert eq.get_path_to_samples() == os.path.join(str(tmp_path), "five_atoms_samples.npz")
+    assert eq.get_path_to_samples() == os.path.join(str(tmp_path), "five_atoms_samples.h5")
     assert not eq.check_for_cached_samples()
     frames = np.random.default_rng(1).normal(size=(3, 5, 3)).astype(np.float32)
     eq.samples = frames

@@ -112,7 +112,7 @@ def test_replica_ids_key_the_streams(ib, orc):
         assert np.array_equal(part, full[:, lo:hi])
     # cache indices are the oracle's, bit for bit
     res = ib.engine.run_protocol(system, prog, 64, 0, 1.0, seed=5, replica0=1 << 33, x_cache=cache, want_final=True)
-    idx = [orc.cache_index(5, (1 << 33) + r, len(cache)) for r in range(64)]
+    idx = [orc.toy_cache_index(5, (1 << 33) + r, len(cache)) for r in range(64)]
     assert np.array_equal(res["x_final"].cpu().numpy(), cache[idx])
 
 
@@ -378,3 +378,36 @@ def test_quartic_steady_state_histogram_matches_the_published_ground_truth(ib):
         got[name] = vqh.histogram_kl(x[np.isfinite(x) & (np.abs(x) < 2.5)], edges)
     assert got["OVRVO"] == pytest.approx(0.01309, rel=0.03), got
     assert 0.00007 < got["VRORV"] < 0.00019, got
+
+
+@pytest.mark.parametrize("kind,precision", [("double_well", "double"), ("quartic", "double"), ("double_well", "mixed")])
+def test_batch_launch_equals_individual_launches(ib, orc, kind, precision):
+    """lsi_run_protocol_batch == one lsi_run_protocol per program, bit for bit: the one-launch families (six 5-letter
+    palindromes, the reference's three 6-letter closure strings), a permuted subset, and batches that fall back to
+    separate launches (mixed families, a repeated program, a string outside the families)."""
+    import torch
+    cache = _cache(orc, kind)
+    system = ib.engine.ScalarSystem(kind, 10.0)
+    six_letter = ["O V R R V O", "V R O O R V", "R V O O V R"]
+    cases = [SIX, six_letter, [SIX[4], SIX[0], SIX[2]], [SIX[0], six_letter[1]], [SIX[1], SIX[1]], [SIX[0], "R V O"],
+             [SIX[3]]]
+    for n, steps in [(3001, 9), (700, 4)]:
+        for strings in cases:
+            progs = [ib.engine.Program(s, 0.35, 10.0) for s in strings]
+            singles = [ib.engine.run_protocol(system, p, n, steps, 1.0, seed=3, replica0=77, x_cache=cache, precision=precision,
+                                              want_heat=True, want_final=True, out={}) for p in progs]
+            mom = torch.full((len(progs), 8), -1.0, dtype=torch.float64, device="cuda")
+            batch = ib.engine.run_protocols(system, progs, n, steps, 1.0, seed=3, replica0=77, x_cache=cache, precision=precision,
+                                            want_heat=True, want_final=True, moments_out=mom)
+            for i, (s, b) in enumerate(zip(singles, batch)):
+                for key in ("W", "heat", "x_final", "v_final", "moments"):
+                    assert torch.equal(s[key], b[key]), (strings, i, key)
+                assert torch.equal(mom[i], s["moments"])
+    # "full" marginal and explicit start states travel through the batch as well
+    x0 = cache[:500].copy()
+    v0 = np.linspace(-0.3, 0.3, 500)
+    progs = [ib.engine.Program(s, 0.2, 5.0) for s in SIX]
+    singles = [ib.engine.run_protocol(system, p, 500, 7, 1.0, marginal="full", seed=9, x0=x0, v0=v0, precision=precision, out={}) for p in progs]
+    batch = ib.engine.run_protocols(system, progs, 500, 7, 1.0, marginal="full", seed=9, x0=x0, v0=v0, precision=precision)
+    for s, b in zip(singles, batch):
+        assert torch.equal(s["W"], b["W"]) and torch.equal(s["moments"], b["moments"])
