@@ -251,13 +251,19 @@ int64_t lsi_protocol_workspace_bytes(int64_t n_replicas);
 int lsi_run_protocol(const lsi_system* sys, const lsi_program* prog, const lsi_protocol_args* args,
                      void* stream);
 
-/* The same for several programs on one system: identical, bit for bit, to calling lsi_run_protocol(sys, progs[p], &args[p])
- * for p = 0 .. n_progs - 1 in that order on `stream`.  What the reference does when it compares schemes
+/* The same for several programs on one system: works, heats and final states are identical, bit for bit, to calling
+ * lsi_run_protocol(sys, progs[p], &args[p]) for p = 0 .. n_progs - 1 in that order on `stream` (moment sums hold the same
+ * terms; their summation order, hence their last bits, may differ).  What the reference does when it compares schemes
  * (experiments/toy/quartic_kl_validation.py:56-70, tests/test_shadow_work.py:47-55: a loop over splittings around the same
  * equilibrium cache).  Scalar systems run the whole batch as ONE kernel launch when the programs are distinct members of
  * one pre-compiled family -- the six 5-letter palindromes over {O, R, V}, or the three 6-letter strings the reference's
  * numba closures perform -- and all args share the ensemble (n_replicas, n_steps, n_legs, marginal, precision, kT, seed,
  * replica0, x_cache / x0 / v0) and ask for no traces: tables are staged once and the GPU never drains between programs.
+ * When the batch is a WHOLE family whose programs were compiled with the same time step and collision rate, every thread
+ * carries one replica through all programs at once: programs that share an ensemble share the replica's start state and its
+ * O-noise stream (the RNG layout keys noise by seed, replica, leg and draw, not by program), so the start block, the cache
+ * gather and every Philox block / Box-Muller pair are computed once per replica instead of once per program -- common random
+ * numbers across the splittings, at about half the arithmetic of separate launches.
  * Every args[p] needs its own outputs and its own workspace.  Anything else falls back to one launch per program. */
 int lsi_run_protocol_batch(const lsi_system* sys, const lsi_program* const* progs, int32_t n_progs,
                            const lsi_protocol_args* args, void* stream);

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 
 #include <cstring>
+#include <type_traits>
+#include <utility>
 
 #include "lsi_internal.h"
 #include "rng.cuh"
@@ -720,6 +722,262 @@ __global__ void __launch_bounds__(kF2Threads, LSI_TOY2_MINB) toy_fused2_batch_ke
 }
 
 // ------------------------------------------------------------------------------------------
+// K1-family: ONE replica per thread pushed through EVERY program of a family at once.  The programs of a batch share the
+// ensemble (same seed, same global replica ids, same start states), hence the replica's start block, its gathered start
+// position, the potential there AND its whole O-noise stream (Philox blocks + Box-Muller pairs, more than half of all fp64
+// instructions of a single-program launch): all of that is computed once per replica and consumed by all programs.  The
+// programs advance in lockstep over the noise blocks: a program with two O substeps per step consumes a block in two steps,
+// one with a single O substep in four; each keeps its own (x, v, g, h).  Besides removing the redundant work this gives
+// every thread as many independent dependency chains as there are programs (the single-program kernel has one).
+// Per-program arithmetic is the single-program kernel's, instruction for instruction: works are bit-identical.
+// Requires (checked on the host): every slot of the family enabled, and all programs with the same number of O
+// substeps share (a, b sigma) -- true when they were compiled with the same time step and collision rate.
+#ifndef LSI_TOY3_THREADS
+#define LSI_TOY3_THREADS 384
+#endif
+#ifndef LSI_TOY3_PIPE
+#define LSI_TOY3_PIPE 0
+#endif
+constexpr int kF3Threads = LSI_TOY3_THREADS;
+
+template <int NOPS, uint32_t... CODES>
+struct Family {
+    static constexpr int NP = (int)sizeof...(CODES);
+    static constexpr uint32_t codes[NP] = {CODES...};
+    static constexpr int no(int p) { return code_count(codes[p], NOPS, LSI_OP_O); }
+    static constexpr bool has_class(int n_o)
+    {
+        for (int p = 0; p < NP; ++p)
+            if (no(p) == n_o) return true;
+        return false;
+    }
+    static constexpr int first_of_class(int n_o)
+    {
+        for (int p = 0; p < NP; ++p)
+            if (no(p) == n_o) return p;
+        return 0;
+    }
+};
+
+template <class F, int... Is>
+__device__ __forceinline__ void for_each_slot(F&& f, std::integer_sequence<int, Is...>)
+{
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+
+constexpr int kF3Acc = 6;  // count, sum wF, sum wR, sum wF^2, sum wR^2, sum wF wR per program (non-finite pairs = replicas seen - count)
+constexpr size_t family_smem(int np) { return (size_t)fm::TabView::kBytes + (size_t)np * kF3Acc * kF3Threads * sizeof(double); }
+
+// the shared part of one Box-Muller pair, and its completion for one scale (b sigma of a class of programs): the same
+// instruction sequence as box_muller_tab / the fp32 path of normal_block_part, split where the scale enters
+struct PairCore { double t, q, c, s; };
+
+template <bool NOISE32, class TAB>
+__device__ __forceinline__ PairCore pair_core(const TAB& T, uint32_t ra, uint32_t rb)
+{
+    PairCore k;
+    if (NOISE32) {
+        float a, b;
+        lsi::box_muller(ra, rb, a, b);
+        k.t = (double)a; k.q = (double)b; k.c = 0.0; k.s = 0.0;
+    } else {
+        const double x = fm::neg2log_tab(T, fm::uniform_from_u32(ra, false));
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        k.t = x * y;
+        const double e = fma(-k.t, y, 1.0);
+        k.q = e * fma(e, 0.375, 0.5);
+        fm::sincos2pi_u32_tab(T, rb, k.s, k.c);
+    }
+    return k;
+}
+
+template <bool NOISE32>
+__device__ __forceinline__ void pair_scaled(const PairCore& k, double scale, double& n0, double& n1)
+{
+    if (NOISE32) {
+        n0 = scale * k.t; n1 = scale * k.q;
+    } else {
+        const double ts = k.t * scale;
+        const double rad = fma(ts, k.q, ts);
+        n0 = rad * k.c; n1 = rad * k.s;
+    }
+}
+
+template <int POT, bool NOISE32, int NOPS, uint32_t... CODES>
+__global__ void __launch_bounds__(kF3Threads, 1) toy_family_kernel(const __grid_constant__ ToyBatchParams B)
+{
+    using Fam = Family<NOPS, CODES...>;
+    constexpr int NP = Fam::NP;
+    constexpr bool C1 = Fam::has_class(1), C2 = Fam::has_class(2);
+    constexpr int S1 = Fam::first_of_class(1), S2 = Fam::first_of_class(2);
+    static_assert(C1 || C2, "every program of a family has one or two O substeps per step");
+    const auto slots = std::make_integer_sequence<int, NP>{};
+    extern __shared__ __align__(16) unsigned char toy3_smem[];
+    const fm::TabView FT = fm::load_tables_replicated(toy3_smem, toy3_smem + fm::TabView::kBytes);
+    double* acc = reinterpret_cast<double*>(toy3_smem + fm::TabView::kBytes) + threadIdx.x;  // [NP][kF3Acc][kF3Threads]
+#pragma unroll
+    for (int j = 0; j < NP * kF3Acc; ++j) acc[j * kF3Threads] = 0.0;
+    int n_seen = 0;  // replicas this thread has finished
+    __syncthreads();
+
+    const ToyParams& P0 = B.P[0];  // the ensemble: identical in every slot
+    const double half_m = 0.5 * P0.mass;
+    const int n_steps = P0.n_steps;
+    const int n_blk = C2 ? (n_steps + 1) / 2 : (n_steps + 3) / 4;  // noise blocks of a leg: the class with two O substeps consumes the most
+    const double oc1 = B.P[S1].oc, oc2 = B.P[S2].oc;
+    // normals of one block, already multiplied by the b sigma of each class
+    struct Normals { double n1[4], n2[4]; };
+    auto generate = [&](uint64_t rid, uint32_t draw, bool second_pair, Normals& N) {
+        const lsi::Philox4 r = lsi::philox_block(P0.keys, rid, draw, LSI_TAG_O, 0u);
+        const PairCore a = pair_core<NOISE32>(FT, r.x, r.y);
+        if (C1) pair_scaled<NOISE32>(a, oc1, N.n1[0], N.n1[1]);
+        if (C2) pair_scaled<NOISE32>(a, oc2, N.n2[0], N.n2[1]);
+        if (second_pair) {
+            const PairCore b = pair_core<NOISE32>(FT, r.z, r.w);
+            if (C1) pair_scaled<NOISE32>(b, oc1, N.n1[2], N.n1[3]);
+            if (C2) pair_scaled<NOISE32>(b, oc2, N.n2[2], N.n2[3]);
+        }
+    };
+
+    const int64_t n_chunks = (P0.n + kF3Threads - 1) / kF3Threads;
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t r = chunk * kF3Threads + threadIdx.x;
+        if (r >= P0.n) continue;
+        const uint64_t rid = P0.replica0 + (uint64_t)r;
+        double n_start, n_mid;
+        int64_t idx0;
+        start_block(FT, P0.keys, rid, P0.n_cache, n_start, n_mid, idx0);
+        const double x0 = P0.x0 ? P0.x0[r] : P0.x_cache[idx0];
+        const double v0 = P0.v0 ? P0.v0[r] : P0.sigma * n_start;
+        const double pe0 = potential<POT>(FT, x0, P0.p0);
+        const double g0 = force_g<POT>(FT, x0);
+        double x[NP][1], v[NP][1], g[NP][1], h[NP][1], pe[NP], wF[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) { x[p][0] = x0; v[p][0] = v0; g[p][0] = g0; pe[p] = pe0; wF[p] = 0.0; }
+
+        for (int leg = 0; leg < P0.n_legs; ++leg) {
+            double E0[NP];
+            if (leg > 0 && P0.marginal == LSI_MARGINAL_CONFIGURATION) {
+                const double vm = P0.sigma * (leg == 1 ? n_mid : later_leg_normal(FT, P0.keys, rid, (uint32_t)leg));
+#pragma unroll
+                for (int p = 0; p < NP; ++p) v[p][0] = vm;
+            }
+            for_each_slot([&](auto ic) {
+                constexpr int p = decltype(ic)::value;
+                constexpr uint32_t CODE = Fam::codes[p];
+                const double v2 = v[p][0] * v[p][0];
+                E0[p] = fma(half_m, v2, pe[p]);
+                h[p][0] = (code_is_O(CODE, NOPS, 0) && code_is_O(CODE, NOPS, NOPS - 1)) ? -v2 : 0.0;
+            }, slots);
+            const uint32_t leg_base = (uint32_t)leg << 26;
+            // steps [2 b + u] of the two-O class and [4 b + u] of the one-O class, for one u
+            auto step_class = [&](auto n_o, const Normals& N, int u) {
+                constexpr int NO = decltype(n_o)::value;
+                for_each_slot([&](auto ic) {
+                    constexpr int p = decltype(ic)::value;
+                    constexpr uint32_t CODE = Fam::codes[p];
+                    if constexpr (code_count(CODE, NOPS, LSI_OP_O) == NO) {
+                        double xi[1][NO];
+#pragma unroll
+                        for (int o = 0; o < NO; ++o) xi[0][o] = NO == 1 ? N.n1[u] : N.n2[2 * u + o];
+                        FusedStep2<POT, CODE, NOPS, 1>::run(FT, x[p], v[p], g[p], h[p], B.P[p].hR, B.P[p].hV * force_scale<POT>(P0.p0),
+                                                            B.P[p].oa, xi);
+                    }
+                }, slots);
+            };
+            auto block_steps = [&](int b, const Normals& N) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool a2 = C2 && u < 2 && 2 * b + u < n_steps;
+                    const bool a1 = C1 && 4 * b + u < n_steps;
+                    if (a2 && a1) {  // one basic block: all programs' chains interleave
+                        step_class(std::integral_constant<int, 2>{}, N, u);
+                        step_class(std::integral_constant<int, 1>{}, N, u);
+                    } else if (a2) {
+                        step_class(std::integral_constant<int, 2>{}, N, u);
+                    } else if (a1) {
+                        step_class(std::integral_constant<int, 1>{}, N, u);
+                    }
+                }
+            };
+            // does block b need its second Box-Muller pair?  (normals 2, 3: the one-O class' steps 4 b + 2, 4 b + 3, the
+            // two-O class' step 2 b + 1)
+            auto needs_second = [&](int b) { return (C2 && 2 * b + 1 < n_steps) || (C1 && 4 * b + 2 < n_steps); };
+            if (n_blk > 0) {
+                Normals cur;
+                generate(rid, leg_base, needs_second(0), cur);
+#if LSI_TOY3_PIPE
+                for (int b = 0; b + 1 < n_blk; ++b) {
+                    Normals nxt;
+                    generate(rid, leg_base | (uint32_t)(b + 1), needs_second(b + 1), nxt);
+                    block_steps(b, cur);
+                    cur = nxt;
+                }
+                block_steps(n_blk - 1, cur);
+#else
+                for (int b = 0; b < n_blk; ++b) {
+                    if (b > 0) generate(rid, leg_base | (uint32_t)b, needs_second(b), cur);
+                    block_steps(b, cur);
+                }
+#endif
+            }
+            for_each_slot([&](auto ic) {
+                constexpr int p = decltype(ic)::value;
+                constexpr uint32_t CODE = Fam::codes[p];
+                constexpr bool CYC_OO = code_is_O(CODE, NOPS, 0) && code_is_O(CODE, NOPS, NOPS - 1);
+                const ToyParams& P = B.P[p];
+                pe[p] = potential<POT>(FT, x[p][0], P0.p0);
+                const double v2 = v[p][0] * v[p][0];
+                const double E1 = fma(half_m, v2, pe[p]);
+                const double heat = half_m * (CYC_OO ? h[p][0] + v2 : h[p][0]);
+                const double w = ((E1 - E0[p]) - heat) * P0.inv_kT;
+                P.W[(int64_t)leg * P0.n + r] = w;
+                if (P.heat) P.heat[(int64_t)leg * P0.n + r] = heat;
+                if (leg == 0) wF[p] = w;
+                if (leg == 1 && P.partials) {
+                    double* a = acc + p * kF3Acc * kF3Threads;
+                    const double wf = wF[p];
+                    if (isfinite(wf) && isfinite(w)) {
+                        a[0] += 1.0; a[kF3Threads] += wf; a[2 * kF3Threads] += w;
+                        a[3 * kF3Threads] += wf * wf; a[4 * kF3Threads] += w * w; a[5 * kF3Threads] += wf * w;
+                    }
+                }
+            }, slots);
+        }
+        for_each_slot([&](auto ic) {
+            constexpr int p = decltype(ic)::value;
+            const ToyParams& P = B.P[p];
+            if (P.x_final) P.x_final[r] = x[p][0];
+            if (P.v_final) P.v_final[r] = v[p][0];
+        }, slots);
+        ++n_seen;
+    }
+    // block partials of every program
+    __shared__ double sh[kF3Threads / 32][7];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for_each_slot([&](auto ic) {
+        constexpr int p = decltype(ic)::value;
+        const ToyParams& P = B.P[p];
+        if (P.partials) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const double s = warp_sum(j < kF3Acc ? acc[(p * kF3Acc + j) * kF3Threads] : (double)n_seen - acc[p * kF3Acc * kF3Threads]);
+                if (lane == 0) sh[warp][j] = s;
+            }
+            __syncthreads();
+            if (threadIdx.x < 8) {
+                double s = 0.0;
+                if (threadIdx.x < 7)
+                    for (int w = 0; w < kF3Threads / 32; ++w) s += sh[w][threadIdx.x];
+                P.partials[(int64_t)blockIdx.x * 8 + threadIdx.x] = s;
+            }
+        }
+    }, slots);
+}
+
+// ------------------------------------------------------------------------------------------
 // interpreter
 template <bool EXT>
 struct ProgRead {
@@ -1049,6 +1307,9 @@ static int toy_prepare(const lsi_system* sys, const lsi_program* prog, const lsi
 // families of the batch kernel (toy_fused2_batch_kernel): slot order is the order of the strings
 #define LSI_FAMILY_FIVE(X) X("OVRVO") X("ORVRO") X("RVOVR") X("ROVOR") X("VRORV") X("VOROV")
 #define LSI_FAMILY_SIX(X) X("OVRRVO") X("VROORV") X("RVOOVR")
+// whole-family (shared-noise) kernel only: the pair the reference's quartic validation compares, vvvr and baoab
+// (experiments/toy/quartic_kl_validation.py:33-36); slots are a prefix of LSI_FAMILY_SIX
+#define LSI_FAMILY_PAIR(X) X("OVRRVO") X("VROORV")
 
 static int family_slot(int family, uint32_t code, int nops)
 {
@@ -1078,6 +1339,42 @@ static cudaError_t launch_batch2(int family, unsigned grid, const ToyBatchParams
     }
 #undef X
     return cudaGetLastError();
+}
+
+template <int POT, bool NOISE32>
+static cudaError_t launch_family2(int family, unsigned grid, const ToyBatchParams& B, cudaStream_t st)
+{
+#define X(S) , pack(S)
+    if (family == 0) {
+        auto k = toy_family_kernel<POT, NOISE32, 5 LSI_FAMILY_FIVE(X)>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)family_smem(6));
+        if (e != cudaSuccess) return e;
+        k<<<grid, kF3Threads, family_smem(6), st>>>(B);
+    } else if (family == 1) {
+        auto k = toy_family_kernel<POT, NOISE32, 6 LSI_FAMILY_SIX(X)>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)family_smem(3));
+        if (e != cudaSuccess) return e;
+        k<<<grid, kF3Threads, family_smem(3), st>>>(B);
+    } else {
+        auto k = toy_family_kernel<POT, NOISE32, 6 LSI_FAMILY_PAIR(X)>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)family_smem(2));
+        if (e != cudaSuccess) return e;
+        k<<<grid, kF3Threads, family_smem(2), st>>>(B);
+    }
+#undef X
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_family(int pot, bool noise32, int family, unsigned grid, const ToyBatchParams& B, cudaStream_t st)
+{
+    switch (pot) {
+    case LSI_POT_QUARTIC:
+        return noise32 ? launch_family2<LSI_POT_QUARTIC, true>(family, grid, B, st) : launch_family2<LSI_POT_QUARTIC, false>(family, grid, B, st);
+    case LSI_POT_DOUBLE_WELL:
+        return noise32 ? launch_family2<LSI_POT_DOUBLE_WELL, true>(family, grid, B, st) : launch_family2<LSI_POT_DOUBLE_WELL, false>(family, grid, B, st);
+    default:
+        return noise32 ? launch_family2<LSI_POT_HARMONIC, true>(family, grid, B, st) : launch_family2<LSI_POT_HARMONIC, false>(family, grid, B, st);
+    }
 }
 
 static cudaError_t launch_batch(int pot, bool noise32, int family, unsigned grid, const ToyBatchParams& B, cudaStream_t st)
@@ -1130,8 +1427,34 @@ int lsi_toy_run_protocol_batch(const lsi_system* sys, const lsi_program* const* 
         }
         return LSI_OK;
     }
-    const unsigned grid = fused2_grid(a0.n_replicas);
-    const cudaError_t err = launch_batch(sys->potential, a0.precision == LSI_PRECISION_MIXED, family, grid, B, st);
+    // the whole family, and one (a, b sigma) per number of O substeps: the shared-noise kernel (one replica per thread through
+    // all programs); otherwise the programs run one after the other inside one launch
+    bool whole_family = B.enabled == (family == 0 ? 0x3Fu : 0x7u) || (family == 1 && B.enabled == 0x3u);
+    const int family_kernel = (family == 1 && B.enabled == 0x3u) ? 2 : family;
+    {
+        double oa[3] = {0, 0, 0}, oc[3] = {0, 0, 0};
+        bool seen[3] = {false, false, false};
+        for (int p = 0; p < n_progs && whole_family; ++p) {
+            const int n_o = progs[p]->n_O;
+            if (n_o < 1 || n_o > 2) { whole_family = false; break; }
+            ToyParams P;
+            bool fusable;
+            uint32_t code;
+            int nops;
+            toy_prepare(sys, progs[p], &args[p], P, fusable, code, nops);
+            if (!seen[n_o]) { seen[n_o] = true; oa[n_o] = P.oa; oc[n_o] = P.oc; }
+            else if (oa[n_o] != P.oa || oc[n_o] != P.oc) whole_family = false;
+        }
+    }
+    unsigned grid;
+    cudaError_t err;
+    if (whole_family) {
+        grid = persistent_grid(a0.n_replicas, kF3Threads, 1);
+        err = launch_family(sys->potential, a0.precision == LSI_PRECISION_MIXED, family_kernel, grid, B, st);
+    } else {
+        grid = fused2_grid(a0.n_replicas);
+        err = launch_batch(sys->potential, a0.precision == LSI_PRECISION_MIXED, family, grid, B, st);
+    }
     if (err != cudaSuccess) return lsi_set_error(LSI_ERR_CUDA, "toy batch kernel launch failed: %s", cudaGetErrorString(err));
     const double* partials[kBatchMax];
     double* moments[kBatchMax];

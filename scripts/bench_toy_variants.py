@@ -43,8 +43,25 @@ def child():
     for j, a, e in evs:
         ms[j] += a.elapsed_time(e) / reps
     W = bufs[0]["W"].double().sum().item()
+    # the six programs as one batch launch (lsi_run_protocol_batch)
+    mom = torch.zeros(6, 8, dtype=torch.float64, device="cuda")
+    for _ in range(10):
+        ib.engine.run_protocols(system, progs, n, steps, 1.0, seed=1, x_cache=cache, outs=bufs, moments_out=mom)
+    torch.cuda.synchronize()
+    bev = []
+    for _ in range(reps):
+        flush.zero_()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ib.engine.run_protocols(system, progs, n, steps, 1.0, seed=1, x_cache=cache, outs=bufs, moments_out=mom)
+        e.record()
+        bev.append((a, e))
+    torch.cuda.synchronize()
+    batch_ms = sum(a.elapsed_time(e) for a, e in bev) / reps
+    Wb = bufs[0]["W"].double().sum().item()
     print(json.dumps({"variant": os.environ.get("LSI_VARIANT", "default"), "ms": [round(m, 4) for m in ms], "sum_ms": round(sum(ms), 4),
-                      "replica_steps_per_s": 6 * n * 2 * steps / sum(ms) * 1e3, "checksum_W_OVRVO": W}))
+                      "replica_steps_per_s": 6 * n * 2 * steps / sum(ms) * 1e3, "checksum_W_OVRVO": W, "batch_ms": round(batch_ms, 4),
+                      "batch_replica_steps_per_s": 6 * n * 2 * steps / batch_ms * 1e3, "batch_checksum_equal": W == Wb}))
 
 
 if __name__ == "__main__":

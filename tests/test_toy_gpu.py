@@ -389,7 +389,7 @@ def test_batch_launch_equals_individual_launches(ib, orc, kind, precision):
     cache = _cache(orc, kind)
     system = ib.engine.ScalarSystem(kind, 10.0)
     six_letter = ["O V R R V O", "V R O O R V", "R V O O V R"]
-    cases = [SIX, six_letter, [SIX[4], SIX[0], SIX[2]], [SIX[0], six_letter[1]], [SIX[1], SIX[1]], [SIX[0], "R V O"],
+    cases = [SIX, six_letter, SIX[::-1], six_letter[:2], six_letter[1::-1], [SIX[4], SIX[0], SIX[2]], [SIX[0], six_letter[1]], [SIX[1], SIX[1]], [SIX[0], "R V O"],
              [SIX[3]]]
     for n, steps in [(3001, 9), (700, 4)]:
         for strings in cases:
@@ -400,14 +400,24 @@ def test_batch_launch_equals_individual_launches(ib, orc, kind, precision):
             batch = ib.engine.run_protocols(system, progs, n, steps, 1.0, seed=3, replica0=77, x_cache=cache, precision=precision,
                                             want_heat=True, want_final=True, moments_out=mom)
             for i, (s, b) in enumerate(zip(singles, batch)):
-                for key in ("W", "heat", "x_final", "v_final", "moments"):
+                for key in ("W", "heat", "x_final", "v_final"):
                     assert torch.equal(s[key], b[key]), (strings, i, key)
-                assert torch.equal(mom[i], s["moments"])
+                # moment sums: same terms, possibly another summation order (the whole-family kernel maps replicas to
+                # threads differently); the count of finite pairs is exact
+                assert torch.equal(mom[i], b["moments"]) and mom[i][0] == s["moments"][0] and mom[i][6] == s["moments"][6]
+                torch.testing.assert_close(mom[i], s["moments"], rtol=1e-11, atol=1e-9)
     # "full" marginal and explicit start states travel through the batch as well
     x0 = cache[:500].copy()
     v0 = np.linspace(-0.3, 0.3, 500)
     progs = [ib.engine.Program(s, 0.2, 5.0) for s in SIX]
     singles = [ib.engine.run_protocol(system, p, 500, 7, 1.0, marginal="full", seed=9, x0=x0, v0=v0, precision=precision, out={}) for p in progs]
     batch = ib.engine.run_protocols(system, progs, 500, 7, 1.0, marginal="full", seed=9, x0=x0, v0=v0, precision=precision)
+    for s, b in zip(singles, batch):
+        assert torch.equal(s["W"], b["W"])
+        torch.testing.assert_close(b["moments"], s["moments"], rtol=1e-11, atol=1e-9)
+    # programs of one family compiled with different time steps share no (a, b sigma): still one launch, still identical
+    progs = [ib.engine.Program(s, 0.1 + 0.05 * i, 5.0 + i) for i, s in enumerate(SIX)]
+    singles = [ib.engine.run_protocol(system, p, 2000, 9, 1.0, seed=4, x_cache=cache, precision=precision, out={}) for p in progs]
+    batch = ib.engine.run_protocols(system, progs, 2000, 9, 1.0, seed=4, x_cache=cache, precision=precision)
     for s, b in zip(singles, batch):
         assert torch.equal(s["W"], b["W"]) and torch.equal(s["moments"], b["moments"])
