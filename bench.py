@@ -13,9 +13,9 @@ One bench "step" = one pass over the batch = the fused protocol (forward leg, mi
 every splitting -- scalar systems: all splittings in ONE launch (lsi_run_protocol_batch), particle systems: one launch per
 splitting -- + the DeltaF_neq moment reduction, all-reduced over ranks.
   value     device-resident throughput: inputs in HBM, CUDA events around every step, L2 flushed (untimed) between steps,
-            max over ranks.  The moment all-reduce of step s is started inside the timed interval of step s + 1 and
-            overlaps its kernels (moments are additive; nothing downstream needs them earlier); the last ones are
-            drained inside the timed region.
+            max over ranks.  The moment vectors of 8 consecutive steps travel in one all-reduce that overlaps the following
+            steps (moments are additive; nothing downstream needs them earlier); the last ones are drained inside the
+            timed region.
   e2e       the same work through the reference-facing drop-in call with DEFAULT arguments, as a reference caller makes it
             (NumbaNonequilibriumSimulator.collect_protocol_samples / NonequilibriumSimulator.collect_protocol_samples):
             host-side equilibrium cache uploaded every call, numpy results on the host (the toy call returns the full
@@ -108,7 +108,7 @@ def workload_config(name, W, n, plen):
            "system": name, "gamma": W["gamma"], "dt": W["dt"], "kT": W["kT"], "marginal": "configuration",
            "splittings": list(W["splittings"].values()), "replicas_per_gpu": n, "protocol_length": plen, "precision": W["precision"],
            "l2": "flushed between timed steps (256 MiB memset, untimed)",
-           "parallelism": "replica shards, no data-path collective; moment all-reduce per step, overlapped with the next step"}
+           "parallelism": "replica shards, no data-path collective; one moment all-reduce per 8 steps, overlapped with the following steps"}
     if W["kind"] == "toy":
         cfg["mass"], cfg["equilibrium_cache"] = W["mass"], W["n_cache"]
     return cfg
@@ -432,7 +432,7 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
         cache = eq.samples_device()
     programs = {k: engine.Program(s, W["dt"], W["gamma"]) for k, s in W["splittings"].items()}
     bufs = {k: {} for k in programs}
-    mom = [torch.zeros(S, 8, dtype=torch.float64, device=dev) for _ in range(2)]
+    mom = torch.zeros(16, S, 8, dtype=torch.float64, device=dev)  # ring of 2 x GROUP rows (GROUP = 8 below)
     pending = [None, None]
 
     def launch(k, prog, x_cache_dev, moments_out=None):
@@ -448,20 +448,28 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
             for j, (k, prog) in enumerate(programs.items()):
                 launch(k, prog, cache, moments_out[j])
 
+    GROUP = 8  # bench steps whose moment vectors travel in one all-reduce
+
     def one_pass(i):
-        """bench step i: the all-reduce of step i - 1 starts now (NCCL's stream) and overlaps this step's kernels; this
-        step's moment buffer is free again once the all-reduce of step i - 2 has finished (stream-ordered wait)"""
-        b = i & 1
-        if i > 0:
-            pending[b ^ 1] = parallel.all_reduce_moments_async(mom[b ^ 1])
-        if pending[b] is not None:
-            pending[b].wait()
-            pending[b] = None
-        launch_all(mom[b])
+        """bench step i writes its S x 8 moment vectors into row i % (2 GROUP) of a ring; every GROUP steps the finished
+        group of rows is all-reduced in ONE collective, started on NCCL's stream after this step's launch so that it overlaps
+        the following steps (moments are additive and nothing downstream needs them earlier); a group's rows are reused only
+        after its all-reduce has finished (stream-ordered wait, no host block)"""
+        row = i % (2 * GROUP)
+        half = row // GROUP
+        if row % GROUP == 0 and pending[half] is not None:
+            pending[half].wait()
+            pending[half] = None
+        launch_all(mom[row])
+        if row % GROUP == GROUP - 1:
+            pending[half] = parallel.all_reduce_moments_async(mom[half * GROUP:(half + 1) * GROUP])
 
     def drain(i_last):
-        b = i_last & 1
-        pending[b] = parallel.all_reduce_moments_async(mom[b])
+        """all-reduce the rows of the unfinished group, wait for everything in flight"""
+        row = i_last % (2 * GROUP)
+        half = row // GROUP
+        if row % GROUP != GROUP - 1:
+            pending[half] = parallel.all_reduce_moments_async(mom[half * GROUP:row + 1])
         for q in (0, 1):
             if pending[q] is not None:
                 pending[q].wait()
@@ -525,7 +533,7 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
     torch.cuda.synchronize()
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / k_reps for k, v in kev.items()}
     batch_ms = sum(a.elapsed_time(b) for a, b in bev) / k_reps if bev else None
-    estimates_dev = [ib.evaluation.estimate_from_moments(mom[(steps - 1) & 1][j].cpu().numpy()) for j in range(S)]
+    estimates_dev = [ib.evaluation.estimate_from_moments(mom[(steps - 1) % 16][j].cpu().numpy()) for j in range(S)]
 
     # ---- end to end through the reference-facing call (host cache in, numpy out)
     n_e2e = min(n, W["e2e_replicas"])
@@ -610,9 +618,13 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
                 "loop (twice the pair evaluations, no atomics) with fp64 constraints and bookkeeping")
     achieved = sum(fl[k] * n * 2 * nsl for k in programs) / kernel_s / 1e12
     hpk, hsrc = hbm_peak()
-    hbm_bytes = S * n * (8 + 16) if toy else S * n * (24 * system.n_atoms + 16)  # per pass: start state in, two works out
+    # per pass: start state in, two works out per splitting (the toy batch launch gathers the start state once for all splittings)
+    hbm_bytes = n * (8 + 16 * S) if toy else S * n * (24 * system.n_atoms + 16)
     roofline = {"bound": bound, "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": 8.04e6 if (name == "double_well" and n == (1 << 20)) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one toy_family_kernel launch, ncu --set full
+                # (profiles/r2f_toy_family_ncu_details.txt: 8.2 MB read, 43-45 MB written; the rest of the 100 MB of works is still
+                # in L2 when the kernel ends)
+                "traffic": 5.2e7 if (name == "double_well" and n == (1 << 20) and S == 6) else None,
                 "peak_source": "lsi_microbench_fma, best of 6, measured in this run (fp64 %.1f, fp32 %.1f TFLOP/s)" % (peaks["fp64"], peaks["fp32"]),
                 "note": note, "replica_steps_per_s_kernel_only": units_per_pass / kernel_s, "kernel_ms_per_splitting": kernel_ms,
                 "kernel_ms_batch_launch": batch_ms,
