@@ -120,6 +120,9 @@ __global__ void __launch_bounds__(kThreads) logmeanexp_kernel(const double* __re
         double mx = -INFINITY;
         for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) mx = fmax(mx, -w[i]);
         mx = block_max(mx, sh);
+        // rows whose largest term is +-inf (all works +inf, or a work of -inf): no shift, so that the sums come out as the
+        // reference's naive formula gives them (0 -> log 0 = -inf, inf -> inf) instead of inf - inf = NaN
+        if (!isfinite(mx)) mx = 0.0;
         double s1 = 0.0, s2 = 0.0;
         for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
             const double e = exp(-w[i] - mx);

@@ -40,6 +40,10 @@ def test_logmeanexp_matches_reference_fixtures_and_numpy(ib, golden_dir):
         ex = np.exp(-r - shift)
         assert e == pytest.approx(np.log(ex.mean()) + shift, rel=1e-12, abs=1e-12)
         assert s_ == pytest.approx(np.std(ex) / (ex.mean() * np.sqrt(len(r))), rel=1e-9, abs=1e-15)
+    # infinite works give what the reference's naive formula gives, not NaN: all +inf -> log(0) = -inf, a -inf -> +inf
+    est, _ = ib.engine.reduce_logmeanexp([np.array([np.inf, np.inf]), np.array([0.5, -np.inf, 1.0]), np.array([np.inf, 0.0])])
+    est = est.cpu().numpy()
+    assert est[0] == -np.inf and est[1] == np.inf and est[2] == pytest.approx(np.log(0.5))
     outer = [{"Ws": r} for r in rows[1:4]]
     per = np.array([np.log(np.mean(np.exp(-r))) for r in rows[1:4]])
     assert nested.stdev_kl_div(outer) == pytest.approx(np.std(per) / np.sqrt(3), rel=1e-10)
