@@ -116,9 +116,9 @@ def workload_config(name, W, n, plen):
 
 class ClockSampler:
     """SM clock + clock-event reasons sampled DURING the timed region (NVML from a thread, every
-    ~2 ms; the nvidia-smi -lms loop of the profiling recipe cannot resolve a region this short)."""
+    ~0.5 ms; the nvidia-smi -lms loop of the profiling recipe cannot resolve a region this short)."""
 
-    def __init__(self, gpu_index=0, period_s=0.002):
+    def __init__(self, gpu_index=0, period_s=0.0005):
         import threading
         self.rows, self.marks, self._stop = [], [], threading.Event()
         self.ok = False

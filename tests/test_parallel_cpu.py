@@ -44,7 +44,17 @@ def _worker(rank, world, port, out_dir):
     rsum = torch.exp(part - rmax[:, None]).sum(dim=1)
     cnt = torch.full((4,), float(chi - clo), dtype=torch.float64)
     lme = parallel.all_reduce_logmeanexp(rmax, rsum, cnt)
-    np.save(os.path.join(out_dir, "r%d.npy" % rank), np.concatenate([[dF, var], lme.numpy(), [lo, hi]]))
+    # the bench's grouped exchange: a slice of a ring of moment rows travels in one asynchronous all-reduce, the other rows
+    # are untouched; ranks hand out replica ids (Philox streams) from disjoint ranges
+    from integrator_benchmark_b200 import _rngstate
+    ring = torch.zeros(4, 3, 8, dtype=torch.float64)
+    ring[:] = torch.arange(4, dtype=torch.float64)[:, None, None] + 10.0 * (rank + 1)
+    h = parallel.all_reduce_moments_async(ring[1:3])
+    h.wait()
+    ok_ring = bool((ring[0] == 10.0 * (rank + 1)).all() and (ring[3] == 3.0 + 10.0 * (rank + 1)).all()
+                   and (ring[1] == 2 * 1.0 + 30.0).all() and (ring[2] == 2 * 2.0 + 30.0).all())
+    ok_ids = (_rngstate.reserve_replicas(10) >> _rngstate.RANK_SHIFT) == rank
+    np.save(os.path.join(out_dir, "r%d.npy" % rank), np.concatenate([[dF, var], lme.numpy(), [lo, hi], [float(ok_ring), float(ok_ids)]]))
     dist.destroy_process_group()
 
 
@@ -63,6 +73,7 @@ def test_gloo_world2_matches_single_process(tmp_path):
         assert g[0] == pytest.approx(dF, rel=1e-12, abs=1e-14) and g[1] == pytest.approx(var, rel=1e-10)
         np.testing.assert_allclose(g[2:6], lme, rtol=1e-12)
     assert (got[0][6], got[0][7], got[1][6], got[1][7]) == (0, 501, 501, 1001)
+    assert all(g[8] == 1.0 and g[9] == 1.0 for g in got)
 
 
 def _fake_outer_sample(noneq_sim=None, marginal=None, n_steps=None):

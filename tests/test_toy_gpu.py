@@ -421,3 +421,34 @@ def test_batch_launch_equals_individual_launches(ib, orc, kind, precision):
     batch = ib.engine.run_protocols(system, progs, 2000, 9, 1.0, seed=4, x_cache=cache, precision=precision)
     for s, b in zip(singles, batch):
         assert torch.equal(s["W"], b["W"]) and torch.equal(s["moments"], b["moments"])
+
+
+def test_family_launch_at_baseline_size(ib):
+    """BASELINE configs[1] at full size (2^20 replicas, protocol_length 10, the six splittings in one launch) through the
+    size-independent properties: a shard of the ensemble reproduces its slice of the full run bit for bit (what multi-GPU
+    weak scaling relies on), two programs run separately agree bit for bit with the batch, the moment vector agrees with a
+    reduction of the returned works, and the works are finite with the sign structure of the schemes (VRORV ~ 0, OVRVO > 0)."""
+    import torch
+    from integrator_benchmark_b200.testsystems import double_well
+    n, steps = 1 << 20, 9
+    system = ib.engine.ScalarSystem("double_well", 10.0)
+    cache = torch.from_numpy(double_well.collect_equilibrium_samples(1000000, n_burn=200, seed=12)).cuda()
+    progs = [ib.engine.Program(s, 0.35, 10.0) for s in SIX]
+    mom = torch.zeros(6, 8, dtype=torch.float64, device="cuda")
+    full = ib.engine.run_protocols(system, progs, n, steps, 1.0, seed=21, replica0=0, x_cache=cache, moments_out=mom)
+    W = [o["W"].clone() for o in full]
+    for lo, hi in [(0, n // 2), (n // 2, n), (n - 1000, n)]:
+        part = ib.engine.run_protocols(system, progs, hi - lo, steps, 1.0, seed=21, replica0=lo, x_cache=cache)
+        for p in range(6):
+            assert torch.equal(part[p]["W"], W[p][:, lo:hi])
+    for p in (0, 4):
+        single = ib.engine.run_protocol(system, progs[p], n, steps, 1.0, seed=21, replica0=0, x_cache=cache, out={})
+        assert torch.equal(single["W"], W[p])
+    for p in range(6):
+        assert bool(torch.isfinite(W[p]).all())
+        m = ib.engine.reduce_moments(W[p][0], W[p][1])
+        torch.testing.assert_close(mom[p][:7], m[:7], rtol=1e-11, atol=1e-7)
+        assert mom[p][0].item() == n and mom[p][6].item() == 0
+    dF = {s: ib.evaluation.estimate_from_moments(mom[i].cpu().numpy()) for i, s in enumerate(SIX)}
+    assert abs(dF["V R O R V"][0]) < 5 * dF["V R O R V"][1] ** 0.5 + 2e-4      # BAOAB: configuration-space error ~ 0 at this dt
+    assert dF["O V R V O"][0] > 10 * dF["O V R V O"][1] ** 0.5                   # OVRVO: clearly positive
