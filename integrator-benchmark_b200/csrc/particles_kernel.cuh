@@ -722,10 +722,13 @@ static __device__ __forceinline__ void star_velocities(const double (&x)[4][3], 
 }
 
 // generic clusters (anything that is not a water or a small star): Gauss-Seidel SHAKE / RATTLE in
-// shared memory by the cluster's owner lane
+// shared memory by the cluster's owner lane.  A cluster that has not converged after 500 sweeps is not left silently
+// off the constraint manifold: its first coordinate becomes NaN, so the replica's works are NaN and the replica is counted
+// as crashed (moments[6]), like any other diverged trajectory.
 static __device__ __noinline__ void shake_cluster(const int32_t* pairs, const double* dist, double tol, const double* mass, const double* x0,
                                            double* x1, int c0, int c1)
 {
+    bool converged = c1 <= c0;
     for (int it = 0; it < 500; ++it) {
         bool done = true;
         for (int k = c0; k < c1; ++k) {
@@ -747,13 +750,15 @@ static __device__ __noinline__ void shake_cluster(const int32_t* pairs, const do
                 x1[3 * j + c] += gl * sv[c] * imj;
             }
         }
-        if (done) break;
+        if (done) { converged = true; break; }
     }
+    if (!converged) x1[3 * pairs[2 * c0]] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
 static __device__ __noinline__ void rattle_cluster(const int32_t* pairs, const double* dist, double tol, const double* mass, const double* x,
                                             double* v, int c0, int c1)
 {
+    bool converged = c1 <= c0;
     for (int it = 0; it < 500; ++it) {
         bool done = true;
         for (int k = c0; k < c1; ++k) {
@@ -774,8 +779,9 @@ static __device__ __noinline__ void rattle_cluster(const int32_t* pairs, const d
                 v[3 * j + c] += gl * r[c] * imj;
             }
         }
-        if (done) break;
+        if (done) { converged = true; break; }
     }
+    if (!converged) v[3 * pairs[2 * c0]] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
 // ------------------------------------------------------------------------------------------ units
