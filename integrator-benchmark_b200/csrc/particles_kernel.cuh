@@ -802,8 +802,8 @@ static __device__ __noinline__ N3 normals3_f32(uint64_t seed, uint64_t rid, uint
 {
     const lsi::Philox4 r = lsi::philox_block(seed, rid, draw, tag, unit);
     float a, b, c, d;
-    lsi::box_muller(r.x, r.y, a, b);
-    lsi::box_muller(r.z, r.w, c, d);
+    lsi::box_muller_sfu(r.x, r.y, a, b);
+    lsi::box_muller_sfu(r.z, r.w, c, d);
     N3 n;
     n.x = (double)a; n.y = (double)b; n.z = (double)c;
     return n;

@@ -112,7 +112,28 @@ __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, double& n0,
     n1 = rad * s;
 }
 
-// fp32 Box-Muller (mixed precision paths); accurate logf / sincospif, not the fast intrinsics
+// fp32 Box-Muller (mixed precision paths: the O noise of LSI_PRECISION_MIXED, as OpenMM's mixed mode draws single-precision
+// gaussians).  Same uniforms and the same formula as the oracle's fp32 restatement (24-bit words, rad = sqrt(-2 ln u1),
+// (cos, sin)(2 pi u2)), evaluated with the special-function unit: lg2.approx (absolute error 2^-22 on [0.5, 2], 2 ulp elsewhere),
+// sqrt.approx, and sin / cos.approx on the angle shifted into [-pi, pi] (absolute error 2^-21.4) -- a normal carries an absolute
+// error of at most ~2e-6, ten fp32 ulps of a typical draw, against the libm evaluation; 14 instructions per pair instead of ~85
+// (the O noise was 10 % of all instructions of the water cluster and alanine dipeptide, 20 % for two-O splittings).
+__device__ __forceinline__ void box_muller_sfu(uint32_t ra, uint32_t rb, float& n0, float& n1)
+{
+    const float u1 = ((float)(ra >> 8) + 0.5f) * 5.9604644775390625e-8f;         // 24 bits -> (0, 1]
+    const float u2x2 = ((float)(rb >> 8) + 0.5f) * 1.1920928955078125e-7f;       // 2 * u2 in (0, 2]
+    float lg, rad, s, c;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(lg * -1.3862943611198906f));  // -2 ln u1
+    const float x = fmaf(u2x2, 3.14159265358979f, -3.14159265358979f);              // 2 pi u2 - pi in (-pi, pi]
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(x));
+    n0 = -rad * c;  // cos(x + pi) = -cos x
+    n1 = -rad * s;
+}
+
+// the same pair with the accurate library functions (scalar systems' "mixed" mode: a 1-DOF double well amplifies a 1e-6
+// difference in a normal beyond the 1e-5 parity bar within ten steps, so its fp32 noise stays within an ulp of the oracle's)
 __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& n0, float& n1)
 {
     const float u1 = ((float)(ra >> 8) + 0.5f) * 5.9604644775390625e-8f;         // 24 bits -> (0, 1)
