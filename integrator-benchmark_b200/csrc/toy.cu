@@ -732,13 +732,21 @@ __global__ void __launch_bounds__(kF2Threads, LSI_TOY2_MINB) toy_fused2_batch_ke
 // Per-program arithmetic is the single-program kernel's, instruction for instruction: works are bit-identical.
 // Requires (checked on the host): every slot of the family enabled, and all programs with the same number of O
 // substeps share (a, b sigma) -- true when they were compiled with the same time step and collision rate.
+// threads per CTA (one CTA per SM) by the number of programs a thread carries: six chains per thread need 164 registers
+// (384 threads); two or three chains leave room for more warps
 #ifndef LSI_TOY3_THREADS
 #define LSI_TOY3_THREADS 384
+#endif
+#ifndef LSI_TOY3_THREADS_NP3
+#define LSI_TOY3_THREADS_NP3 512
+#endif
+#ifndef LSI_TOY3_THREADS_NP2
+#define LSI_TOY3_THREADS_NP2 768
 #endif
 #ifndef LSI_TOY3_PIPE
 #define LSI_TOY3_PIPE 0
 #endif
-constexpr int kF3Threads = LSI_TOY3_THREADS;
+constexpr int family_threads(int np) { return np >= 4 ? LSI_TOY3_THREADS : (np == 3 ? LSI_TOY3_THREADS_NP3 : LSI_TOY3_THREADS_NP2); }
 
 template <int NOPS, uint32_t... CODES>
 struct Family {
@@ -766,7 +774,7 @@ __device__ __forceinline__ void for_each_slot(F&& f, std::integer_sequence<int, 
 }
 
 constexpr int kF3Acc = 6;  // count, sum wF, sum wR, sum wF^2, sum wR^2, sum wF wR per program (non-finite pairs = replicas seen - count)
-constexpr size_t family_smem(int np) { return (size_t)fm::TabView::kBytes + (size_t)np * kF3Acc * kF3Threads * sizeof(double); }
+constexpr size_t family_smem(int np) { return (size_t)fm::TabView::kBytes + (size_t)np * kF3Acc * family_threads(np) * sizeof(double); }
 
 // the shared part of one Box-Muller pair, and its completion for one scale (b sigma of a class of programs): the same
 // instruction sequence as box_muller_tab / the fp32 path of normal_block_part, split where the scale enters
@@ -805,10 +813,11 @@ __device__ __forceinline__ void pair_scaled(const PairCore& k, double scale, dou
 }
 
 template <int POT, bool NOISE32, int NOPS, uint32_t... CODES>
-__global__ void __launch_bounds__(kF3Threads, 1) toy_family_kernel(const __grid_constant__ ToyBatchParams B)
+__global__ void __launch_bounds__(family_threads((int)sizeof...(CODES)), 1) toy_family_kernel(const __grid_constant__ ToyBatchParams B)
 {
     using Fam = Family<NOPS, CODES...>;
     constexpr int NP = Fam::NP;
+    constexpr int kF3Threads = family_threads(NP);
     constexpr bool C1 = Fam::has_class(1), C2 = Fam::has_class(2);
     constexpr int S1 = Fam::first_of_class(1), S2 = Fam::first_of_class(2);
     static_assert(C1 || C2, "every program of a family has one or two O substeps per step");
@@ -1349,17 +1358,17 @@ static cudaError_t launch_family2(int family, unsigned grid, const ToyBatchParam
         auto k = toy_family_kernel<POT, NOISE32, 5 LSI_FAMILY_FIVE(X)>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)family_smem(6));
         if (e != cudaSuccess) return e;
-        k<<<grid, kF3Threads, family_smem(6), st>>>(B);
+        k<<<grid, family_threads(6), family_smem(6), st>>>(B);
     } else if (family == 1) {
         auto k = toy_family_kernel<POT, NOISE32, 6 LSI_FAMILY_SIX(X)>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)family_smem(3));
         if (e != cudaSuccess) return e;
-        k<<<grid, kF3Threads, family_smem(3), st>>>(B);
+        k<<<grid, family_threads(3), family_smem(3), st>>>(B);
     } else {
         auto k = toy_family_kernel<POT, NOISE32, 6 LSI_FAMILY_PAIR(X)>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)family_smem(2));
         if (e != cudaSuccess) return e;
-        k<<<grid, kF3Threads, family_smem(2), st>>>(B);
+        k<<<grid, family_threads(2), family_smem(2), st>>>(B);
     }
 #undef X
     return cudaGetLastError();
@@ -1449,7 +1458,7 @@ int lsi_toy_run_protocol_batch(const lsi_system* sys, const lsi_program* const* 
     unsigned grid;
     cudaError_t err;
     if (whole_family) {
-        grid = persistent_grid(a0.n_replicas, kF3Threads, 1);
+        grid = persistent_grid(a0.n_replicas, family_threads(family_kernel == 0 ? 6 : (family_kernel == 1 ? 3 : 2)), 1);
         err = launch_family(sys->potential, a0.precision == LSI_PRECISION_MIXED, family_kernel, grid, B, st);
     } else {
         grid = fused2_grid(a0.n_replicas);

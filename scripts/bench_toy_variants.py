@@ -17,11 +17,19 @@ SPLITTINGS = ["O V R V O", "O R V R O", "R V O V R", "R O V O R", "V R O R V", "
 def child():
     import torch
     import integrator_benchmark_b200 as ib
-    n, steps = 1 << 20, int(os.environ.get("TOY_STEPS", 9))
-    system = ib.engine.ScalarSystem("double_well", 10.0)
-    from integrator_benchmark_b200.testsystems import double_well
-    cache = torch.from_numpy(double_well.collect_equilibrium_samples(1000000, n_burn=100, seed=2)).cuda()
-    progs = [ib.engine.Program(s, 0.35, 10.0) for s in SPLITTINGS]
+    from integrator_benchmark_b200.testsystems import double_well, quartic
+    if os.environ.get("TOY_CASE", "c2") == "c1":  # quartic, the reference's vvvr + baoab closure strings, protocol_length 100
+        global SPLITTINGS
+        SPLITTINGS = ["O V R R V O", "V R O O R V"]
+        n, steps = 1 << 20, int(os.environ.get("TOY_STEPS", 99))
+        system = ib.engine.ScalarSystem("quartic", 10.0)
+        cache = torch.from_numpy(quartic.collect_equilibrium_samples(1000000, n_burn=100, seed=2)).cuda()
+        progs = [ib.engine.Program(s, 1.1, 100.0) for s in SPLITTINGS]
+    else:
+        n, steps = 1 << 20, int(os.environ.get("TOY_STEPS", 9))
+        system = ib.engine.ScalarSystem("double_well", 10.0)
+        cache = torch.from_numpy(double_well.collect_equilibrium_samples(1000000, n_burn=100, seed=2)).cuda()
+        progs = [ib.engine.Program(s, 0.35, 10.0) for s in SPLITTINGS]
     bufs = [{} for _ in SPLITTINGS]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(20):
@@ -44,7 +52,7 @@ def child():
         ms[j] += a.elapsed_time(e) / reps
     W = bufs[0]["W"].double().sum().item()
     # the six programs as one batch launch (lsi_run_protocol_batch)
-    mom = torch.zeros(6, 8, dtype=torch.float64, device="cuda")
+    mom = torch.zeros(len(progs), 8, dtype=torch.float64, device="cuda")
     for _ in range(10):
         ib.engine.run_protocols(system, progs, n, steps, 1.0, seed=1, x_cache=cache, outs=bufs, moments_out=mom)
     torch.cuda.synchronize()
@@ -60,8 +68,8 @@ def child():
     batch_ms = sum(a.elapsed_time(e) for a, e in bev) / reps
     Wb = bufs[0]["W"].double().sum().item()
     print(json.dumps({"variant": os.environ.get("LSI_VARIANT", "default"), "ms": [round(m, 4) for m in ms], "sum_ms": round(sum(ms), 4),
-                      "replica_steps_per_s": 6 * n * 2 * steps / sum(ms) * 1e3, "checksum_W_OVRVO": W, "batch_ms": round(batch_ms, 4),
-                      "batch_replica_steps_per_s": 6 * n * 2 * steps / batch_ms * 1e3, "batch_checksum_equal": W == Wb}))
+                      "replica_steps_per_s": len(progs) * n * 2 * steps / sum(ms) * 1e3, "checksum_W_OVRVO": W, "batch_ms": round(batch_ms, 4),
+                      "batch_replica_steps_per_s": len(progs) * n * 2 * steps / batch_ms * 1e3, "batch_checksum_equal": W == Wb}))
 
 
 if __name__ == "__main__":
