@@ -34,7 +34,10 @@
 extern "C" {
 #endif
 
-#define LSI_ABI_VERSION 2
+/* 3: lsi_run_protocol_batch added; scalar systems draw the start velocity, the midpoint velocity and the cache index of a
+ *    replica from ONE start block (results of version-2 libraries are not reproduced for scalar systems);
+ *    LSI_PRECISION_MIXED evaluates the fp32 O noise of particle systems with the special-function unit */
+#define LSI_ABI_VERSION 3
 
 /* error codes; the Python shim maps them to the exception types the reference raises */
 #define LSI_OK 0
@@ -188,11 +191,13 @@ int lsi_system_num_dof(const lsi_system* s);
  * and accumulate_shadow_work (bookkeepers.py:184-295) for a whole ensemble in one launch.
  *
  * Per replica r (global id replica0 + r, which alone keys its RNG streams):
- *   leg 0: x0 = x0[r] if given, else x_cache[index drawn from TAG_X0];
- *          v0 = v0[r] if given, else sqrt(kT/m) * N(0,1) from TAG_V0
+ *   leg 0: x0 = x0[r] if given, else x_cache[index]; v0 = v0[r] if given, else sqrt(kT/m) * N(0,1).
+ *          Particle systems: index from lane 0 of the block (draw 0, TAG_X0), velocities from TAG_V0 (unit = atom).
+ *          Scalar systems: ONE start block (draw 0, TAG_V0, unit 0) per replica: words 0, 1 -> the Box-Muller pair
+ *          (start-velocity normal, midpoint-velocity normal), word 2 -> index = (word * n_cache) >> 32
  *   leg l>0: x continues; v is redrawn (configuration) or kept (full).  Particle systems redraw from TAG_VMID
- *          (draw l - 1, unit = atom); scalar systems take normal number l of the replica's TAG_V0 scalar stream, so
- *          the start and the midpoint velocity of a two-leg protocol are the two halves of one Box-Muller pair
+ *          (draw l - 1, unit = atom); scalar systems take the second normal of the start block for leg 1 and normal l - 2 of
+ *          the TAG_V0 stream that begins at draw 1 for legs l >= 2
  *   each leg applies the program n_steps times and yields
  *          W = ((E_end - E_start) - (heat_end - heat_start)) / kT
  * Particle systems: states are [replica][atom][3] (x_cache [n_cache][atom][3]); before each leg

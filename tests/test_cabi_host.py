@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "liblsi.so does not export %s" % n
     # and the ctypes binding covers each of them
     assert set(names) == set(_cabi.EXPORTED)
-    assert _cabi.lib.lsi_abi_version() == 2
+    assert _cabi.lib.lsi_abi_version() == 3
 
 
 def test_compiler_matches_reference_constructor(golden_dir):
