@@ -18,7 +18,7 @@ splitting -- + the DeltaF_neq moment reduction, all-reduced over ranks.
             timed region.
   e2e       the same work through the reference-facing drop-in call with DEFAULT arguments, as a reference caller makes it
             (NumbaNonequilibriumSimulator.collect_protocol_samples / NonequilibriumSimulator.collect_protocol_samples):
-            host-side equilibrium cache uploaded every call, numpy results on the host (the toy call returns the full
+            host-side equilibrium cache uploaded every step, numpy results on the host (the toy call returns the full
             work and (x, v) traces, as the reference does).  Sub-keys give the same call with `traces=False` (final works
             only) and `as_numpy=False` (estimate only).
   roofline  dominant kernel alone (events around each launch) against the FMA peak measured in the same run.
@@ -549,7 +549,6 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
         h2d = int(eq.x_samples.nbytes)
 
         def call(sim, mode):
-            eq.release_device_cache()  # the host-side cache is uploaded again, as for a caller that owns it on the host
             if mode == "default":  # the reference's call: full work and (x, v) traces as numpy arrays
                 W_F, W_R, xv_F, xv_R = sim.collect_protocol_samples(n_e2e, plen, "configuration")
                 return ib.evaluation.estimate_nonequilibrium_free_energy(W_F[:, -1], W_R[:, -1]), W_F.nbytes + W_R.nbytes + xv_F.nbytes + xv_R.nbytes
@@ -568,7 +567,6 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
         h2d = int(eq.samples.nbytes)
 
         def call(sim, mode):
-            eq.release_device_cache()
             if mode == "default":  # the reference's call: {"W_shads_F", "W_shads_R"} as numpy arrays
                 r = sim.collect_protocol_samples(n_e2e, plen, "configuration")
                 return ib.evaluation.estimate_nonequilibrium_free_energy(r["W_shads_F"], r["W_shads_R"]), r["W_shads_F"].nbytes + r["W_shads_R"].nbytes
@@ -581,6 +579,7 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
     for mode in modes:
         d2h = 0
         for _ in range(2):  # first calls page-lock their staging buffers
+            eq.release_device_cache()
             for sim in sims.values():
                 call(sim, mode)
         ctx.barrier()
@@ -588,13 +587,16 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
         for _ in range(e2e_steps):
             d2h = 0
             ests = []
+            # the step's input, the host-side equilibrium cache, is uploaded again every step (the simulators of a step share
+            # their equilibrium simulator, as the reference's callers do, hence its device copy)
+            eq.release_device_cache()
             for sim in sims.values():
                 est, nbytes = call(sim, mode)
                 ests.append(est)
                 d2h += nbytes
         ctx.barrier()
         secs = ctx.max_over_ranks(time.perf_counter() - t0)
-        e2e[mode] = {"value": world * S * n_e2e * 2 * nsl * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": h2d * S,
+        e2e[mode] = {"value": world * S * n_e2e * 2 * nsl * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "replicas_per_call": n_e2e}
         if mode == "default":
             estimates_e2e = ests

@@ -56,6 +56,7 @@ LSI_EXPORT int lsi_run_protocol(const lsi_system* sys, const lsi_program* prog, 
 LSI_EXPORT int lsi_run_protocol_batch(const lsi_system* sys, const lsi_program* const* progs, int32_t n_progs,
                                       const lsi_protocol_args* args, void* stream)
 {
+    if (n_progs == 0) return LSI_OK;
     if (!sys || !progs || !args || n_progs < 0) return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol_batch: bad argument");
     for (int p = 0; p < n_progs; ++p)
         if (!progs[p]) return lsi_set_error(LSI_ERR_ARG, "lsi_run_protocol_batch: NULL program");

@@ -406,6 +406,10 @@ def test_batch_launch_equals_individual_launches(ib, orc, kind, precision):
                 # threads differently); the count of finite pairs is exact
                 assert torch.equal(mom[i], b["moments"]) and mom[i][0] == s["moments"][0] and mom[i][6] == s["moments"][6]
                 torch.testing.assert_close(mom[i], s["moments"], rtol=1e-11, atol=1e-9)
+    # degenerate batches: no program, no replica
+    assert ib.engine.run_protocols(system, [], 10, 3, 1.0, x_cache=cache) == []
+    empty = ib.engine.run_protocols(system, [ib.engine.Program(s, 0.35, 10.0) for s in SIX], 0, 3, 1.0, x_cache=cache, want_moments=False)
+    assert all(o["W"].shape == (2, 0) for o in empty)
     # "full" marginal and explicit start states travel through the batch as well
     x0 = cache[:500].copy()
     v0 = np.linspace(-0.3, 0.3, 500)
