@@ -380,14 +380,15 @@ def test_quartic_steady_state_histogram_matches_the_published_ground_truth(ib):
     assert 0.00007 < got["VRORV"] < 0.00019, got
 
 
-@pytest.mark.parametrize("kind,precision", [("double_well", "double"), ("quartic", "double"), ("double_well", "mixed")])
+@pytest.mark.parametrize("kind,precision", [("double_well", "double"), ("quartic", "double"), ("double_well", "mixed"),
+                                            ("harmonic", "double")])
 def test_batch_launch_equals_individual_launches(ib, orc, kind, precision):
     """lsi_run_protocol_batch == one lsi_run_protocol per program, bit for bit: the one-launch families (six 5-letter
     palindromes, the reference's three 6-letter closure strings), a permuted subset, and batches that fall back to
     separate launches (mixed families, a repeated program, a string outside the families)."""
     import torch
-    cache = _cache(orc, kind)
-    system = ib.engine.ScalarSystem(kind, 10.0)
+    cache = _cache(orc, "quartic" if kind == "harmonic" else kind)
+    system = ib.engine.ScalarSystem(kind, 10.0, (3.0, 0.0, 0.0, 0.0)) if kind == "harmonic" else ib.engine.ScalarSystem(kind, 10.0)
     six_letter = ["O V R R V O", "V R O O R V", "R V O O V R"]
     cases = [SIX, six_letter, SIX[::-1], six_letter[:2], six_letter[1::-1], [SIX[4], SIX[0], SIX[2]], [SIX[0], six_letter[1]], [SIX[1], SIX[1]], [SIX[0], "R V O"],
              [SIX[3]]]
@@ -419,6 +420,15 @@ def test_batch_launch_equals_individual_launches(ib, orc, kind, precision):
     for s, b in zip(singles, batch):
         assert torch.equal(s["W"], b["W"])
         torch.testing.assert_close(b["moments"], s["moments"], rtol=1e-11, atol=1e-9)
+    # one leg and three legs (legs >= 2 draw their start velocities from the TAG_V0 stream that begins at draw 1)
+    for n_legs in (1, 3):
+        progs = [ib.engine.Program(s, 0.3, 10.0) for s in SIX]
+        singles = [ib.engine.run_protocol(system, p, 1500, 6, 1.0, n_legs=n_legs, seed=8, x_cache=cache, precision=precision,
+                                          want_final=True, out={}) for p in progs]
+        batch = ib.engine.run_protocols(system, progs, 1500, 6, 1.0, n_legs=n_legs, seed=8, x_cache=cache, precision=precision,
+                                        want_final=True)
+        for s, b in zip(singles, batch):
+            assert s["W"].shape == (n_legs, 1500) and torch.equal(s["W"], b["W"]) and torch.equal(s["x_final"], b["x_final"])
     # programs of one family compiled with different time steps share no (a, b sigma): still one launch, still identical
     progs = [ib.engine.Program(s, 0.1 + 0.05 * i, 5.0 + i) for i, s in enumerate(SIX)]
     singles = [ib.engine.run_protocol(system, p, 2000, 9, 1.0, seed=4, x_cache=cache, precision=precision, out={}) for p in progs]
