@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(kF2Threads, LSI_TOY2_MINB) toy_fused2_batch_ke
 #define LSI_TOY3_THREADS_NP3 512
 #endif
 #ifndef LSI_TOY3_THREADS_NP2
-#define LSI_TOY3_THREADS_NP2 768
+#define LSI_TOY3_THREADS_NP2 1024
 #endif
 #ifndef LSI_TOY3_PIPE
 #define LSI_TOY3_PIPE 0

@@ -184,6 +184,20 @@ def test_mdtraj_hdf5_round_trip(tmp_path, n_frames, n_atoms):
     assert out["cell_lengths"] is None and out["potential_energy"] is None
 
 
+def test_mdtraj_hdf5_empty_and_large(tmp_path):
+    """edge cases: a trajectory without frames; more frames than 64 chunks of the default size (chunks grow, one leaf node)"""
+    h5, hmin = _h5()
+    path = str(tmp_path / "e.h5")
+    h5.save_mdtraj_hdf5(path, np.zeros((0, 4, 3), np.float32), cell_lengths=(1.0, 1.0, 1.0))
+    out = h5.load_mdtraj_hdf5(path, 4)
+    assert out["xyz"].shape == (0, 4, 3) and out["cell_lengths"].shape == (0, 3)
+    xyz = np.random.default_rng(0).normal(size=(5000, 700, 3)).astype(np.float32)  # 8400 B per frame: 7 frames per 64 KB chunk
+    h5.save_mdtraj_hdf5(path, xyz)
+    raw = hmin.read(path)
+    assert raw["coordinates"].chunks[0] >= 5000 / 64 and raw["coordinates"].chunks[1:] == (700, 3)
+    np.testing.assert_array_equal(h5.load_mdtraj_hdf5(path, 700)["xyz"], xyz)
+
+
 def test_mdtraj_hdf5_file_structure(tmp_path):
     """the bytes follow the HDF5 specification the way libhdf5 lays these files out: fixed-size B-tree nodes, 8-byte alignment,
     sorted symbol table, end-of-file address, chunk keys (size, mask, offsets) with the closing key"""
