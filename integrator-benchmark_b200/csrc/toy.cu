@@ -1406,9 +1406,12 @@ int lsi_toy_run_protocol_batch(const lsi_system* sys, const lsi_program* const* 
     cudaStream_t st = (cudaStream_t)stream;
     bool one_launch = n_progs >= 2 && n_progs <= kBatchMax && args[0].n_replicas > 0;
     ToyBatchParams B;
-    B.enabled = 0;
+    std::memset(&B, 0, sizeof(B));  // slots that stay disabled travel as zeros
     int family = -1;
     const lsi_protocol_args& a0 = args[0];
+    // (a, b sigma) of the programs with one / two O substeps per step: the whole-family kernel needs one pair per class
+    double class_oa[3] = {0, 0, 0}, class_oc[3] = {0, 0, 0};
+    bool class_seen[3] = {false, false, false}, classes_ok = true;
     for (int p = 0; p < n_progs && one_launch; ++p) {
         const lsi_protocol_args& a = args[p];
         ToyParams P;
@@ -1428,6 +1431,10 @@ int lsi_toy_run_protocol_batch(const lsi_system* sys, const lsi_program* const* 
         family = fam;
         B.enabled |= 1u << slot;
         B.P[slot] = P;
+        const int n_o = progs[p]->n_O;
+        if (n_o < 1 || n_o > 2) classes_ok = false;
+        else if (!class_seen[n_o]) { class_seen[n_o] = true; class_oa[n_o] = P.oa; class_oc[n_o] = P.oc; }
+        else if (class_oa[n_o] != P.oa || class_oc[n_o] != P.oc) classes_ok = false;
     }
     if (!one_launch) {
         for (int p = 0; p < n_progs; ++p) {
@@ -1438,23 +1445,8 @@ int lsi_toy_run_protocol_batch(const lsi_system* sys, const lsi_program* const* 
     }
     // the whole family, and one (a, b sigma) per number of O substeps: the shared-noise kernel (one replica per thread through
     // all programs); otherwise the programs run one after the other inside one launch
-    bool whole_family = B.enabled == (family == 0 ? 0x3Fu : 0x7u) || (family == 1 && B.enabled == 0x3u);
+    const bool whole_family = classes_ok && (B.enabled == (family == 0 ? 0x3Fu : 0x7u) || (family == 1 && B.enabled == 0x3u));
     const int family_kernel = (family == 1 && B.enabled == 0x3u) ? 2 : family;
-    {
-        double oa[3] = {0, 0, 0}, oc[3] = {0, 0, 0};
-        bool seen[3] = {false, false, false};
-        for (int p = 0; p < n_progs && whole_family; ++p) {
-            const int n_o = progs[p]->n_O;
-            if (n_o < 1 || n_o > 2) { whole_family = false; break; }
-            ToyParams P;
-            bool fusable;
-            uint32_t code;
-            int nops;
-            toy_prepare(sys, progs[p], &args[p], P, fusable, code, nops);
-            if (!seen[n_o]) { seen[n_o] = true; oa[n_o] = P.oa; oc[n_o] = P.oc; }
-            else if (oa[n_o] != P.oa || oc[n_o] != P.oc) whole_family = false;
-        }
-    }
     unsigned grid;
     cudaError_t err;
     if (whole_family) {
