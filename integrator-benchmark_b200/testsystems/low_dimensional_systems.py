@@ -151,7 +151,9 @@ class NumbaNonequilibriumSimulator:
                 W_F, W_R = W_F * kT, W_R * kT
             xv_F, xv_R = res["trace_xv"][0].permute(1, 0, 2), res["trace_xv"][1].permute(1, 0, 2)
         else:
-            W_F, W_R = res["W"][0].unsqueeze(1) * integ.kT, res["W"][1].unsqueeze(1) * integ.kT
+            W_F, W_R = res["W"][0].unsqueeze(1), res["W"][1].unsqueeze(1)
+            if integ.kT != 1.0:
+                W_F, W_R = W_F * integ.kT, W_R * integ.kT
             xv_F = xv_R = None
         if as_numpy:
             # one asynchronous copy per array into pinned host memory, one synchronisation (_staging.to_host)
