@@ -247,9 +247,14 @@ class _Reader:
 
 
 def read(path):
-    """{name: Dataset} of the root group's datasets; root attributes under "/"."""
+    """{name: Dataset} of the root group's datasets; root attributes under "/".  Anything that is not a well-formed file of the
+    supported kind -- wrong signature, unsupported structure, truncated or corrupt offsets -- raises ValueError."""
     with open(path, "rb") as f:
-        return _Reader(f.read()).read()
+        buf = f.read()
+    try:
+        return _Reader(buf).read()
+    except (struct.error, IndexError, zlib.error, OverflowError, MemoryError) as e:
+        raise ValueError("{}: truncated or corrupt HDF5 file ({}: {})".format(path, type(e).__name__, e))
 
 
 # ------------------------------------------------------------------------------------------------ writer

@@ -177,6 +177,12 @@ def test_mdtraj_hdf5_round_trip(tmp_path, n_frames, n_atoms):
     (tmp_path / "not.h5").write_bytes(b"hello")
     with pytest.raises(ValueError):
         h5.load_mdtraj_hdf5(str(tmp_path / "not.h5"), n_atoms)
+    # truncated and corrupted files are errors, not garbage frames
+    blob = open(path, "rb").read()
+    for cut in (50, 200, len(blob) // 2):
+        (tmp_path / "cut.h5").write_bytes(blob[:cut])
+        with pytest.raises(ValueError):
+            h5.load_mdtraj_hdf5(str(tmp_path / "cut.h5"), n_atoms)
     # without a cell and without energies (the water cluster, alanine dipeptide)
     h5.save_mdtraj_hdf5(path, xyz)
     out = h5.load_mdtraj_hdf5(path)
