@@ -392,7 +392,7 @@ def test_batch_launch_equals_individual_launches(ib, orc, kind, precision):
     six_letter = ["O V R R V O", "V R O O R V", "R V O O V R"]
     cases = [SIX, six_letter, SIX[::-1], six_letter[:2], six_letter[1::-1], [SIX[4], SIX[0], SIX[2]], [SIX[0], six_letter[1]], [SIX[1], SIX[1]], [SIX[0], "R V O"],
              [SIX[3]]]
-    for n, steps in [(3001, 9), (700, 4)]:
+    for n, steps in [(3001, 9), (700, 4), (1, 3), (33, 0), (385, 1), (2049, 2)]:
         for strings in cases:
             progs = [ib.engine.Program(s, 0.35, 10.0) for s in strings]
             singles = [ib.engine.run_protocol(system, p, n, steps, 1.0, seed=3, replica0=77, x_cache=cache, precision=precision,
