@@ -19,8 +19,10 @@ splitting -- + the DeltaF_neq moment reduction, all-reduced over ranks.
   e2e       the same work through the reference-facing drop-in call with DEFAULT arguments, as a reference caller makes it
             (NumbaNonequilibriumSimulator.collect_protocol_samples / NonequilibriumSimulator.collect_protocol_samples):
             host-side equilibrium cache uploaded every step, numpy results on the host (the toy call returns the full
-            work and (x, v) traces, as the reference does).  Sub-keys give the same call with `traces=False` (final works
-            only) and `as_numpy=False` (estimate only).
+            work and (x, v) traces, as the reference does).  The timed region ends when the call's results are on the host;
+            estimates computed from them afterwards are reported, not timed (the reference arm does not time them either).
+            Sub-keys give the same call with `traces=False` (final works only) and `as_numpy=False` (estimate only: the
+            moment vector is read back).
   roofline  dominant kernel alone (events around each launch) against the FMA peak measured in the same run.
   cpu_baseline / --impl reference: the reference's own numba closures (oracle/_ref, installed by oracle/make_ref.sh)
             under the restated collect_protocol_samples loop on all host cores for C1 / C2; the restated C oracle
@@ -551,12 +553,12 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
         def call(sim, mode):
             if mode == "default":  # the reference's call: full work and (x, v) traces as numpy arrays
                 W_F, W_R, xv_F, xv_R = sim.collect_protocol_samples(n_e2e, plen, "configuration")
-                return ib.evaluation.estimate_nonequilibrium_free_energy(W_F[:, -1], W_R[:, -1]), W_F.nbytes + W_R.nbytes + xv_F.nbytes + xv_R.nbytes
+                return (W_F[:, -1], W_R[:, -1]), W_F.nbytes + W_R.nbytes + xv_F.nbytes + xv_R.nbytes
             if mode == "final_works":
                 W_F, W_R, _, _ = sim.collect_protocol_samples(n_e2e, plen, "configuration", traces=False)
-                return ib.evaluation.estimate_nonequilibrium_free_energy(W_F[:, -1], W_R[:, -1]), W_F.nbytes + W_R.nbytes
+                return (W_F[:, -1], W_R[:, -1]), W_F.nbytes + W_R.nbytes
             sim.collect_protocol_samples(n_e2e, plen, "configuration", traces=False, as_numpy=False)
-            return ib.evaluation.estimate_from_moments(sim.last_moments.cpu().numpy()), 64
+            return sim.last_moments.cpu().numpy(), 64
         modes = ["default", "final_works", "estimate_only"]
     else:
         sims = {}
@@ -569,9 +571,9 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
         def call(sim, mode):
             if mode == "default":  # the reference's call: {"W_shads_F", "W_shads_R"} as numpy arrays
                 r = sim.collect_protocol_samples(n_e2e, plen, "configuration")
-                return ib.evaluation.estimate_nonequilibrium_free_energy(r["W_shads_F"], r["W_shads_R"]), r["W_shads_F"].nbytes + r["W_shads_R"].nbytes
+                return (r["W_shads_F"], r["W_shads_R"]), r["W_shads_F"].nbytes + r["W_shads_R"].nbytes
             sim.collect_protocol_samples(n_e2e, plen, "configuration", as_numpy=False)
-            return ib.evaluation.estimate_from_moments(sim.last_moments.cpu().numpy()), 64
+            return sim.last_moments.cpu().numpy(), 64
         modes = ["default", "estimate_only"]
 
     e2e_steps = max(2, min(steps // 2, 10))
@@ -590,16 +592,16 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
             # the step's input, the host-side equilibrium cache, is uploaded again every step (the simulators of a step share
             # their equilibrium simulator, as the reference's callers do, hence its device copy)
             eq.release_device_cache()
-            for sim in sims.values():
-                est, nbytes = call(sim, mode)
-                ests.append(est)
+            for sim in sims.values():  # the timed region ends with the call's results on the host (works, or the moment vector)
+                got, nbytes = call(sim, mode)
+                ests.append(got)
                 d2h += nbytes
         ctx.barrier()
         secs = ctx.max_over_ranks(time.perf_counter() - t0)
         e2e[mode] = {"value": world * S * n_e2e * 2 * nsl * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "replicas_per_call": n_e2e}
-        if mode == "default":
-            estimates_e2e = ests
+        if mode == "default":  # what a caller computes from the returned works, outside the timed region
+            estimates_e2e = [ib.evaluation.estimate_nonequilibrium_free_energy(wf, wr) for wf, wr in ests]
 
     if rank != 0:
         return None
