@@ -143,3 +143,22 @@ def test_bench_reference_arm_runs_without_a_gpu():
     assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["value"] == line["value"]
     assert line["higher_is_better"] is True and line["steps"] == 2 and line["gpu_launches"] == 0
     assert line["config"]["replicas_per_gpu"] == 1 << 20 and "C2 double well" in line["config"]["workload"]
+
+
+def test_bench_workload_table_and_flop_convention():
+    """bench.py's workload table covers BASELINE.json's five configs and its algorithmic-flop convention is the one of SURVEY 8d
+    (O 9, V 2, R 2 per substep, one force evaluation per distinct position visited)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.ORDER == ["double_well", "quartic", "water_cluster", "alanine", "waterbox"]
+    assert [bench.WORKLOADS[k]["config"] for k in bench.ORDER] == ["C2", "C1", "C3", "C4", "C5"]
+    W = bench.WORKLOADS["double_well"]
+    assert W["replicas"] == 1 << 20 and W["protocol_length"] == 10 and len(W["splittings"]) == 6
+    assert bench.steps_per_leg(W) == 9 and bench.steps_per_leg(bench.WORKLOADS["waterbox"]) == 200
+    fl = {k: bench.flops_per_step(s, W["f_force"]) for k, s in W["splittings"].items()}
+    assert fl == {"OVRVO": 34, "ORVRO": 34, "RVOVR": 27, "ROVOR": 34, "VRORV": 27, "VOROV": 34} and sum(fl.values()) == 190
+    assert bench.flops_per_step("O V R R V O", 3) == 18 + 4 + 4 + 3 and bench.flops_per_step("V R O O R V", 3) == 4 + 4 + 18 + 3
+    cfg = bench.workload_config("double_well", W, W["replicas"], W["protocol_length"])
+    assert "C2 double well" in cfg["workload"] and "model" not in cfg and cfg["replicas_per_gpu"] == 1 << 20
