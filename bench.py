@@ -588,20 +588,23 @@ def gpu_record(ctx, name, W, steps, warmup, n, plen, with_cpu, min_warm_s=0.0):
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             d2h = 0
-            ests = []
             # the step's input, the host-side equilibrium cache, is uploaded again every step (the simulators of a step share
             # their equilibrium simulator, as the reference's callers do, hence its device copy)
             eq.release_device_cache()
-            for sim in sims.values():  # the timed region ends with the call's results on the host (works, or the moment vector)
-                got, nbytes = call(sim, mode)
-                ests.append(got)
+            for sim in sims.values():  # the timed region ends with the call's results on the host (works, or the moment vector);
+                got, nbytes = call(sim, mode)  # they are dropped at once, so their pinned staging blocks are recycled
                 d2h += nbytes
+                del got
         ctx.barrier()
         secs = ctx.max_over_ranks(time.perf_counter() - t0)
         e2e[mode] = {"value": world * S * n_e2e * 2 * nsl * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "replicas_per_call": n_e2e}
-        if mode == "default":  # what a caller computes from the returned works, outside the timed region
-            estimates_e2e = [ib.evaluation.estimate_nonequilibrium_free_energy(wf, wr) for wf, wr in ests]
+        if mode == "default":  # what a caller computes from the returned works: one more pass, outside the timed region
+            estimates_e2e = []
+            for sim in sims.values():
+                (wf, wr), _ = call(sim, mode)
+                estimates_e2e.append(ib.evaluation.estimate_nonequilibrium_free_energy(wf, wr))
+                del wf, wr
 
     if rank != 0:
         return None
