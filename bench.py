@@ -117,10 +117,12 @@ def workload_config(name, W, n, plen):
 
 
 class ClockSampler:
-    """SM clock + clock-event reasons sampled DURING the timed region (NVML from a thread, every
-    ~0.5 ms; the nvidia-smi -lms loop of the profiling recipe cannot resolve a region this short)."""
+    """SM clock + clock-event reasons sampled DURING the timed region (NVML from a thread, back to back -- a query takes a
+    fraction of a millisecond and releases the GIL --; the nvidia-smi -lms loop of the profiling recipe cannot resolve a region of
+    a few milliseconds).  The interpreter's thread switch interval is shortened while the sampler lives, so that the main
+    thread's launch loop cannot starve it."""
 
-    def __init__(self, gpu_index=0, period_s=0.0005):
+    def __init__(self, gpu_index=0, period_s=0.0):
         import threading
         self.rows, self.marks, self._stop = [], [], threading.Event()
         self.ok = False
@@ -134,8 +136,13 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             return
         self.period = period_s
+        self._switch = sys.getswitchinterval()
+        sys.setswitchinterval(2e-4)
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
+        t_wait = time.perf_counter()  # the first queries after nvmlInit can take tens of milliseconds: let them pass
+        while len(self.rows) < 5 and time.perf_counter() - t_wait < 1.0:
+            time.sleep(0.002)
 
     def _run(self):
         nv = self.nv
@@ -157,8 +164,14 @@ class ClockSampler:
             return out
         self._stop.set()
         self.t.join(timeout=2)
+        sys.setswitchinterval(self._switch)
         lo, hi = (self.marks[0], self.marks[-1]) if len(self.marks) >= 2 else (0.0, 1e30)
         rows = [r for r in self.rows if lo <= r[0] <= hi]
+        if len(rows) < 2 and self.rows:  # a region shorter than two queries: the samples that bracket it
+            before = [r for r in self.rows if r[0] < lo][-1:]
+            after = [r for r in self.rows if r[0] > hi][:1]
+            rows = before + rows + after
+            out["bracketing_samples"] = True
         out["sm_max_mhz"] = self.max_mhz
         if rows:
             out["sm_mhz"] = float(np.median([r[1] for r in rows]))
