@@ -837,8 +837,7 @@ __global__ void __launch_bounds__(family_threads((int)sizeof...(CODES)), 1) toy_
     const double oc1 = B.P[S1].oc, oc2 = B.P[S2].oc;
     // normals of one block, already multiplied by the b sigma of each class
     struct Normals { double n1[4], n2[4]; };
-    auto generate = [&](uint64_t rid, uint32_t draw, bool second_pair, Normals& N) {
-        const lsi::Philox4 r = lsi::philox_block(P0.keys, rid, draw, LSI_TAG_O, 0u);
+    auto generate_from = [&](const lsi::Philox4& r, bool second_pair, Normals& N) {
         const PairCore a = pair_core<NOISE32>(FT, r.x, r.y);
         if (C1) pair_scaled<NOISE32>(a, oc1, N.n1[0], N.n1[1]);
         if (C2) pair_scaled<NOISE32>(a, oc2, N.n2[0], N.n2[1]);
@@ -847,6 +846,9 @@ __global__ void __launch_bounds__(family_threads((int)sizeof...(CODES)), 1) toy_
             if (C1) pair_scaled<NOISE32>(b, oc1, N.n1[2], N.n1[3]);
             if (C2) pair_scaled<NOISE32>(b, oc2, N.n2[2], N.n2[3]);
         }
+    };
+    auto generate = [&](uint64_t rid, uint32_t draw, bool second_pair, Normals& N) {
+        generate_from(lsi::philox_block(P0.keys, rid, draw, LSI_TAG_O, 0u), second_pair, N);
     };
 
     const int64_t n_chunks = (P0.n + kF3Threads - 1) / kF3Threads;
@@ -895,17 +897,23 @@ __global__ void __launch_bounds__(family_threads((int)sizeof...(CODES)), 1) toy_
                     }
                 }, slots);
             };
-            auto block_steps = [&](int b, const Normals& N) {
+            // `wn`: with LSI_TOY3_PIPE == 2 the Philox words of the NEXT block are computed inside the first basic block of this
+            // one (whichever branch runs at u = 0): ten dependent integer rounds that need no fp64 slot and no result of the
+            // dynamics, so they issue in the shadow of the block's fp64 instructions (four registers, not a second set of normals)
+            auto block_steps = [&](int b, const Normals& N, lsi::Philox4& wn) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const bool a2 = C2 && u < 2 && 2 * b + u < n_steps;
                     const bool a1 = C1 && 4 * b + u < n_steps;
                     if (a2 && a1) {  // one basic block: all programs' chains interleave
+                        if (LSI_TOY3_PIPE == 2 && u == 0) wn = lsi::philox_block(P0.keys, rid, leg_base | (uint32_t)(b + 1), LSI_TAG_O, 0u);
                         step_class(std::integral_constant<int, 2>{}, N, u);
                         step_class(std::integral_constant<int, 1>{}, N, u);
                     } else if (a2) {
+                        if (LSI_TOY3_PIPE == 2 && u == 0) wn = lsi::philox_block(P0.keys, rid, leg_base | (uint32_t)(b + 1), LSI_TAG_O, 0u);
                         step_class(std::integral_constant<int, 2>{}, N, u);
                     } else if (a1) {
+                        if (LSI_TOY3_PIPE == 2 && u == 0) wn = lsi::philox_block(P0.keys, rid, leg_base | (uint32_t)(b + 1), LSI_TAG_O, 0u);
                         step_class(std::integral_constant<int, 1>{}, N, u);
                     }
                 }
@@ -916,18 +924,24 @@ __global__ void __launch_bounds__(family_threads((int)sizeof...(CODES)), 1) toy_
             if (n_blk > 0) {
                 Normals cur;
                 generate(rid, leg_base, needs_second(0), cur);
-#if LSI_TOY3_PIPE
+                lsi::Philox4 wn = {0u, 0u, 0u, 0u};
+#if LSI_TOY3_PIPE == 1
                 for (int b = 0; b + 1 < n_blk; ++b) {
                     Normals nxt;
                     generate(rid, leg_base | (uint32_t)(b + 1), needs_second(b + 1), nxt);
-                    block_steps(b, cur);
+                    block_steps(b, cur, wn);
                     cur = nxt;
                 }
-                block_steps(n_blk - 1, cur);
+                block_steps(n_blk - 1, cur, wn);
+#elif LSI_TOY3_PIPE == 2
+                for (int b = 0; b < n_blk; ++b) {
+                    block_steps(b, cur, wn);
+                    if (b + 1 < n_blk) generate_from(wn, needs_second(b + 1), cur);
+                }
 #else
                 for (int b = 0; b < n_blk; ++b) {
                     if (b > 0) generate(rid, leg_base | (uint32_t)b, needs_second(b), cur);
-                    block_steps(b, cur);
+                    block_steps(b, cur, wn);
                 }
 #endif
             }
